@@ -1,0 +1,379 @@
+"""CPU oracle: the reference's model assembly (DeepModel.__build_model, deepmodel.py:259-317),
+net builders (deepnets.py:43-224, 401-427), loss (deepmodel.py:319-346) and Keras Adam, restated
+over a flat state dict keyed by the reference's layer / weight names.
+
+TEST INFRASTRUCTURE ONLY (see oracle/layers_ref.py header).  PARITY UNPINNED (TF/Keras absent).
+
+The state dict maps ``'<layer>/<weight>'`` -> torch CPU tensor, e.g.
+``emb_categorical_vars_all/embeddings_3``, ``bn_concat_emb_dense/gamma``, ``linear_logit/kernel``,
+``cin/f_0``, ``cin/exFM_out/kernel``, ``dnn_dense_1/kernel``, ``cross_layer/kernels_0``,
+``multihead_attention_1/dense_Q/kernel``, ``pnn_outer_product_layer/kernel``,
+``dense_logit_dnn_nets/kernel``, ``task_output/kernel``.  Non-trainable BN statistics use
+``.../moving_mean`` and ``.../moving_variance``.
+"""
+import math
+import numpy as np
+import torch
+
+from . import layers_ref as L
+
+SUPPORTED_NETS = ('linear', 'cin_nets', 'fm_nets', 'opnn_nets', 'ipnn_nets', 'pnn_nets', 'dnn_nets',
+                  'cross_nets', 'cross_dnn_nets', 'dcn_nets', 'autoint_nets')
+
+
+def _get(cfg, name, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    return getattr(cfg, name, default)
+
+
+# ---------------------------------------------------------------------------------------------
+# Keras initialisers
+# ---------------------------------------------------------------------------------------------
+def _fans(shape):
+    if len(shape) < 1:
+        return 1, 1
+    if len(shape) == 1:
+        return shape[0], shape[0]
+    if len(shape) == 2:
+        return shape[0], shape[1]
+    rf = int(np.prod(shape[:-2]))
+    return shape[-2] * rf, shape[-1] * rf
+
+
+def init_weight(rng, shape, kind):
+    shape = tuple(int(s) for s in shape)
+    fan_in, fan_out = _fans(shape)
+    if kind == 'uniform':
+        lim = 0.05
+    elif kind == 'glorot_uniform':
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+    elif kind == 'he_uniform':
+        lim = math.sqrt(6.0 / fan_in)
+    elif kind == 'zeros':
+        return torch.zeros(shape, dtype=torch.float32)
+    elif kind == 'ones':
+        return torch.ones(shape, dtype=torch.float32)
+    else:
+        raise ValueError(kind)
+    return torch.from_numpy(rng.uniform(-lim, lim, size=shape).astype(np.float32))
+
+
+def _bn_entries(name, width):
+    return [(f'{name}/gamma', (width,), 'ones'), (f'{name}/beta', (width,), 'zeros'),
+            (f'{name}/moving_mean', (width,), 'zeros'), (f'{name}/moving_variance', (width,), 'ones')]
+
+
+def _dnn_entries(width, params, cellname):
+    ents = []
+    hidden = params.get('hidden_units', ((128, 0, True), (64, 0, False)))
+    kinit = params.get('kernel_initializer', 'he_uniform')
+    for i, (units, _drop, use_bn) in enumerate(hidden, start=1):
+        ents.append((f'{cellname}_dense_{i}/kernel', (width, units), kinit))
+        if use_bn:
+            ents += _bn_entries(f'{cellname}_bn_{i}', units)
+        else:
+            ents.append((f'{cellname}_dense_{i}/bias', (units,), 'zeros'))
+        width = units
+    return ents, width
+
+
+def param_spec(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes=2):
+    """[(name, shape, initializer)] in build order + {net: output width} (deepmodel.py:259-317)."""
+    nets = list(_get(config, 'nets'))
+    f = len(vocab_sizes)
+    ents = []
+    for i, (v, d) in enumerate(zip(vocab_sizes, emb_dims)):
+        ents.append((f'emb_categorical_vars_all/embeddings_{i}', (v, d),
+                     _get(config, 'embeddings_initializer', 'uniform')))
+    sum_d = int(sum(emb_dims))
+    w = sum_d + n_cont
+    ents += _bn_entries('bn_concat_emb_dense', w)
+    widths = {}
+    d0 = emb_dims[0] if f else 0
+    for net in nets:
+        if net == 'linear':
+            ents.append(('linear_logit/kernel', (f + n_cont, 1), 'glorot_uniform'))
+            widths[net] = 1
+        elif net == 'fm_nets':
+            if f:
+                widths[net] = 1
+        elif net == 'cin_nets':
+            if not f:
+                continue
+            p = _get(config, 'cin_params')
+            sizes = tuple(p.get('cross_layer_size', (128, 128)))
+            fns = L.cin_field_nums(f, sizes, p.get('direct', False))
+            for k, size in enumerate(sizes):
+                if p.get('reduce_D', False):
+                    ents.append((f'cin/f0_{k}', (1, size, fns[0], d0), 'he_uniform'))
+                    ents.append((f'cin/f__{k}', (1, size, d0, fns[k]), 'he_uniform'))
+                else:
+                    ents.append((f'cin/f_{k}', (1, fns[k] * fns[0], size), 'he_uniform'))
+                if p.get('use_bias', False):
+                    ents.append((f'cin/bias{k}', (size,), 'zeros'))
+            pooled = L.cin_pooled_width(f, p)
+            if p.get('use_residual', False):
+                ents.append(('cin/exFM_out0/kernel', (pooled, sizes[-1]), 'he_uniform'))
+                ents.append(('cin/exFM_out0/bias', (sizes[-1],), 'zeros'))
+                ents.append(('cin/exFM_out/kernel', (pooled + sizes[-1], 1), 'glorot_uniform'))
+            else:
+                ents.append(('cin/exFM_out/kernel', (pooled, 1), 'glorot_uniform'))
+            ents.append(('cin/exFM_out/bias', (1,), 'zeros'))
+            widths[net] = 1
+        elif net in ('opnn_nets', 'ipnn_nets', 'pnn_nets'):
+            if f < 2:
+                continue
+            cell = net[:-5]
+            pairs = f * (f - 1) // 2
+            extra = 0
+            if net in ('ipnn_nets', 'pnn_nets'):
+                extra += pairs
+            if net in ('opnn_nets', 'pnn_nets'):
+                kt = _get(config, 'pnn_params').get('outer_product_kernel_type', 'mat')
+                shape = {'mat': (d0, pairs, d0), 'vec': (pairs, d0), 'num': (pairs, 1)}[kt]
+                lname = 'pnn_outer_product_layer' if net == 'pnn_nets' else 'outer_product_layer'
+                ents.append((f'{lname}/kernel', shape, 'glorot_uniform'))
+                extra += pairs
+            e, width = _dnn_entries(w + extra, _get(config, 'dnn_params'), cell)
+            ents += e
+            widths[net] = width
+        elif net == 'dnn_nets':
+            e, width = _dnn_entries(w, _get(config, 'dnn_params'), 'dnn')
+            ents += e
+            widths[net] = width
+        elif net in ('cross_nets', 'cross_dnn_nets', 'dcn_nets'):
+            lname = {'cross_nets': 'cross_layer', 'cross_dnn_nets': 'cross_dnn_layer',
+                     'dcn_nets': 'dcn_cross_layer'}[net]
+            n_layers = _get(config, 'cross_params').get('num_cross_layer', 2)
+            for i in range(n_layers):
+                ents.append((f'{lname}/kernels_{i}', (w, 1), 'glorot_uniform'))
+                ents.append((f'{lname}/bias_{i}', (w, 1), 'zeros'))
+            if net == 'cross_nets':
+                widths[net] = w
+            elif net == 'cross_dnn_nets':
+                e, width = _dnn_entries(w, _get(config, 'dnn_params'), 'cross_dnn')
+                ents += e
+                widths[net] = width
+            else:
+                e, width = _dnn_entries(w, _get(config, 'dnn_params'), 'dcn')
+                ents += e
+                widths[net] = w + width
+        elif net == 'autoint_nets':
+            if not f:
+                continue
+            p = _get(config, 'autoint_params')
+            for i in range(p['num_attention']):
+                lname = 'multihead_attention' if i == 0 else f'multihead_attention_{i}'
+                for proj in ('dense_Q', 'dense_K', 'dense_V', 'dense_residual'):
+                    ents.append((f'{lname}/{proj}/kernel', (d0, d0), 'he_uniform'))
+                    ents.append((f'{lname}/{proj}/bias', (d0,), 'zeros'))
+                ents += _bn_entries(f'{lname}/batch_normalize', d0)
+            widths[net] = f * d0
+        else:
+            raise NotImplementedError(f'oracle: net {net!r} is outside the hot path')
+    live = [n for n in nets if n in widths]
+    if len(live) > 1:
+        for n in live:
+            if widths[n] > 1:
+                ents.append((f'dense_logit_{n}/kernel', (widths[n], 1), 'glorot_uniform'))
+        head_in = 1 if _get(config, 'stacking_op', 'add') == 'add' else len(live)
+    elif len(live) == 1:
+        head_in = widths[live[0]]
+    else:
+        raise ValueError('Unexpected logit output.')
+    out_dim = 1 if task in ('binary', 'regression') else num_classes
+    ents.append(('task_output/kernel', (head_in, out_dim), 'glorot_uniform'))
+    if _get(config, 'output_use_bias', True):
+        ents.append(('task_output/bias', (out_dim,), 'zeros'))
+    return ents, widths
+
+
+def init_state(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes=2, seed=0):
+    rng = np.random.default_rng(seed)
+    ents, _ = param_spec(config, vocab_sizes, emb_dims, n_cont, task, num_classes)
+    return {name: init_weight(rng, shape, kind) for name, shape, kind in ents}
+
+
+def is_trainable(name):
+    return not (name.endswith('/moving_mean') or name.endswith('/moving_variance'))
+
+
+def _sub(state, prefix):
+    plen = len(prefix) + 1
+    return {k[plen:]: v for k, v in state.items() if k.startswith(prefix + '/')}
+
+
+# ---------------------------------------------------------------------------------------------
+# Forward (deepmodel.py:259-317 + deepnets.py builders)
+# ---------------------------------------------------------------------------------------------
+def forward(state, config, cat_idx, cont, n_fields, training, task='binary', return_parts=False):
+    """cat_idx: (B,F) integer/float tensor or None; cont: (B,C) float tensor or None.
+    Returns (output, new_bn_state[, parts])."""
+    nets = list(_get(config, 'nets'))
+    new_bn = {}
+    parts = {}
+    embeddings = []
+    if n_fields:
+        tables = [state[f'emb_categorical_vars_all/embeddings_{i}'] for i in range(n_fields)]
+        embeddings = L.embedding_lookup(tables, cat_idx)
+    dense_layer = cont
+    flat = L.flatten_embeddings(embeddings) if embeddings else None
+    if flat is not None and dense_layer is not None:
+        x = torch.cat([flat, dense_layer], dim=-1)
+    elif flat is not None:
+        x = flat
+    elif dense_layer is not None:
+        x = dense_layer
+    else:
+        raise ValueError('No input layer exists.')
+    ced, nm, nv = L.batch_norm(x, state['bn_concat_emb_dense/gamma'], state['bn_concat_emb_dense/beta'],
+                               state['bn_concat_emb_dense/moving_mean'],
+                               state['bn_concat_emb_dense/moving_variance'], training)
+    new_bn['bn_concat_emb_dense/moving_mean'] = nm
+    new_bn['bn_concat_emb_dense/moving_variance'] = nv
+    parts['concat_emb_dense'] = ced
+    bn_state = {k: v for k, v in state.items() if not is_trainable(k)}
+
+    def run_dnn(inp, cell):
+        y, ns = L.dnn(inp, _get(config, 'dnn_params'), state, bn_state, training, cellname=cell)
+        new_bn.update(ns)
+        return y
+
+    outs = {}
+    for net in nets:
+        if net == 'linear':
+            outs[net] = L.linear(embeddings, dense_layer, state['linear_logit/kernel'])
+        elif net == 'fm_nets':
+            cat = L.concat_embeddings(embeddings)
+            if cat is not None:
+                outs[net] = L.fm(cat)
+        elif net == 'cin_nets':
+            cat = L.concat_embeddings(embeddings)
+            if cat is not None:
+                outs[net] = L.cin(cat, _get(config, 'cin_params'), _sub(state, 'cin'))
+        elif net in ('opnn_nets', 'ipnn_nets', 'pnn_nets'):
+            if len(embeddings) < 2:
+                continue
+            feats = []
+            if net in ('ipnn_nets', 'pnn_nets'):
+                feats.append(L.inner_product(embeddings))
+            if net in ('opnn_nets', 'pnn_nets'):
+                lname = 'pnn_outer_product_layer' if net == 'pnn_nets' else 'outer_product_layer'
+                kt = _get(config, 'pnn_params').get('outer_product_kernel_type', 'mat')
+                feats.append(L.outer_product(embeddings, state[f'{lname}/kernel'], kt))
+            outs[net] = run_dnn(torch.cat(feats + [ced], dim=-1), net[:-5])
+        elif net == 'dnn_nets':
+            outs[net] = run_dnn(ced, 'dnn')
+        elif net in ('cross_nets', 'cross_dnn_nets', 'dcn_nets'):
+            lname = {'cross_nets': 'cross_layer', 'cross_dnn_nets': 'cross_dnn_layer',
+                     'dcn_nets': 'dcn_cross_layer'}[net]
+            n_layers = _get(config, 'cross_params').get('num_cross_layer', 2)
+            ks = [state[f'{lname}/kernels_{i}'] for i in range(n_layers)]
+            bs = [state[f'{lname}/bias_{i}'] for i in range(n_layers)]
+            c = L.cross(ced, ks, bs)
+            if net == 'cross_nets':
+                outs[net] = c
+            elif net == 'cross_dnn_nets':
+                outs[net] = run_dnn(c, 'cross_dnn')
+            else:
+                outs[net] = torch.cat([c, run_dnn(ced, 'dcn')], dim=-1)
+        elif net == 'autoint_nets':
+            cat = L.concat_embeddings(embeddings)
+            if cat is None:
+                continue
+            p = _get(config, 'autoint_params')
+            out = cat
+            for i in range(p['num_attention']):
+                lname = 'multihead_attention' if i == 0 else f'multihead_attention_{i}'
+                st = {'moving_mean': state[f'{lname}/batch_normalize/moving_mean'],
+                      'moving_variance': state[f'{lname}/batch_normalize/moving_variance']}
+                out, ns = L.multihead_attention(out, p, _sub(state, lname), st, training)
+                new_bn[f'{lname}/batch_normalize/moving_mean'] = ns['moving_mean']
+                new_bn[f'{lname}/batch_normalize/moving_variance'] = ns['moving_variance']
+            outs[net] = out.reshape(out.shape[0], -1)
+        else:
+            raise NotImplementedError(net)
+    parts['outs'] = outs
+    if len(outs) > 1:
+        logits = []
+        for name, out in outs.items():
+            if out.dim() > 2:
+                out = out.reshape(out.shape[0], -1)
+            if out.shape[-1] > 1:
+                out = out @ state[f'dense_logit_{name}/kernel']
+            logits.append(out)
+        if _get(config, 'stacking_op', 'add') == 'add':
+            x = sum(logits[1:], logits[0])
+        elif _get(config, 'stacking_op') == 'concat':
+            x = torch.cat(logits, dim=-1)
+        else:
+            raise ValueError(f"Unsupported stacking_op:{_get(config, 'stacking_op')}.")
+    elif len(outs) == 1:
+        x = list(outs.values())[0]
+        if x.dim() > 2:
+            x = x.reshape(x.shape[0], -1)
+    else:
+        raise ValueError(f'Unexpected logit output.{outs}')
+    parts['stack'] = x
+    z = x @ state['task_output/kernel']
+    if 'task_output/bias' in state:
+        z = z + state['task_output/bias']
+    parts['z'] = z
+    if task in ('binary', 'multilabel'):
+        y = torch.sigmoid(z)
+    elif task == 'regression':
+        y = z
+    elif task == 'multiclass':
+        y = torch.softmax(z, dim=-1)
+    else:
+        raise ValueError(f'Unknown task type:{task}')
+    if return_parts:
+        return y, new_bn, parts
+    return y, new_bn
+
+
+def loss_fn(task, y_true, y_pred):
+    if task in ('binary', 'multilabel'):
+        return L.binary_crossentropy(y_true, y_pred)
+    if task == 'regression':
+        return L.mean_squared_error(y_true, y_pred)
+    if task == 'multiclass':
+        return L.categorical_crossentropy(y_true, y_pred)
+    raise RuntimeError(f'unseen task "{task}"')
+
+
+class RefTrainer:
+    """One Keras-style train step at a time: forward (training=True) -> loss -> autograd ->
+    dense Adam on every trainable weight (embedding tables included, as Keras does)."""
+
+    def __init__(self, state, config, n_fields, task='binary', dtype=torch.float32):
+        self.state = {k: v.detach().clone().to(dtype) for k, v in state.items()}
+        self.config = config
+        self.n_fields = n_fields
+        self.task = task
+        self.step = 0
+        self.m = {k: torch.zeros_like(v) for k, v in self.state.items() if is_trainable(k)}
+        self.v = {k: torch.zeros_like(v) for k, v in self.state.items() if is_trainable(k)}
+
+    def loss_and_grads(self, cat_idx, cont, y):
+        params = {k: v.detach().clone().requires_grad_(is_trainable(k)) for k, v in self.state.items()}
+        out, new_bn = forward(params, self.config, cat_idx, cont, self.n_fields, True, self.task)
+        loss = loss_fn(self.task, y.to(out.dtype).reshape(out.shape[0], -1), out)
+        names = [k for k in params if is_trainable(k)]
+        grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
+        gd = {k: (g if g is not None else torch.zeros_like(params[k])) for k, g in zip(names, grads)}
+        return loss.detach(), gd, {k: v.detach() for k, v in new_bn.items()}, out.detach()
+
+    def train_step(self, cat_idx, cont, y):
+        loss, grads, new_bn, _ = self.loss_and_grads(cat_idx, cont, y)
+        self.step += 1
+        for k, g in grads.items():
+            L.adam_step(self.state[k], g, self.m[k], self.v[k], self.step)
+        self.state.update(new_bn)
+        return float(loss)
+
+    def predict(self, cat_idx, cont):
+        with torch.no_grad():
+            out, _ = forward(self.state, self.config, cat_idx, cont, self.n_fields, False, self.task)
+        return out
