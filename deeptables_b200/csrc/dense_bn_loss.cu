@@ -1,0 +1,475 @@
+// BatchNormalization, Dense, task losses and the dense Adam step.
+//   BN     : keras BatchNormalization(axis=-1)  (deepmodel.py:359, layers.py:152, deepnets.py:422)
+//   Dense  : keras Dense                        (deepnets.py:415-424, deepmodel.py:292,455)
+//   losses : sigmoid+BCE / MSE / softmax+CCE    (deepmodel.py:319-346,436-457)
+//   Adam   : keras.optimizers.Adam.update_step  (deepmodel.py:321-322)
+// The Dense GEMMs are plain fp32 library GEMMs (cuBLAS Sgemm); everything around them (bias,
+// activation, narrow logit layers, reductions) is hand-written.  All of it is HBM-bound streaming.
+#include "dtb_common.cuh"
+#include "dtb_cublas.cuh"
+
+namespace dtb {
+
+// ------------------------------------------------------------------------------------------
+// column statistics over X[rows, cols]: block = 32 columns x 8 row-lanes, fp64 accumulation
+// ------------------------------------------------------------------------------------------
+constexpr int kColTile = 32;
+constexpr int kRowLanes = 8;
+
+// MODE 0: ws[c] += sum x ; ws[cols+c] += sum x^2
+// MODE 1: ws[c] += sum dy ; ws[cols+c] += sum dy * xhat      (BN backward)
+// MODE 2: ws[c] += sum a[r,c]*b[r]  (b is a per-row vector, used by narrow Dense backward), cols only
+template <int MODE>
+__global__ void col_reduce_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                  const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                  double* __restrict__ ws, int rows, int cols, int rows_per_block) {
+  __shared__ double s0[kRowLanes][kColTile];
+  __shared__ double s1[kRowLanes][kColTile];
+  const int c = blockIdx.x * kColTile + threadIdx.x;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(rows, r_begin + rows_per_block);
+  double a0 = 0.0, a1 = 0.0;
+  if (c < cols) {
+    float mu = 0.f, inv = 0.f;
+    if (MODE == 1) {
+      mu = mean[c];
+      inv = rsqrtf(var[c] + eps);
+    }
+    for (int r = r_begin + threadIdx.y; r < r_end; r += kRowLanes) {
+      const float x = A[(int64_t)r * cols + c];
+      if (MODE == 0) {
+        a0 += (double)x;
+        a1 += (double)x * (double)x;
+      } else if (MODE == 1) {
+        const float dy = Bm[(int64_t)r * cols + c];
+        a0 += (double)dy;
+        a1 += (double)(dy * ((x - mu) * inv));
+      } else {
+        a0 += (double)(x * Bm[r]);
+      }
+    }
+  }
+  s0[threadIdx.y][threadIdx.x] = a0;
+  s1[threadIdx.y][threadIdx.x] = a1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    for (int k = 1; k < kRowLanes; ++k) {
+      a0 += s0[k][threadIdx.x];
+      a1 += s1[k][threadIdx.x];
+    }
+    atomicAdd(ws + c, a0);
+    if (MODE != 2) atomicAdd(ws + cols + c, a1);
+  }
+}
+
+static void col_reduce_grid(int rows, int cols, dim3& grid, dim3& block, int& rows_per_block) {
+  block = dim3(kColTile, kRowLanes);
+  const int col_blocks = ceil_div(cols, kColTile);
+  int row_blocks = ceil_div((int64_t)sm_count() * 8, col_blocks);
+  const int max_row_blocks = ceil_div(rows, kRowLanes * 4);
+  if (row_blocks > max_row_blocks) row_blocks = max_row_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  rows_per_block = ceil_div(rows, row_blocks);
+  row_blocks = ceil_div(rows, rows_per_block);
+  grid = dim3(col_blocks, row_blocks);
+}
+
+__global__ void bn_finalize_stats(const double* __restrict__ ws, float* __restrict__ moving_mean,
+                                  float* __restrict__ moving_var, float* __restrict__ save_mean,
+                                  float* __restrict__ save_var, int rows, int cols, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const double mean = ws[c] / rows;
+  double var = ws[cols + c] / rows - mean * mean;   // biased variance (tf.nn.moments)
+  if (var < 0.0) var = 0.0;
+  save_mean[c] = (float)mean;
+  save_var[c] = (float)var;
+  moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+  moving_var[c] = moving_var[c] * momentum + (float)var * (1.f - momentum);
+}
+
+__global__ void bn_apply_kernel(const float* __restrict__ X, float* __restrict__ Y,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                int64_t total, int cols) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    Y[i] = (X[i] - mean[c]) * rsqrtf(var[c] + eps) * gamma[c] + beta[c];
+  }
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                    float* __restrict__ dX, const float* __restrict__ gamma,
+                                    const float* __restrict__ mean, const float* __restrict__ var,
+                                    const double* __restrict__ ws, float eps, int64_t total, int rows,
+                                    int cols) {
+  const float inv_n = 1.f / (float)rows;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cols);
+    const float inv = rsqrtf(var[c] + eps);
+    const float xhat = (X[i] - mean[c]) * inv;
+    const float dbeta = (float)ws[c], dgamma = (float)ws[cols + c];
+    dX[i] = gamma[c] * inv * (dY[i] - dbeta * inv_n - xhat * dgamma * inv_n);
+  }
+}
+
+__global__ void bn_bwd_commit_params(const double* __restrict__ ws, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  dbeta[c] += (float)ws[c];
+  dgamma[c] += (float)ws[cols + c];
+}
+
+static int ew_grid(int64_t total) {
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense epilogues and narrow (out_dim <= 8) logit layers
+// ------------------------------------------------------------------------------------------
+__global__ void bias_act_kernel(float* __restrict__ Y, const float* __restrict__ bias, int64_t total,
+                                int out_dim, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v = Y[i];
+    if (bias) v += bias[i % out_dim];
+    if (act == DTB_ACT_RELU) v = fmaxf(v, 0.f);
+    Y[i] = v;
+  }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ Y, float* __restrict__ dY, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (!(Y[i] > 0.f)) dY[i] = 0.f;
+}
+
+constexpr int kNarrow = 8;
+
+// warp per row: y[r,o] = act(sum_k x[r,k] w[k,o] + b[o]),  out_dim <= kNarrow
+__global__ void dense_narrow_fwd(const float* __restrict__ X, const float* __restrict__ W,
+                                 const float* __restrict__ bias, float* __restrict__ Y, int rows, int in_dim,
+                                 int out_dim, int act) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += n_warps) {
+    float acc[kNarrow];
+#pragma unroll
+    for (int o = 0; o < kNarrow; ++o) acc[o] = 0.f;
+    for (int k = lane; k < in_dim; k += 32) {
+      const float x = X[(int64_t)r * in_dim + k];
+#pragma unroll
+      for (int o = 0; o < kNarrow; ++o)
+        if (o < out_dim) acc[o] += x * __ldg(W + (int64_t)k * out_dim + o);
+    }
+#pragma unroll
+    for (int o = 0; o < kNarrow; ++o) {
+      if (o >= out_dim) break;
+      float v = warp_sum(acc[o]);
+      if (lane == 0) {
+        if (bias) v += bias[o];
+        if (act == DTB_ACT_RELU) v = fmaxf(v, 0.f);
+        Y[(int64_t)r * out_dim + o] = v;
+      }
+    }
+  }
+}
+
+// dX[r,k] = sum_o dZ[r,o] W[k,o]
+__global__ void dense_narrow_bwd_dx(const float* __restrict__ dZ, const float* __restrict__ W,
+                                    float* __restrict__ dX, int64_t total, int in_dim, int out_dim) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / in_dim;
+    const int k = (int)(i - r * in_dim);
+    float s = 0.f;
+    for (int o = 0; o < out_dim; ++o) s += dZ[r * out_dim + o] * __ldg(W + (int64_t)k * out_dim + o);
+    dX[i] = s;
+  }
+}
+
+// dW[k,o] += sum_r X[r,k] dZ[r,o]  for one o (blockIdx.z); same tiling as col_reduce (MODE 2 shape)
+__global__ void dense_narrow_bwd_dw(const float* __restrict__ X, const float* __restrict__ dZ,
+                                    float* __restrict__ dW, int rows, int in_dim, int out_dim,
+                                    int rows_per_block) {
+  __shared__ float s0[kRowLanes][kColTile];
+  const int o = blockIdx.z;
+  const int k = blockIdx.x * kColTile + threadIdx.x;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(rows, r_begin + rows_per_block);
+  float a = 0.f;
+  if (k < in_dim)
+    for (int r = r_begin + threadIdx.y; r < r_end; r += kRowLanes)
+      a += X[(int64_t)r * in_dim + k] * dZ[(int64_t)r * out_dim + o];
+  s0[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && k < in_dim) {
+    for (int j = 1; j < kRowLanes; ++j) a += s0[j][threadIdx.x];
+    atomicAdd(dW + (int64_t)k * out_dim + o, a);
+  }
+}
+
+// dbias[o] += sum_r dZ[r,o]   (any out_dim)
+__global__ void col_sum_float_kernel(const float* __restrict__ A, float* __restrict__ out, int rows,
+                                     int cols, int rows_per_block) {
+  __shared__ float s0[kRowLanes][kColTile];
+  const int c = blockIdx.x * kColTile + threadIdx.x;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(rows, r_begin + rows_per_block);
+  float a = 0.f;
+  if (c < cols)
+    for (int r = r_begin + threadIdx.y; r < r_end; r += kRowLanes) a += A[(int64_t)r * cols + c];
+  s0[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    for (int j = 1; j < kRowLanes; ++j) a += s0[j][threadIdx.x];
+    atomicAdd(out + c, a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// losses
+// ------------------------------------------------------------------------------------------
+__global__ void loss_kernel(const float* __restrict__ z, const float* __restrict__ y,
+                            const float* __restrict__ sw, float* __restrict__ prob, float* __restrict__ dz,
+                            double* __restrict__ loss_sum, int rows, int cols, int task) {
+  const float eps = 1e-7f;
+  double local = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float w = sw ? sw[r] : 1.f;
+    const float* zr = z + (int64_t)r * cols;
+    const float* yr = y + (int64_t)r * cols;
+    float* pr = prob + (int64_t)r * cols;
+    float* dr = dz ? dz + (int64_t)r * cols : nullptr;
+    float row_loss = 0.f;
+    if (task == 0) {
+      const float scale = w / ((float)rows * (float)cols);
+      for (int c = 0; c < cols; ++c) {
+        const float p = 1.f / (1.f + expf(-zr[c]));
+        pr[c] = p;
+        const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+        row_loss -= yr[c] * logf(pc) + (1.f - yr[c]) * logf(1.f - pc);
+        if (dr) dr[c] = (p >= eps && p <= 1.f - eps) ? (p - yr[c]) * scale : 0.f;
+      }
+      row_loss /= (float)cols;
+    } else if (task == 1) {
+      const float scale = 2.f * w / ((float)rows * (float)cols);
+      for (int c = 0; c < cols; ++c) {
+        pr[c] = zr[c];
+        const float d = zr[c] - yr[c];
+        row_loss += d * d;
+        if (dr) dr[c] = d * scale;
+      }
+      row_loss /= (float)cols;
+    } else {
+      float mx = -INFINITY;
+      for (int c = 0; c < cols; ++c) mx = fmaxf(mx, zr[c]);
+      float den = 0.f;
+      for (int c = 0; c < cols; ++c) den += expf(zr[c] - mx);
+      const float scale = w / (float)rows;
+      // keras categorical_crossentropy on probabilities: renormalise (no-op after softmax), clip, -sum y log p
+      float gdot = 0.f;   // sum_c y_c * [p_c unclipped]  -- softmax Jacobian contraction
+      for (int c = 0; c < cols; ++c) {
+        const float p = expf(zr[c] - mx) / den;
+        pr[c] = p;
+        const float pc = fminf(fmaxf(p, eps), 1.f - eps);
+        row_loss -= yr[c] * logf(pc);
+        if (p >= eps && p <= 1.f - eps) gdot += yr[c];
+      }
+      if (dr)
+        for (int c = 0; c < cols; ++c) {
+          const float p = pr[c];
+          const float direct = (p >= eps && p <= 1.f - eps) ? yr[c] : 0.f;
+          dr[c] = (p * gdot - direct) * scale;
+        }
+    }
+    local += (double)(row_loss * w);
+  }
+  local = warp_sum(local);
+  if (loss_sum && (threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(loss_sum, local);
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (dense)
+// ------------------------------------------------------------------------------------------
+__global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                  float* __restrict__ g, int64_t n, float alpha, float b1, float b2,
+                                  float eps, int zero_grad) {
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], alpha, omb1, omb2, eps);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+extern "C" {
+
+int dtb_batchnorm_train_fwd(const float* X, float* Y, const float* gamma, const float* beta,
+                            float* moving_mean, float* moving_var, float* save_mean, float* save_var,
+                            double* workspace, int rows, int cols, float eps, float momentum, void* stream) {
+  DTB_CHECK_ARG(X && Y && gamma && beta && moving_mean && moving_var && save_mean && save_var && workspace,
+                "NULL argument");
+  DTB_CHECK_ARG(rows > 0 && cols > 0, "rows/cols must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  DTB_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
+  dim3 grid, block;
+  int rpb;
+  col_reduce_grid(rows, cols, grid, block, rpb);
+  col_reduce_kernel<0><<<grid, block, 0, st>>>(X, nullptr, nullptr, nullptr, 0.f, workspace, rows, cols, rpb);
+  DTB_LAUNCH_OK();
+  bn_finalize_stats<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, moving_mean, moving_var, save_mean,
+                                                        save_var, rows, cols, momentum);
+  DTB_LAUNCH_OK();
+  const int64_t total = (int64_t)rows * cols;
+  bn_apply_kernel<<<ew_grid(total), 256, 0, st>>>(X, Y, gamma, beta, save_mean, save_var, eps, total, cols);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_batchnorm_infer_fwd(const float* X, float* Y, const float* gamma, const float* beta,
+                            const float* moving_mean, const float* moving_var, int rows, int cols, float eps,
+                            void* stream) {
+  DTB_CHECK_ARG(X && Y && gamma && beta && moving_mean && moving_var, "NULL argument");
+  DTB_CHECK_ARG(rows >= 0 && cols > 0, "bad shape");
+  const int64_t total = (int64_t)rows * cols;
+  if (total == 0) return DTB_OK;
+  bn_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(X, Y, gamma, beta, moving_mean,
+                                                                    moving_var, eps, total, cols);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_batchnorm_bwd(const float* X, const float* dY, float* dX, const float* gamma, const float* save_mean,
+                      const float* save_var, float* dgamma, float* dbeta, double* workspace, int rows,
+                      int cols, float eps, void* stream) {
+  DTB_CHECK_ARG(X && dY && dX && gamma && save_mean && save_var && dgamma && dbeta && workspace,
+                "NULL argument");
+  DTB_CHECK_ARG(rows > 0 && cols > 0, "rows/cols must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  DTB_CUDA_OK(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * cols, st));
+  dim3 grid, block;
+  int rpb;
+  col_reduce_grid(rows, cols, grid, block, rpb);
+  col_reduce_kernel<1><<<grid, block, 0, st>>>(X, dY, save_mean, save_var, eps, workspace, rows, cols, rpb);
+  DTB_LAUNCH_OK();
+  const int64_t total = (int64_t)rows * cols;
+  bn_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(X, dY, dX, gamma, save_mean, save_var, workspace, eps,
+                                                      total, rows, cols);
+  DTB_LAUNCH_OK();
+  bn_bwd_commit_params<<<ceil_div(cols, 128), 128, 0, st>>>(workspace, dgamma, dbeta, cols);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, int rows, int in_dim,
+                  int out_dim, int act, void* stream) {
+  DTB_CHECK_ARG(X && W && Y, "NULL argument");
+  DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
+  DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU, "unsupported activation");
+  if (rows == 0) return DTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dim <= kNarrow) {
+    int blocks = ceil_div(rows, 8);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    dense_narrow_fwd<<<blocks, 256, 0, st>>>(X, W, bias, Y, rows, in_dim, out_dim, act);
+    DTB_LAUNCH_OK();
+    return DTB_OK;
+  }
+  cublasHandle_t h = cublas_handle(st);
+  if (!h) {
+    set_error("dtb_dense_fwd: cuBLAS handle unavailable");
+    return DTB_ERR_CUBLAS;
+  }
+  DTB_CUBLAS_OK(gemm_nn(h, rows, out_dim, in_dim, X, in_dim, W, out_dim, Y, out_dim, 0.f));
+  if (bias || act != DTB_ACT_NONE) {
+    const int64_t total = (int64_t)rows * out_dim;
+    bias_act_kernel<<<ew_grid(total), 256, 0, st>>>(Y, bias, total, out_dim, act);
+    DTB_LAUNCH_OK();
+  }
+  return DTB_OK;
+}
+
+int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, float* dX, float* dW,
+                  float* dbias, int rows, int in_dim, int out_dim, int act, void* stream) {
+  DTB_CHECK_ARG(X && W && dY && dW, "NULL argument");
+  DTB_CHECK_ARG(act == DTB_ACT_NONE || (act == DTB_ACT_RELU && Y), "relu backward needs Y");
+  DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
+  if (rows == 0) return DTB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total_out = (int64_t)rows * out_dim;
+  if (act == DTB_ACT_RELU) {
+    act_bwd_kernel<<<ew_grid(total_out), 256, 0, st>>>(Y, dY, total_out);
+    DTB_LAUNCH_OK();
+  }
+  dim3 grid, block;
+  int rpb;
+  if (dbias) {
+    col_reduce_grid(rows, out_dim, grid, block, rpb);
+    col_sum_float_kernel<<<grid, block, 0, st>>>(dY, dbias, rows, out_dim, rpb);
+    DTB_LAUNCH_OK();
+  }
+  if (out_dim <= kNarrow) {
+    col_reduce_grid(rows, in_dim, grid, block, rpb);
+    grid.z = out_dim;
+    dense_narrow_bwd_dw<<<grid, block, 0, st>>>(X, dY, dW, rows, in_dim, out_dim, rpb);
+    DTB_LAUNCH_OK();
+    if (dX) {
+      const int64_t total_in = (int64_t)rows * in_dim;
+      dense_narrow_bwd_dx<<<ew_grid(total_in), 256, 0, st>>>(dY, W, dX, total_in, in_dim, out_dim);
+      DTB_LAUNCH_OK();
+    }
+    return DTB_OK;
+  }
+  cublasHandle_t h = cublas_handle(st);
+  if (!h) {
+    set_error("dtb_dense_bwd: cuBLAS handle unavailable");
+    return DTB_ERR_CUBLAS;
+  }
+  // dW[in,out] += X^T dZ ; dX[rows,in] = dZ W^T
+  DTB_CUBLAS_OK(gemm_tn(h, in_dim, out_dim, rows, X, in_dim, dY, out_dim, dW, out_dim, 1.f));
+  if (dX) DTB_CUBLAS_OK(gemm_nt(h, rows, in_dim, out_dim, dY, out_dim, W, out_dim, dX, in_dim, 0.f));
+  return DTB_OK;
+}
+
+int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_weight, float* prob, float* dz,
+                     double* loss_sum, int rows, int cols, int task, void* stream) {
+  DTB_CHECK_ARG(z && y_true && prob, "NULL argument");
+  DTB_CHECK_ARG(rows >= 0 && cols > 0 && task >= 0 && task <= 2, "bad shape/task");
+  if (rows == 0) return DTB_OK;
+  int blocks = ceil_div(rows, 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, y_true, sample_weight, prob, dz, loss_sum, rows,
+                                                        cols, task);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, float beta1, float beta2,
+                   float eps, int zero_grad, void* stream) {
+  DTB_CHECK_ARG(p && m && v && g, "NULL argument");
+  if (n <= 0) return DTB_OK;
+  adam_dense_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, alpha, beta1, beta2, eps,
+                                                                  zero_grad);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+}  // extern "C"

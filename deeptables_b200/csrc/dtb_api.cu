@@ -1,0 +1,71 @@
+// Library-level entry points of the C ABI: version, error string, device query, cuBLAS context.
+#include "dtb_common.cuh"
+#include "dtb_cublas.cuh"
+#include <mutex>
+#include <atomic>
+#include <cstring>
+
+namespace dtb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// One cuBLAS handle per device, created on first use; immutable afterwards (the only mutable
+// global of the library, guarded by a mutex as INTEGRATION.md states).
+static std::mutex g_cublas_mu;
+static cublasHandle_t g_cublas[64] = {nullptr};
+
+cublasHandle_t cublas_handle(cudaStream_t stream) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_cublas_mu);
+  if (!g_cublas[dev]) {
+    cublasHandle_t h = nullptr;
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
+    cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);  // Sgemm stays true fp32 (no TF32): fp32 parity
+    g_cublas[dev] = h;
+  }
+  if (cublasSetStream(g_cublas[dev], stream) != CUBLAS_STATUS_SUCCESS) return nullptr;
+  return g_cublas[dev];
+}
+
+}  // namespace dtb
+
+extern "C" {
+
+int dtb_version(void) { return 100; }
+
+long long dtb_launch_count(void) { return dtb::g_launches.load(); }
+
+const char* dtb_last_error(void) { return dtb::g_err; }
+
+int dtb_device_sm_count(int* out_host) {
+  DTB_CHECK_ARG(out_host != nullptr, "out_host is NULL");
+  int dev = 0;
+  DTB_CUDA_OK(cudaGetDevice(&dev));
+  DTB_CUDA_OK(cudaDeviceGetAttribute(out_host, cudaDevAttrMultiProcessorCount, dev));
+  return DTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+/*
+ * deeptables_b200 -- C ABI of the B200-native feature-interaction engine.
+ *
+ * The reference (DataCanvasIO/DeepTables) has no native boundary at all: every op below is, in
+ * the reference, a chain of TensorFlow/Keras ops inside a Keras layer (file:line cited per
+ * entry point, relative to /root/reference).  This header is therefore the boundary a
+ * maintainer would bind (ctypes stub shown in INTEGRATION.md) to replace those layers' `call`
+ * bodies.  Conventions:
+ *
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns every
+ *    buffer; the library never allocates output storage (cuBLAS owns a private workspace);
+ *  - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued asynchronously on it;
+ *  - return value: 0 = OK, negative = error (DTB_ERR_*); `dtb_last_error()` gives the text;
+ *    no C++ exception crosses this boundary;
+ *  - categorical ids: `idx` is int32 [B, F] row-major; the F tables live in ONE buffer
+ *    `table` [sum_f V_f, D] (row-major, uniform D) with `row_offsets` int64 [F+1] the prefix sum
+ *    of the vocabulary sizes (device memory).  Row r of field f is table[(row_offsets[f]+r)*D].
+ *    An id outside [0, V_f) sets bit f&31 of *status (if status != NULL) and reads as zeros
+ *    (TF-GPU behaviour; TF-CPU raises -- the host checks `status`, layers.py:893-898);
+ *  - embedding gradients are scatter-ADDED into `grad_table` (same shape as `table`), which the
+ *    caller keeps zeroed between steps (the row-wise Adam kernel re-zeroes rows it consumes);
+ *  - fp32 everywhere unless stated; "rows" are batch rows.
+ */
+#ifndef DEEPTABLES_B200_H_
+#define DEEPTABLES_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTB_OK 0
+#define DTB_ERR_INVALID_ARG (-1)
+#define DTB_ERR_UNSUPPORTED (-2)
+#define DTB_ERR_CUDA (-3)
+#define DTB_ERR_CUBLAS (-4)
+
+/* activation codes (keras Activation names the hot path uses) */
+#define DTB_ACT_NONE 0
+#define DTB_ACT_RELU 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dtb_version(void);
+const char* dtb_last_error(void);
+int dtb_device_sm_count(int* out_host);
+/* number of hand-written kernels this process has launched so far (cuBLAS GEMMs not counted) */
+long long dtb_launch_count(void);
+
+/* ---- MultiColumnEmbedding (layers.py:889-904) ------------------------------------------- */
+/* out[B,F,D] = table rows; the materialising form used by custom nets / tests. */
+int dtb_embedding_gather(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                         float* out, int B, int F, int D, int* status, void* stream);
+/* grad_table[row] += d_out[b,f,:]  (gradient of embedding_lookup). */
+int dtb_embedding_scatter_add(const int32_t* idx, const int64_t* row_offsets, const float* d_out,
+                              float* grad_table, int B, int F, int D, void* stream);
+
+/* ---- linear (deepnets.py:43-66) + FM (layers.py:53-62), gather fused -------------------- */
+/* out_lin[b] = sum_f w_lin[f]*sum_d e[b,f,d] + sum_c w_lin[F+c]*dense[b,c]   (NULL: skipped)
+ * out_fm[b]  = 0.5*sum_d[(sum_f e)^2 - sum_f e^2]                             (NULL: skipped)
+ * dense may be NULL iff C == 0; idx/table may be NULL iff F == 0. */
+int dtb_fm_linear_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                      const float* dense, const float* w_lin, float* out_lin, float* out_fm,
+                      int B, int F, int D, int C, int* status, void* stream);
+/* g_lin/g_fm: dLoss/d out_lin, dLoss/d out_fm [B] (NULL: that branch absent).
+ * grad_table += dE ; grad_wlin[F+C] += dW (both accumulate). */
+int dtb_fm_linear_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                      const float* dense, const float* w_lin, const float* g_lin, const float* g_fm,
+                      float* grad_table, float* grad_wlin, int B, int F, int D, int C, void* stream);
+
+/* ---- flatten_embeddings + concat_embedding_dense (deepmodel.py:269-278,348-357) --------- */
+/* X[b, :] = [e[b,0,:], ..., e[b,F-1,:], dense[b,:]]   width W = F*D + C. */
+int dtb_concat_emb_dense_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                             const float* dense, float* X, int B, int F, int D, int C, int* status,
+                             void* stream);
+/* grad_table += dX[:, :F*D] scattered by idx (the dense columns are inputs: no gradient). */
+int dtb_concat_emb_dense_bwd(const int32_t* idx, const int64_t* row_offsets, const float* dX,
+                             float* grad_table, int B, int F, int D, int C, void* stream);
+
+/* ---- BatchNormalization(axis=-1) (deepmodel.py:359; layers.py:152; deepnets.py:422) ------ */
+/* Training forward over X[rows, cols]: batch mean / biased variance (two-pass, fp64 accumulate),
+ * Y = gamma*(X-mean)*rsqrt(var+eps)+beta, save_mean/save_var [cols] written for backward, and
+ * moving = moving*momentum + batch*(1-momentum).  Y may alias X. */
+int dtb_batchnorm_train_fwd(const float* X, float* Y, const float* gamma, const float* beta,
+                            float* moving_mean, float* moving_var, float* save_mean, float* save_var,
+                            double* workspace /* [2*cols] */, int rows, int cols, float eps,
+                            float momentum, void* stream);
+/* Inference forward with the moving statistics. */
+int dtb_batchnorm_infer_fwd(const float* X, float* Y, const float* gamma, const float* beta,
+                            const float* moving_mean, const float* moving_var, int rows, int cols,
+                            float eps, void* stream);
+/* Backward of the training forward.  dX may alias dY.  dgamma/dbeta [cols] accumulate. */
+int dtb_batchnorm_bwd(const float* X, const float* dY, float* dX, const float* gamma,
+                      const float* save_mean, const float* save_var, float* dgamma, float* dbeta,
+                      double* workspace /* [2*cols] */, int rows, int cols, float eps, void* stream);
+
+/* ---- Dense (keras Dense used by deepnets.dnn 415-424, stacking 292, task_output 455) ---- */
+/* Y[rows,out] = act(X[rows,in] @ W[in,out] + bias).  bias may be NULL. */
+int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, int rows, int in_dim,
+                  int out_dim, int act, void* stream);
+/* dY holds dLoss/dY on entry and is overwritten with dLoss/d(pre-activation).  dX may be NULL.
+ * dW[in,out] and dbias[out] accumulate (dbias may be NULL). */
+int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, float* dX, float* dW,
+                  float* dbias, int rows, int in_dim, int out_dim, int act, void* stream);
+
+/* ---- losses on the task_output pre-activation (deepmodel.py:319-346, 436-457) ------------ */
+/* task: 0 binary/multilabel (sigmoid + BCE, probabilities clipped to [1e-7,1-1e-7] as keras),
+ *       1 regression (identity + MSE), 2 multiclass (softmax + CCE, y one-hot).
+ * prob[rows,cols] always written; if dz != NULL: dz = dLoss/dz with Loss = mean over rows (and
+ * over cols for task 0/1) of the per-sample loss times sample_weight (NULL = 1).
+ * loss_sum (double, device, may be NULL) += sum of per-row losses (un-normalised). */
+int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_weight, float* prob,
+                     float* dz, double* loss_sum, int rows, int cols, int task, void* stream);
+
+/* ---- keras Adam (deepmodel.py:321-322), dense semantics ---------------------------------- */
+/* m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= m*alpha/(sqrt(v)+eps), alpha computed by caller
+ * as lr*sqrt(1-b2^t)/(1-b1^t).  If zero_grad != 0, g is zeroed after use. */
+int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, float beta1,
+                   float beta2, float eps, int zero_grad, void* stream);
+
+/* Exact-lazy row-wise Adam for embedding tables (same arithmetic as dtb_adam_dense applied to
+ * every row every step, but rows whose gradient is zero are caught up only when next touched).
+ * last_step[row] = last optimiser step already applied to that row.  alpha_table[s] (device,
+ * s = 1..) = alpha of step s.
+ *   catchup: for every (b,f): apply the zero-gradient steps last_step+1 .. upto to that row once.
+ *   apply  : for every (b,f): apply step `step` with the accumulated grad_table row once, zero
+ *            the grad row, set last_step = step. */
+int dtb_adam_rows_catchup(const int32_t* idx, const int64_t* row_offsets, float* table, float* m,
+                          float* v, int32_t* last_step, const float* alpha_table, int upto,
+                          float beta1, float beta2, float eps, int B, int F, int D, void* stream);
+int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* table, float* m,
+                        float* v, float* grad_table, int32_t* last_step, const float* alpha_table,
+                        int step, float beta1, float beta2, float eps, int B, int F, int D,
+                        void* stream);
+/* Bring every row of the table up to date (before save / export / dense evaluation). */
+int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step,
+                        const float* alpha_table, int upto, float beta1, float beta2, float eps,
+                        int64_t n_rows, int D, void* stream);
+
+/* ---- CIN (layers.py:638-734), gather fused ------------------------------------------------ */
+/* Shapes: F0 = F fields, D, n_layers layer sizes L[k] (host array), direct flag; H[0]=F,
+ * H[k+1] = direct ? L[k] : L[k]/2 (all L[k]); K[k] = F*H[k].
+ * weights: concatenation of the n_layers filters, filter k is [K[k], L[k]] row-major (the
+ * reference's f_k[0]); bias: concatenation of [L[k]] or NULL.  act in {NONE, RELU}.
+ * pooled[B, P] with P = direct ? sum L : sum_{k<last} L[k]/2 + L[last]  (layers.py:725-726; the
+ * final Dense(1) / residual MLP is a dtb_dense_* call).
+ * saved (training only, may be NULL for inference): workspace of dtb_cin_saved_bytes() holding
+ * the activations backward needs. */
+size_t dtb_cin_saved_bytes(int B, int F, int D, const int* layer_sizes_host, int n_layers, int direct);
+size_t dtb_cin_workspace_bytes(int B, int F, int D, const int* layer_sizes_host, int n_layers,
+                               int direct, int training);
+int dtb_cin_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* weights, const float* bias, float* pooled, void* saved,
+                void* workspace, size_t workspace_bytes, int B, int F, int D,
+                const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
+                int* status, void* stream);
+/* d_pooled[B,P] -> grad_table += dE, d_weights/d_bias accumulate. */
+int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* weights, const float* d_pooled, const void* saved, float* grad_table,
+                float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int F,
+                int D, const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
+                void* stream);
+/* precision: 0 = auto (tensor-core bf16x3 split when the shape is supported, else fp32 SIMT),
+ *            1 = force fp32 SIMT/cuBLAS formulation, 2 = tensor-core bf16x3, 3 = tensor-core bf16x1. */
+#define DTB_CIN_AUTO 0
+#define DTB_CIN_FP32 1
+#define DTB_CIN_TC_BF16X3 2
+#define DTB_CIN_TC_BF16X1 3
+int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct);
+
+/* ---- Cross (layers.py:417-436) on a dense [B,W] input ------------------------------------- */
+/* x_{l+1} = x0*(x_l . w_l) + x_l + b_l ; kernels/biases [n_layers, W]; Y [B,W].
+ * xw_saved [B, n_layers] keeps the per-layer scalars x_l.w_l for backward. */
+int dtb_cross_fwd(const float* X, const float* kernels, const float* biases, float* Y,
+                  float* xw_saved, int B, int W, int n_layers, void* stream);
+int dtb_cross_bwd(const float* X, const float* kernels, const float* biases, const float* xw_saved,
+                  const float* dY, float* dX, float* d_kernels, float* d_biases, int B, int W,
+                  int n_layers, void* stream);
+
+/* ---- InnerProduct / OuterProduct (layers.py:473-487, 541-581), gather fused --------------- */
+/* ip[B,P] (NULL: skipped), op[B,P] (NULL: skipped); P = F(F-1)/2 pairs (i<j) row-major.
+ * kernel_type 0 mat [D,P,D], 1 vec [P,D], 2 num [P,1]. */
+int dtb_pnn_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* op_kernel, float* ip, float* op, int B, int F, int D, int kernel_type,
+                int* status, void* stream);
+int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* op_kernel, const float* d_ip, const float* d_op, float* grad_table,
+                float* d_op_kernel, int B, int F, int D, int kernel_type, void* stream);
+
+/* ---- MultiheadAttention interacting layer (layers.py:115-150), pre-BatchNorm --------------- */
+/* X[B,F,D] -> Y[B,F,D] = relu(softmax(QK^T/sqrt(dh)) V + residual), Q/K/V/res = relu(XW+b).
+ * Wqkvr: [4, D, D] (Q,K,V,residual kernels, each [in,out]); bqkvr: [4, D]. */
+int dtb_attention_fwd(const float* X, const float* Wqkvr, const float* bqkvr, float* Y, int B, int F,
+                      int D, int heads, int use_residual, void* stream);
+int dtb_attention_bwd(const float* X, const float* Wqkvr, const float* bqkvr, const float* dY,
+                      float* dX, float* dWqkvr, float* dbqkvr, int B, int F, int D, int heads,
+                      int use_residual, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPTABLES_B200_H_ */

@@ -1,0 +1,113 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol; host-side logic
+(config, registry, column metadata, preprocessor) behaves like the reference's."""
+import inspect
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+
+def test_library_exports_every_declared_symbol():
+    from deeptables_b200 import _native
+    declared = _native.declared_symbols()
+    assert len(declared) >= 25
+    for sym in declared:
+        assert hasattr(_native.lib, sym), f'{sym} declared in include/deeptables_b200.h but not exported'
+        assert sym in _native._SIGNATURES, f'{sym} has no ctypes signature'
+    assert _native.lib.dtb_version() >= 100
+
+
+def test_graft_build_is_idempotent():
+    import __graft_entry__ as g
+    path = g.build()
+    assert os.path.exists(path)
+
+
+def test_model_config_defaults_match_reference():
+    from deeptables_b200 import deeptable
+    c = deeptable.ModelConfig()
+    # reference deeptables/models/config.py:59-136
+    assert c.name == 'conf-1' and c.nets == ['dnn_nets'] and c.metrics == ['accuracy']
+    assert c.embeddings_output_dim == 4 and c.embedding_dropout == 0.3 and c.dense_dropout == 0
+    assert c.stacking_op == 'add' and c.output_use_bias is True and c.optimizer == 'auto' and c.loss == 'auto'
+    assert c.dnn_params == {'hidden_units': ((128, 0, False), (64, 0, False)), 'activation': 'relu'}
+    assert c.cross_params == {'num_cross_layer': 4}
+    assert c.cin_params['cross_layer_size'] == (128, 128) and c.cin_params['direct'] is False
+    assert c.autoint_params == {'num_attention': 3, 'num_heads': 1, 'dropout_rate': 0, 'use_residual': True}
+    assert c.earlystopping_patience == 1 and c.earlystopping_mode == 'auto'
+    assert len(c._fields) == 45
+    assert c.first_metric_name == 'accuracy'
+    # positional order is the reference's
+    assert c._fields[:5] == ('name', 'nets', 'categorical_columns', 'exclude_columns', 'task')
+    with pytest.raises(TypeError):
+        deeptable.ModelConfig(not_a_field=1)
+    with pytest.raises(ValueError):
+        deeptable.ModelConfig(var_len_categorical_columns=[('a', '|')])
+    # defaults are not shared between instances
+    c.dnn_params['activation'] = 'x'
+    assert deeptable.ModelConfig().dnn_params['activation'] == 'relu'
+
+
+def test_nets_registry_names_presets_and_signature():
+    from deeptables_b200 import deepnets
+    assert deepnets.xDeepFM == ['linear', 'cin_nets', 'dnn_nets'] and deepnets.DeepFM == ['linear', 'fm_nets', 'dnn_nets']
+    assert deepnets.DCN == ['dcn_nets'] and deepnets.PNN == ['pnn_nets'] and deepnets.AutoInt == ['autoint_nets']
+    names = ['linear', 'cin_nets', 'fm_nets', 'afm_nets', 'opnn_nets', 'ipnn_nets', 'pnn_nets', 'dnn_nets', 'cross_nets',
+             'cross_dnn_nets', 'dcn_nets', 'autoint_nets', 'fg_nets', 'fgcnn_cin_nets', 'fgcnn_fm_nets',
+             'fgcnn_ipnn_nets', 'fgcnn_dnn_nets', 'fibi_nets', 'fibi_dnn_nets']
+    sig = inspect.signature(deepnets.linear)
+    assert list(sig.parameters) == ['embeddings', 'flatten_emb_layer', 'dense_layer', 'concat_emb_dense', 'config',
+                                    'model_desc']
+    for n in names:
+        fn = deepnets.get(n)
+        assert callable(fn) and inspect.signature(fn) == sig
+    with pytest.raises(ValueError):
+        deepnets.get('no_such_nets')
+    with pytest.raises(ValueError):
+        deepnets.get(None)
+    with pytest.raises(NotImplementedError):
+        deepnets.get('afm_nets')(None, None, None, None, None, None)
+
+    def custom(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+        return None
+    assert deepnets.get_nets(['dnn_nets', custom, 'dnn_nets']) == ['dnn_nets', 'custom']
+    assert deepnets.get('custom') is custom
+
+
+def test_metainfo_records():
+    from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
+    c = CategoricalColumn('x', 10000, 0)
+    assert c.embeddings_output_dim == 10 and c.input_name == 'cat_x' and c.dtype == 'int32'
+    assert hash(c) == hash('x')
+    cc = ContinuousColumn('input_continuous_all', ['a', 'b', 'c'])
+    assert cc.input_dim == 3 and cc.dtype == 'float32'
+
+
+def test_preprocessor_conventions():
+    from deeptables_b200 import deeptable
+    from deeptables_b200.deeptable import DefaultPreprocessor
+    df = pd.DataFrame({'a': ['x', 'y', None, 'x'], 'b': [1.0, np.nan, 3.0, 4.0], 'k': [7, 7, 7, 7]})
+    pre = DefaultPreprocessor(deeptable.ModelConfig())
+    X, y = pre.fit_transform(df, ['n', 'p', 'n', 'p'])
+    assert pre.task == 'binary' and pre.labels == ['n', 'p'] and list(y) == [0, 1, 0, 1]
+    assert [c.name for c in pre.categorical_columns] == ['a']
+    assert pre.categorical_columns[0].vocabulary_size == 3 + 2        # nunique(+nan) + 2 (preprocessor.py:333)
+    assert pre.continuous_columns[0].name == 'input_continuous_all' and pre.continuous_columns[0].column_names == ['b']
+    assert 'k' not in X.columns                                        # auto_discard_unique
+    assert not X['b'].isna().any()
+    Xt = pre.transform_X(pd.DataFrame({'a': ['zzz'], 'b': [2.0], 'k': [7]}))
+    assert int(Xt['a'][0]) == 3                                        # unseen -> reserved slot
+    pre2 = DefaultPreprocessor(deeptable.ModelConfig())
+    _, y2 = pre2.fit_transform(df, [0.5, 1.25, 3.75, 2.0])
+    assert pre2.task == 'regression'
+
+
+def test_ignore_case_dict():
+    from deeptables_b200.deepmodel import IgnoreCaseDict
+    d = IgnoreCaseDict({'AUC': 1, 'loss': 2})
+    assert d['auc'] == 1 and 'Loss' in d
+    d['Val_AUC'] = 3
+    assert d['val_auc'] == 3
+    with pytest.raises(KeyError):
+        d[1]

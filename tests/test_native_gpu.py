@@ -1,0 +1,416 @@
+"""GPU parity tests: every C-ABI op against the CPU oracle on the same seeded inputs.
+fp32 kernels: rtol 1e-4 (tolerance stated per test); index bookkeeping bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers_ref as L
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nat():
+    from deeptables_b200 import _native
+    return _native
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def make_table(vocab, d, seed=0):
+    g = np.random.default_rng(seed)
+    tabs = [g.uniform(-0.5, 0.5, size=(v, d)).astype(np.float32) for v in vocab]
+    offs = np.concatenate([[0], np.cumsum(vocab)]).astype(np.int64)
+    return tabs, np.concatenate(tabs, axis=0), offs
+
+
+def make_idx(vocab, b, seed=1):
+    g = np.random.default_rng(seed)
+    return np.stack([g.integers(0, v, size=b) for v in vocab], axis=1).astype(np.int32)
+
+
+def P(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+SHAPES = [  # (vocab sizes, D, C, B)
+    ([50] * 26, 16, 13, 257),     # Criteo shape
+    ([7, 5, 9, 4], 4, 3, 64),     # README-like small dims
+    ([11, 3], 2, 0, 33),          # D=2: generic (non-vector) path, no continuous
+    ([13], 8, 2, 19),             # single categorical column
+    ([6, 7, 8], 32, 1, 40),       # D=32
+]
+
+
+@pytest.mark.parametrize('vocab,d,c,b', SHAPES)
+def test_gather_scatter_bit_exact(nat, vocab, d, c, b):
+    tabs, flat, offs = make_table(vocab, d)
+    idx = make_idx(vocab, b)
+    f = len(vocab)
+    out = torch.empty(b, f, d, device='cuda')
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
+    nat.check(nat.lib.dtb_embedding_gather(P(dev(idx)), P(dev(flat)), P(dev(offs)), P(out), b, f, d, P(status), None))
+    want = torch.cat(L.embedding_lookup([torch.tensor(t) for t in tabs], torch.tensor(idx)), dim=1)
+    assert torch.equal(out.cpu(), want)            # pure data movement: bit exact
+    assert int(status.item()) == 0
+    # scatter-add == gradient of the gather (duplicates accumulate)
+    gout = np.random.default_rng(3).normal(size=(b, f, d)).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    nat.check(nat.lib.dtb_embedding_scatter_add(P(dev(idx)), P(dev(offs)), P(dev(gout)), P(gt), b, f, d, None))
+    want_g = np.zeros_like(flat, dtype=np.float64)
+    for i in range(f):
+        np.add.at(want_g, offs[i] + idx[:, i], gout[:, i].astype(np.float64))
+    np.testing.assert_allclose(gt.cpu().numpy(), want_g, rtol=1e-5, atol=1e-6)
+
+
+def test_out_of_range_id_sets_status_and_reads_zero(nat):
+    vocab, d, b = [5, 6], 4, 3
+    _, flat, offs = make_table(vocab, d)
+    idx = np.array([[1, 2], [5, 0], [0, -1]], dtype=np.int32)      # (1,0) and (2,1) invalid
+    out = torch.full((b, 2, d), 7.0, device='cuda')
+    status = torch.zeros(1, dtype=torch.int32, device='cuda')
+    nat.check(nat.lib.dtb_embedding_gather(P(dev(idx)), P(dev(flat)), P(dev(offs)), P(out), b, 2, d, P(status), None))
+    assert int(status.item()) == 0b11
+    assert float(out[1, 0].abs().sum()) == 0.0 and float(out[2, 1].abs().sum()) == 0.0
+    assert float(out[0].abs().sum()) > 0
+
+
+@pytest.mark.parametrize('vocab,d,c,b', SHAPES)
+def test_fm_linear_fwd_bwd(nat, vocab, d, c, b):
+    tabs, flat, offs = make_table(vocab, d)
+    idx = make_idx(vocab, b)
+    f = len(vocab)
+    g = np.random.default_rng(5)
+    dense = g.normal(size=(b, c)).astype(np.float32) if c else None
+    wl = g.normal(size=(f + c,)).astype(np.float32)
+    d_idx, d_tab, d_offs = dev(idx), dev(flat), dev(offs)
+    d_dense = dev(dense) if c else None
+    d_wl = dev(wl)
+    out_lin = torch.empty(b, device='cuda')
+    out_fm = torch.empty(b, device='cuda')
+    nat.check(nat.lib.dtb_fm_linear_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_dense), P(d_wl), P(out_lin), P(out_fm),
+                                        b, f, d, c, None, None))
+    # oracle (float64 for a tight check)
+    t64 = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tabs]
+    emb = L.embedding_lookup(t64, torch.tensor(idx))
+    dn = torch.tensor(dense, dtype=torch.float64) if c else None
+    w64 = torch.tensor(wl, dtype=torch.float64, requires_grad=True)
+    lin = L.linear(emb, dn, w64.reshape(-1, 1))
+    fm = L.fm(L.concat_embeddings(emb))
+    np.testing.assert_allclose(out_lin.cpu().numpy(), lin.detach().numpy()[:, 0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(out_fm.cpu().numpy(), fm.detach().numpy()[:, 0], rtol=1e-4, atol=1e-5)
+    # backward
+    g_lin = g.normal(size=b).astype(np.float32)
+    g_fm = g.normal(size=b).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    gw = torch.zeros(f + c, device='cuda')
+    nat.check(nat.lib.dtb_fm_linear_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_dense), P(d_wl), P(dev(g_lin)),
+                                        P(dev(g_fm)), P(gt), P(gw), b, f, d, c, None))
+    loss = (lin[:, 0] * torch.tensor(g_lin, dtype=torch.float64)).sum() + \
+           (fm[:, 0] * torch.tensor(g_fm, dtype=torch.float64)).sum()
+    grads = torch.autograd.grad(loss, t64 + [w64])
+    want_t = torch.cat(grads[:-1], dim=0).numpy()
+    np.testing.assert_allclose(gt.cpu().numpy(), want_t, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(gw.cpu().numpy(), grads[-1].numpy(), rtol=1e-4, atol=1e-4)
+    # FM only / linear only branches
+    out2 = torch.empty(b, device='cuda')
+    nat.check(nat.lib.dtb_fm_linear_fwd(P(d_idx), P(d_tab), P(d_offs), None, None, None, P(out2), b, f, d, 0, None, None))
+    np.testing.assert_allclose(out2.cpu().numpy(), fm.detach().numpy()[:, 0], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('vocab,d,c,b', SHAPES)
+def test_concat_and_batchnorm(nat, vocab, d, c, b):
+    tabs, flat, offs = make_table(vocab, d)
+    idx = make_idx(vocab, b)
+    f = len(vocab)
+    w = f * d + c
+    g = np.random.default_rng(6)
+    dense = (g.normal(size=(b, c)) * 3 + 1).astype(np.float32) if c else None
+    X = torch.empty(b, w, device='cuda')
+    nat.check(nat.lib.dtb_concat_emb_dense_fwd(P(dev(idx)), P(dev(flat)), P(dev(offs)), P(dev(dense)) if c else None,
+                                               P(X), b, f, d, c, None, None))
+    emb = L.embedding_lookup([torch.tensor(t) for t in tabs], torch.tensor(idx))
+    want = L.flatten_embeddings(emb)
+    if c:
+        want = torch.cat([want, torch.tensor(dense)], dim=-1)
+    assert torch.equal(X.cpu(), want)              # data movement: bit exact, field-major layout
+    gamma = (g.normal(size=w) + 2).astype(np.float32)
+    beta = g.normal(size=w).astype(np.float32)
+    mm = torch.zeros(w, device='cuda')
+    mv = torch.ones(w, device='cuda')
+    sm, sv = torch.empty(w, device='cuda'), torch.empty(w, device='cuda')
+    ws = torch.empty(2 * w, dtype=torch.float64, device='cuda')
+    Y = torch.empty_like(X)
+    d_g, d_b = dev(gamma), dev(beta)
+    nat.check(nat.lib.dtb_batchnorm_train_fwd(P(X), P(Y), P(d_g), P(d_b), P(mm), P(mv), P(sm), P(sv), P(ws), b, w,
+                                              1e-3, 0.99, None))
+    x64 = want.double().requires_grad_(True)
+    g64 = torch.tensor(gamma, dtype=torch.float64, requires_grad=True)
+    b64 = torch.tensor(beta, dtype=torch.float64, requires_grad=True)
+    y64, nm, nv = L.batch_norm(x64, g64, b64, torch.zeros(w, dtype=torch.float64),
+                               torch.ones(w, dtype=torch.float64), True)
+    np.testing.assert_allclose(Y.cpu().numpy(), y64.detach().numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(mm.cpu().numpy(), nm.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(mv.cpu().numpy(), nv.numpy(), rtol=1e-5, atol=1e-7)
+    dy = g.normal(size=(b, w)).astype(np.float32)
+    dX = torch.empty_like(X)
+    dg, db = torch.zeros(w, device='cuda'), torch.zeros(w, device='cuda')
+    nat.check(nat.lib.dtb_batchnorm_bwd(P(X), P(dev(dy)), P(dX), P(d_g), P(sm), P(sv), P(dg), P(db), P(ws), b, w,
+                                        1e-3, None))
+    gx, gg, gb = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64, g64, b64])
+    np.testing.assert_allclose(dX.cpu().numpy(), gx.numpy(), rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(dg.cpu().numpy(), gg.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(db.cpu().numpy(), gb.numpy(), rtol=1e-4, atol=1e-4)
+    # inference mode with the moving statistics
+    Y2 = torch.empty_like(X)
+    nat.check(nat.lib.dtb_batchnorm_infer_fwd(P(X), P(Y2), P(d_g), P(d_b), P(mm), P(mv), b, w, 1e-3, None))
+    y2, _, _ = L.batch_norm(want.double(), g64.detach(), b64.detach(), nm, nv, False)
+    np.testing.assert_allclose(Y2.cpu().numpy(), y2.numpy(), rtol=1e-4, atol=2e-5)
+    # concat backward scatters only the embedding columns
+    gt = torch.zeros(flat.shape, device='cuda')
+    nat.check(nat.lib.dtb_concat_emb_dense_bwd(P(dev(idx)), P(dev(offs)), P(dev(dy)), P(gt), b, f, d, c, None))
+    want_g = np.zeros(flat.shape, dtype=np.float64)
+    for i in range(f):
+        np.add.at(want_g, offs[i] + idx[:, i], dy[:, i * d:(i + 1) * d].astype(np.float64))
+    np.testing.assert_allclose(gt.cpu().numpy(), want_g, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('rows,i,o,act', [(300, 429, 128, 1), (300, 128, 64, 1), (77, 64, 1, 0), (50, 1, 1, 0),
+                                           (64, 37, 3, 0), (5, 10, 20, 1)])
+def test_dense_fwd_bwd(nat, rows, i, o, act):
+    g = np.random.default_rng(7)
+    x = g.normal(size=(rows, i)).astype(np.float32)
+    w = (g.normal(size=(i, o)) / np.sqrt(i)).astype(np.float32)
+    bias = g.normal(size=o).astype(np.float32)
+    dy = g.normal(size=(rows, o)).astype(np.float32)
+    X, W, Bv = dev(x), dev(w), dev(bias)
+    Y = torch.empty(rows, o, device='cuda')
+    nat.check(nat.lib.dtb_dense_fwd(P(X), P(W), P(Bv), P(Y), rows, i, o, act, None))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    w64 = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    b64 = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+    y64 = L.dense(x64, w64, b64, 'relu' if act else None)
+    np.testing.assert_allclose(Y.cpu().numpy(), y64.detach().numpy(), rtol=1e-4, atol=1e-5)
+    dY = dev(dy)
+    dX = torch.empty(rows, i, device='cuda')
+    dW = torch.zeros(i, o, device='cuda')
+    dB = torch.zeros(o, device='cuda')
+    nat.check(nat.lib.dtb_dense_bwd(P(X), P(W), P(Y), P(dY), P(dX), P(dW), P(dB), rows, i, o, act, None))
+    gx, gw, gb = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64, w64, b64])
+    np.testing.assert_allclose(dX.cpu().numpy(), gx.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dW.cpu().numpy(), gw.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dB.cpu().numpy(), gb.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('task,cols', [(0, 1), (0, 3), (1, 1), (2, 4)])
+def test_losses(nat, task, cols):
+    g = np.random.default_rng(8)
+    rows = 130
+    z = (g.normal(size=(rows, cols)) * 2).astype(np.float32)
+    if task == 0:
+        y = (g.random((rows, cols)) < 0.4).astype(np.float32)
+    elif task == 1:
+        y = g.normal(size=(rows, cols)).astype(np.float32)
+    else:
+        y = np.eye(cols, dtype=np.float32)[g.integers(0, cols, size=rows)]
+    sw = g.uniform(0.5, 2.0, size=rows).astype(np.float32)
+    for weights in (None, sw):
+        prob = torch.empty(rows, cols, device='cuda')
+        dz = torch.empty(rows, cols, device='cuda')
+        acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+        nat.check(nat.lib.dtb_loss_fwd_bwd(P(dev(z)), P(dev(y)), P(dev(weights)) if weights is not None else None,
+                                           P(prob), P(dz), P(acc), rows, cols, task, None))
+        z64 = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+        y64 = torch.tensor(y, dtype=torch.float64)
+        if task == 0:
+            p = torch.sigmoid(z64)
+            per = -(y64 * torch.log(p.clamp(1e-7, 1 - 1e-7)) + (1 - y64) * torch.log((1 - p).clamp(1e-7, 1))).mean(-1)
+        elif task == 1:
+            p = z64
+            per = ((p - y64) ** 2).mean(-1)
+        else:
+            p = torch.softmax(z64, -1)
+            per = -(y64 * torch.log(p.clamp(1e-7, 1 - 1e-7))).sum(-1)
+        wv = torch.tensor(weights, dtype=torch.float64) if weights is not None else torch.ones(rows, dtype=torch.float64)
+        loss = (per * wv).sum() / rows
+        (gz,) = torch.autograd.grad(loss, [z64])
+        np.testing.assert_allclose(prob.cpu().numpy(), p.detach().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(dz.cpu().numpy(), gz.numpy(), rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(float(acc.item()) / rows, float(loss), rtol=1e-5)
+
+
+def test_adam_dense_matches_oracle(nat):
+    g = np.random.default_rng(9)
+    n = 1000
+    p0 = g.normal(size=n).astype(np.float32)
+    pt, m, v = dev(p0.copy()), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    po, mo, vo = torch.tensor(p0.copy()), torch.zeros(n), torch.zeros(n)
+    from deeptables_b200.engine import adam_alpha
+    for step in range(1, 6):
+        grad = g.normal(size=n).astype(np.float32)
+        gd = dev(grad.copy())
+        nat.check(nat.lib.dtb_adam_dense(P(pt), P(m), P(v), P(gd), n, adam_alpha(step), 0.9, 0.999, 1e-7, 1, None))
+        assert float(gd.abs().sum()) == 0.0                   # zero_grad
+        L.adam_step(po, torch.tensor(grad), mo, vo, step)
+    np.testing.assert_allclose(pt.cpu().numpy(), po.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(m.cpu().numpy(), mo.numpy(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(v.cpu().numpy(), vo.numpy(), rtol=1e-6, atol=1e-12)
+
+
+def test_lazy_adam_matches_dense(nat):
+    """Exact-lazy row-wise Adam is BIT-identical to dense Adam over the whole table."""
+    from deeptables_b200.engine import adam_alpha
+    vocab, d, b, steps = [40, 25, 60], 16, 12, 25
+    f = len(vocab)
+    rows = sum(vocab)
+    offs = dev(np.concatenate([[0], np.cumsum(vocab)]).astype(np.int64))
+    g = np.random.default_rng(10)
+    w0 = g.uniform(-0.05, 0.05, size=(rows, d)).astype(np.float32)
+    alpha = dev(np.array([0.0] + [adam_alpha(s) for s in range(1, steps + 2)], dtype=np.float32))
+    wd, md, vd = dev(w0.copy()), torch.zeros(rows, d, device='cuda'), torch.zeros(rows, d, device='cuda')
+    wl, ml, vl = dev(w0.copy()), torch.zeros(rows, d, device='cuda'), torch.zeros(rows, d, device='cuda')
+    gl = torch.zeros(rows, d, device='cuda')
+    last = torch.zeros(rows, dtype=torch.int32, device='cuda')
+    for step in range(1, steps + 1):
+        idx = make_idx(vocab, b, seed=100 + step)
+        idx[1] = idx[0]                                            # duplicate ids inside a batch
+        d_idx = dev(idx)
+        nat.check(nat.lib.dtb_adam_rows_catchup(P(d_idx), P(offs), P(wl), P(ml), P(vl), P(last), P(alpha), step - 1,
+                                                0.9, 0.999, 1e-7, b, f, d, None))
+        # rows read by this step must already equal the dense trajectory
+        flat_rows = (offs[:-1].cpu().numpy()[None, :] + idx).reshape(-1)
+        assert torch.equal(wl[flat_rows], wd[flat_rows])
+        gout = g.normal(size=(b, f, d)).astype(np.float32)
+        gd = torch.zeros(rows, d, device='cuda')
+        for tgt in (gd, gl):
+            nat.check(nat.lib.dtb_embedding_scatter_add(P(d_idx), P(offs), P(dev(gout)), P(tgt), b, f, d, None))
+        a = float(alpha[step].item())
+        nat.check(nat.lib.dtb_adam_dense(P(wd), P(md), P(vd), P(gd), rows * d, a, 0.9, 0.999, 1e-7, 1, None))
+        nat.check(nat.lib.dtb_adam_rows_apply(P(d_idx), P(offs), P(wl), P(ml), P(vl), P(gl), P(last), P(alpha), step,
+                                              0.9, 0.999, 1e-7, b, f, d, None))
+        assert float(gl.abs().sum()) == 0.0
+    nat.check(nat.lib.dtb_adam_rows_flush(P(wl), P(ml), P(vl), P(last), P(alpha), steps, 0.9, 0.999, 1e-7, rows, d, None))
+    assert torch.equal(wl, wd) and torch.equal(ml, md) and torch.equal(vl, vd)
+    assert int(last.min().item()) == steps
+
+
+CIN_CASES = [  # (F, D, sizes, direct, bias, act)
+    (5, 4, (6, 4), False, False, 1),
+    (26, 16, (32, 32, 16), False, False, 1),
+    (4, 8, (6, 5), True, True, 1),
+    (3, 2, (4, 3), False, True, 0),
+    (1, 4, (4, 2), False, False, 1),
+    (7, 32, (8,), False, False, 1),
+]
+
+
+def _cin_oracle(x, sizes, direct, filters, biases, act):
+    params = dict(cross_layer_size=sizes, direct=direct, use_bias=biases is not None,
+                  activation='relu' if act else 'linear')
+    width = L.cin_pooled_width(x.shape[1], params)
+    w = {f'f_{k}': filters[k].unsqueeze(0) for k in range(len(sizes))}
+    if biases is not None:
+        for k in range(len(sizes)):
+            w[f'bias{k}'] = biases[k]
+    # identity head so that the oracle returns the pooled features column by column
+    outs = []
+    for col in range(width):
+        kernel = torch.zeros(width, 1, dtype=x.dtype)
+        kernel[col, 0] = 1.0
+        w['exFM_out/kernel'] = kernel
+        w['exFM_out/bias'] = torch.zeros(1, dtype=x.dtype)
+        outs.append(L.cin(x, params, w))
+    return torch.cat(outs, dim=1)
+
+
+@pytest.mark.parametrize('f,d,sizes,direct,use_bias,act', CIN_CASES)
+@pytest.mark.parametrize('precision', [1, 0])
+def test_cin_fwd_bwd(nat, f, d, sizes, direct, use_bias, act, precision):
+    b = 37
+    vocab = [9 + i for i in range(f)]
+    tabs, flat, offs = make_table(vocab, d, seed=11)
+    idx = make_idx(vocab, b, seed=12)
+    g = np.random.default_rng(13)
+    fns = L.cin_field_nums(f, sizes, direct)
+    filt = [(g.normal(size=(f * fns[k], s)) / np.sqrt(f * fns[k])).astype(np.float32) for k, s in enumerate(sizes)]
+    bias = [g.normal(size=s).astype(np.float32) * 0.1 for s in sizes] if use_bias else None
+    wcat = np.concatenate([x.reshape(-1) for x in filt])
+    sizes_c = nat.int_array(sizes)
+    n = len(sizes)
+    pw = L.cin_pooled_width(f, dict(cross_layer_size=sizes, direct=direct))
+    pooled = torch.empty(b, pw, device='cuda')
+    ws_bytes = nat.lib.dtb_cin_workspace_bytes(b, f, d, sizes_c, n, int(direct), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+    saved = torch.empty(nat.lib.dtb_cin_saved_bytes(b, f, d, sizes_c, n, int(direct)), dtype=torch.uint8, device='cuda')
+    d_idx, d_tab, d_offs, d_w = dev(idx), dev(flat), dev(offs), dev(wcat)
+    d_b = dev(np.concatenate(bias)) if use_bias else None
+    nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(pooled), P(saved), P(ws), ws_bytes,
+                                  b, f, d, sizes_c, n, int(direct), act, precision, None, None))
+    t64 = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tabs]
+    x = torch.cat(L.embedding_lookup(t64, torch.tensor(idx)), dim=1)
+    f64 = [torch.tensor(w_, dtype=torch.float64, requires_grad=True) for w_ in filt]
+    b64 = [torch.tensor(b_, dtype=torch.float64, requires_grad=True) for b_ in bias] if use_bias else None
+    want = _cin_oracle(x, sizes, direct, f64, b64, act)
+    scale = float(want.abs().max())
+    tol = 1e-4 if precision == 1 else 1e-3            # fp32 path vs bf16x3 tensor-core path
+    np.testing.assert_allclose(pooled.cpu().numpy(), want.detach().numpy(), rtol=tol, atol=tol * scale)
+    dp = g.normal(size=(b, pw)).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    dw = torch.zeros(wcat.shape, device='cuda')
+    dbias = torch.zeros(sum(sizes), device='cuda') if use_bias else None
+    nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(dev(dp)), P(saved), P(gt), P(dw), P(dbias),
+                                  P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, precision, None))
+    loss = (want * torch.tensor(dp, dtype=torch.float64)).sum()
+    params = t64 + f64 + (b64 or [])
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    want_t = torch.cat(grads[:f], dim=0).numpy()
+    want_w = np.concatenate([gg.numpy().reshape(-1) for gg in grads[f:f + n]])
+    np.testing.assert_allclose(gt.cpu().numpy(), want_t, rtol=tol * 10, atol=tol * np.abs(want_t).max())
+    np.testing.assert_allclose(dw.cpu().numpy(), want_w, rtol=tol * 10, atol=tol * np.abs(want_w).max())
+    if use_bias:
+        want_b = np.concatenate([gg.numpy() for gg in grads[f + n:]])
+        np.testing.assert_allclose(dbias.cpu().numpy(), want_b, rtol=tol * 10, atol=tol * np.abs(want_b).max())
+
+
+def test_cin_invalid_config_rejected(nat):
+    sizes_c = nat.int_array((3, 4))
+    assert nat.lib.dtb_cin_workspace_bytes(4, 3, 4, sizes_c, 2, 0, 1) == 0      # odd non-last layer, direct=False
+    dummy = torch.zeros(16, device='cuda')
+    rc = nat.lib.dtb_cin_fwd(P(dummy), P(dummy), P(dummy), P(dummy), None, P(dummy), None, P(dummy), 64, 4, 3, 4,
+                             sizes_c, 2, 0, 1, 1, None, None)
+    assert rc == -1 and 'cross_layer_size' in nat.last_error()
+
+
+@pytest.mark.parametrize('b,w,n', [(50, 429, 6), (33, 17, 1), (64, 40, 4)])
+def test_cross_fwd_bwd(nat, b, w, n):
+    g = np.random.default_rng(14)
+    x = g.normal(size=(b, w)).astype(np.float32)
+    ks = (g.normal(size=(n, w)) / np.sqrt(w)).astype(np.float32)
+    bs = (g.normal(size=(n, w)) * 0.1).astype(np.float32)
+    X, K, Bv = dev(x), dev(ks), dev(bs)
+    Y = torch.empty(b, w, device='cuda')
+    xw = torch.empty(b, n, device='cuda')
+    nat.check(nat.lib.dtb_cross_fwd(P(X), P(K), P(Bv), P(Y), P(xw), b, w, n, None))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    k64 = [torch.tensor(ks[i].reshape(w, 1), dtype=torch.float64, requires_grad=True) for i in range(n)]
+    b64 = [torch.tensor(bs[i].reshape(w, 1), dtype=torch.float64, requires_grad=True) for i in range(n)]
+    y64 = L.cross(x64, k64, b64)
+    np.testing.assert_allclose(Y.cpu().numpy(), y64.detach().numpy(), rtol=1e-4, atol=1e-4)
+    dy = g.normal(size=(b, w)).astype(np.float32)
+    dX = torch.empty(b, w, device='cuda')
+    dK, dB = torch.zeros(n, w, device='cuda'), torch.zeros(n, w, device='cuda')
+    nat.check(nat.lib.dtb_cross_bwd(P(X), P(K), P(Bv), P(xw), P(dev(dy)), P(dX), P(dK), P(dB), b, w, n, None))
+    grads = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64] + k64 + b64)
+    sc = max(1.0, float(grads[0].abs().max()))
+    np.testing.assert_allclose(dX.cpu().numpy(), grads[0].numpy(), rtol=1e-3, atol=1e-4 * sc)
+    wk = np.stack([gg.numpy()[:, 0] for gg in grads[1:1 + n]])
+    wb = np.stack([gg.numpy()[:, 0] for gg in grads[1 + n:]])
+    np.testing.assert_allclose(dK.cpu().numpy(), wk, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(wk).max()))
+    np.testing.assert_allclose(dB.cpu().numpy(), wb, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(wb).max()))
