@@ -1,12 +1,577 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// CIN (layers.py:638-734) on the 5th-generation tensor cores -- the product path.
+//
+// Math.  For batch row b, embedding dim d:  C_k[(b,d), l] = sum_{i,j} x0[b,i,d] h_k[b,j,d] W_k[i*H+j, l].
+// That is a GEMM whose A operand  Z_k[(b,d), (i,j)] = x0[b,i,d]*h_k[b,j,d]  never needs to exist in
+// HBM (the reference materialises it: 7 GB per layer at B = 65 536, layers.py:693-695).  Here one CTA
+// owns 2 x (128/D) batch rows = two M=128 tiles; thread p of a tile's producer group owns GEMM row
+// m = p = (row r, dim d), keeps h_k[b, :, d] in REGISTERS across the whole layer (it is that thread's
+// own slice of the previous accumulator), and per K-chunk (one x0 field i, all j) multiplies by the
+// scalar x0[b,i,d], splits the fp32 products into bf16 hi + lo and hands them to the tensor core
+// either through TMEM (tcgen05.st, A-from-TMEM MMA) or through shared memory (canonical no-swizzle
+// K-major core matrices).  W_k is pre-split into bf16 hi/lo and pre-tiled in the UMMA canonical
+// layout by a tiny pack kernel, so a whole K-chunk (<= 32 KB) arrives with ONE bulk async copy.
+//
+// Precision.  bf16x3: Z_hi*W_hi + Z_lo*W_hi + Z_hi*W_lo, fp32 accumulate in TMEM: relative error
+// ~2^-16 per product -- inside the 1e-3 parity bar with margin (single-pass bf16 is ~4e-3).
+//
+// Pipeline per CTA (320 threads): warps 0-3 / 4-7 = producer+epilogue groups of tile 0 / 1 (warp%4 =
+// TMEM lane quadrant), warp 8 = MMA issuer (one thread) + TMEM allocator, warp 9 = weight loader.
+// mbarriers: full_a[tile][stage] (producers -> MMA), full_b[stage] (bulk copy -> MMA),
+// empty_a / empty_b (tcgen05.commit -> producers / loader), acc_full[tile] (commit -> epilogue).
+// Both tiles share each W chunk in smem, which halves the L2->SM weight stream (the limiter at one
+// tile per CTA: 42 B/clk/SM against a ~42 B/clk/SM L2 cap).
 #include "dtb_common.cuh"
 #include "cin_impl.h"
+#include "tcgen05.cuh"
+#include <cuda_bf16.h>
+
 namespace dtb {
-bool cin_tc_supported(const CinShape&) { return false; }
-size_t cin_tc_saved_bytes(const CinShape&, int) { return 0; }
-size_t cin_tc_workspace_bytes(const CinShape&, int, int) { return 0; }
-int cin_tc_fwd(const CinShape&, const int32_t*, const float*, const int64_t*, const float*, const float*, float*,
-               void*, void*, size_t, int, int, int, int*, cudaStream_t) { return DTB_ERR_UNSUPPORTED; }
-int cin_tc_bwd(const CinShape&, const int32_t*, const float*, const int64_t*, const float*, const float*,
-               const void*, float*, float*, float*, void*, size_t, int, int, int, cudaStream_t) { return DTB_ERR_UNSUPPORTED; }
+
+constexpr int kMaxL = 128;      // feature maps per layer (UMMA N)
+constexpr int kMaxHp = 64;      // padded hidden fields per layer (K chunk)
+constexpr int kTcThreads = 320;
+constexpr int kStagesA = 2;
+constexpr int kAccCols = 128;   // TMEM columns per accumulator tile
+constexpr int kTmemCols = 512;
+
+struct CinTcParams {
+  const int32_t* idx;
+  const float* table;
+  const int64_t* row_offsets;
+  const uint8_t* wpack;
+  const float* bias;
+  float* pooled;
+  float* saved;       // training: x0t [B,D,F] then T_k [B,D,L_k] (same layout as the fp32 path)
+  int* status;
+  int B, F, n_layers, act, n_pass, P;
+  int L[kCinMaxLayers], H[kCinMaxLayers], Hp[kCinMaxLayers];
+  int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
+  unsigned long long wpack_off[kCinMaxLayers];   // byte offset of layer k's chunk images
+  unsigned long long saved_off[kCinMaxLayers];   // float offset of T_k inside saved
+  unsigned long long bias_off[kCinMaxLayers];
+  int b_stage_bytes;                              // bytes reserved per weight stage in smem
+};
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------
+// weight pack: fp32 [K_k, L_k] -> per chunk i: [hi image | lo image], image = canonical K-major
+// no-swizzle tile of B[n][kk] = W[(i*H + kk), n]  (zero for kk >= H): core (kk/8, n/8) at
+// ((kk/8)*(L/8) + n/8)*128 B, row n%8 at 16 B, element kk%8 at 2 B.
+// ------------------------------------------------------------------------------------------
+__global__ void cin_tc_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
+                                   int L) {
+  const int64_t per_chunk = (int64_t)L * Hp;
+  const int64_t total = per_chunk * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / per_chunk);
+    const int rem = (int)(t - (int64_t)i * per_chunk);
+    const int kk = rem / L, n = rem - kk * L;     // n fastest: coalesced reads of W rows
+    const float v = kk < H ? w[((int64_t)i * H + kk) * L + n] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int64_t off = ((int64_t)(kk >> 3) * (L >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+    uint8_t* base = out + (int64_t)i * per_chunk * 4;      // hi + lo images, 2 bytes each
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + per_chunk * 2 + off) = lo;
+  }
 }
+
+// ------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------
+struct TcSmemLayout {
+  int b_off, a_off, x0_off, bar_off, total;
+};
+
+template <bool kATmem>
+__host__ __device__ inline TcSmemLayout tc_layout(int b_stage_bytes, int F, int D) {
+  const int stages_b = kATmem ? 4 : 2;
+  TcSmemLayout l;
+  l.b_off = 0;
+  l.a_off = stages_b * b_stage_bytes;
+  const int a_bytes = kATmem ? 0 : kStagesA * 2 * (2 * 128 * kMaxHp * 2);   // [stage][tile][hi|lo]
+  l.x0_off = l.a_off + a_bytes;
+  l.bar_off = l.x0_off + 2 * 128 * F * 4;                                    // x0s[tile][r][i][d]
+  l.bar_off = (l.bar_off + 15) / 16 * 16;
+  l.total = l.bar_off + 256;
+  return l;
+}
+
+template <int D, bool kATmem>
+__global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_constant__ CinTcParams p) {
+  constexpr int R = 128 / D;                 // batch rows per M=128 tile
+  constexpr int kStagesB = kATmem ? 4 : 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcSmemLayout lay = tc_layout<kATmem>(p.b_stage_bytes, p.F, D);
+  uint8_t* smem_b = smem + lay.b_off;
+  uint8_t* smem_a = smem + lay.a_off;
+  float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* full_a = bars;                        // [tile][stage] -> 4
+  uint64_t* empty_a = bars + 4;                   // [stage]       -> 2
+  uint64_t* full_b = bars + 6;                    // [stage]       -> 4
+  uint64_t* empty_b = bars + 10;                  // [stage]       -> 4
+  uint64_t* acc_full = bars + 14;                 // [tile]        -> 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = p.F;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < 2; ++g)
+      for (int s = 0; s < kStagesA; ++s) tc::mbar_init(&full_a[g * kStagesA + s], 128);
+    for (int s = 0; s < kStagesA; ++s) tc::mbar_init(&empty_a[s], 1);
+    for (int s = 0; s < kStagesB; ++s) {
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty_b[s], 1);
+    }
+    tc::mbar_init(&acc_full[0], 1);
+    tc::mbar_init(&acc_full[1], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =================== producer + epilogue group g, GEMM row m = t =========================
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;
+    const int r = t / D, d = t % D;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* x0g = x0s + (size_t)g * 128 * F;         // [r][i][d]
+    uint32_t chunk = 0, layer_cnt = 0;
+    float h[kMaxHp];
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int row0 = (st * 2 + g) * R;
+      const int b = row0 + r;
+      // ---- gather this tile's x0 block: R rows x F fields x D floats, 16-byte pieces ----------
+      if constexpr (D % 4 == 0) {
+        constexpr int Q = D / 4;
+        for (int e = t; e < R * F * Q; e += 128) {
+          const int rr = e / (F * Q);
+          const int rem = e - rr * F * Q;
+          const int i = rem / Q, q = rem - i * Q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + rr < p.B) {
+            const int64_t rb = table_row(p.row_offsets, i, __ldg(p.idx + (int64_t)(row0 + rr) * F + i), D, p.status);
+            if (rb >= 0) v = ldg_stream_f4(p.table + rb + (q << 2));
+          }
+          *reinterpret_cast<float4*>(x0g + ((size_t)rr * F + i) * D + (q << 2)) = v;
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      // ---- h_0 = x0 (zero padded to Hp[0]) ; training: save x0t ------------------------------
+#pragma unroll
+      for (int j = 0; j < kMaxHp; ++j) h[j] = (j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
+      if (p.saved && b < p.B) {
+        float* dst = p.saved + ((size_t)b * D + d) * F;
+        for (int j = 0; j < F; ++j) dst[j] = x0g[((size_t)r * F + j) * D + d];
+      }
+      for (int k = 0; k < p.n_layers; ++k) {
+        const int Hp = p.Hp[k], L = p.L[k];
+        for (int i = 0; i < F; ++i, ++chunk) {
+          const uint32_t sa = chunk % kStagesA, pa = (chunk / kStagesA) & 1;
+          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+          const float xi = x0g[((size_t)r * F + i) * D + d];
+          if constexpr (kATmem) {
+            tc::fence_after_thread_sync();
+            const uint32_t a_col = 2 * kAccCols + ((sa * 2 + g) * 2) * (kMaxHp / 2);
+#pragma unroll
+            for (int jb = 0; jb < kMaxHp / 16; ++jb) {
+              if (jb * 16 < Hp) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  tc::split_bf16x2(xi * h[jb * 16 + 2 * q], xi * h[jb * 16 + 2 * q + 1], hi[q], lo[q]);
+                tc::tmem_st8(tmem_base + lane_base + a_col + jb * 8, hi);
+                if (p.n_pass > 1) tc::tmem_st8(tmem_base + lane_base + a_col + kMaxHp / 2 + jb * 8, lo);
+              }
+            }
+            tc::tmem_wait_st();
+            tc::fence_before_thread_sync();
+          } else {
+            uint8_t* a_hi = smem_a + (size_t)((sa * 2 + g) * 2) * (128 * kMaxHp * 2);
+            uint8_t* a_lo = a_hi + 128 * kMaxHp * 2;
+            const int row_off = (t >> 3) * 128 + (t & 7) * 16;
+#pragma unroll
+            for (int jb = 0; jb < kMaxHp / 16; ++jb) {
+              if (jb * 16 < Hp) {
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  tc::split_bf16x2(xi * h[jb * 16 + 2 * q], xi * h[jb * 16 + 2 * q + 1], hi[q], lo[q]);
+                // 16 K-elements = two 16-byte core-matrix rows (K cores 2*jb and 2*jb+1)
+                *reinterpret_cast<uint4*>(a_hi + (2 * jb) * 2048 + row_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(a_hi + (2 * jb + 1) * 2048 + row_off) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                if (p.n_pass > 1) {
+                  *reinterpret_cast<uint4*>(a_lo + (2 * jb) * 2048 + row_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  *reinterpret_cast<uint4*>(a_lo + (2 * jb + 1) * 2048 + row_off) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+              }
+            }
+            tc::fence_proxy_async_smem();
+          }
+          tc::mbar_arrive(&full_a[g * kStagesA + sa]);
+        }
+        // ---- epilogue of layer k: this thread's accumulator row -> bias/act -> h / pooled / saved
+        tc::mbar_wait(&acc_full[g], layer_cnt & 1);
+        ++layer_cnt;
+        tc::fence_after_thread_sync();
+        const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
+        const float* bias = p.bias ? p.bias + p.bias_off[k] : nullptr;
+        float* sv = (p.saved && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
+#pragma unroll
+        for (int cb = 0; cb < kMaxL / 16; ++cb) {
+          if (cb * 16 < L) {
+            uint32_t v[16];
+            tc::tmem_ld16(tmem_base + lane_base + g * kAccCols + cb * 16, v);
+            tc::tmem_wait_ld();
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float val = __uint_as_float(v[j]);
+              if (bias) val += __ldg(bias + cb * 16 + j);
+              if (p.act == DTB_ACT_RELU) val = fmaxf(val, 0.f);
+              o[j] = val;
+              if (cb * 16 + j < kMaxHp) {
+                if (cb * 16 + j < hid_n) h[cb * 16 + j] = val;
+              }
+            }
+            if (sv) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(sv + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+            // sum over the D lanes that share a batch row (xor-shuffle inside D-aligned lane groups)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = cb * 16 + j;
+              if (col >= pool_lo && col < pool_lo + pool_n) {      // warp-uniform
+                float s = o[j];
+#pragma unroll
+                for (int off = 1; off < D && off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                if (D > 32) {   // not instantiated (D <= 32 supported)
+                }
+                if (d == 0 && b < p.B) p.pooled[(size_t)b * p.P + p.pcol0[k] + (col - pool_lo)] = s;
+              }
+            }
+          }
+        }
+        // zero the padding of the next layer's K chunk
+        if (k + 1 < p.n_layers) {
+#pragma unroll
+          for (int j = 0; j < kMaxHp; ++j)
+            if (j >= hid_n) h[j] = 0.f;
+        }
+        tc::fence_before_thread_sync();
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");   // x0 block free for the next super tile
+    }
+  } else if (warp == 8) {
+    // ================================ MMA issuer ===============================================
+    if (lane == 0) {
+      uint32_t chunk = 0;
+      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int k = 0; k < p.n_layers; ++k) {
+          const int Hp = p.Hp[k], L = p.L[k];
+          const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)L);
+          const uint32_t lbo_b = (uint32_t)(L >> 3) * 128;       // K-direction core stride of the W image
+          const uint32_t img_b = (uint32_t)L * Hp * 2;           // bytes of one (hi or lo) image
+          for (int i = 0; i < F; ++i, ++chunk) {
+            const uint32_t sa = chunk % kStagesA, pa = (chunk / kStagesA) & 1;
+            const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+            tc::mbar_wait(&full_b[sb], pb);
+            const uint32_t b_addr = tc::smem_u32(smem_b + (size_t)sb * p.b_stage_bytes);
+            for (int g = 0; g < 2; ++g) {
+              tc::mbar_wait(&full_a[g * kStagesA + sa], pa);
+              tc::fence_after_thread_sync();
+              const uint32_t d_tmem = tmem_base + g * kAccCols;
+              for (int pass = 0; pass < p.n_pass; ++pass) {
+                // pass 0: A_hi*B_hi ; 1: A_lo*B_hi ; 2: A_hi*B_lo
+                const int a_lo = (pass == 1), b_lo = (pass == 2);
+                for (int ks = 0; ks < Hp / 16; ++ks) {
+                  const uint32_t acc = (i | pass | ks) != 0;
+                  const uint64_t desc_b = tc::make_smem_desc(b_addr + b_lo * img_b + ks * 2 * lbo_b, lbo_b, 128);
+                  if constexpr (kATmem) {
+                    const uint32_t a_col = 2 * kAccCols + ((sa * 2 + g) * 2 + a_lo) * (kMaxHp / 2) + ks * 8;
+                    tc::mma_ts(d_tmem, tmem_base + a_col, desc_b, idesc, acc);
+                  } else {
+                    const uint32_t a_addr =
+                        tc::smem_u32(smem_a + (size_t)((sa * 2 + g) * 2 + a_lo) * (128 * kMaxHp * 2)) + ks * 4096;
+                    tc::mma_ss(d_tmem, tc::make_smem_desc(a_addr, 2048, 128), desc_b, idesc, acc);
+                  }
+                }
+              }
+              if (i == F - 1) tc::mma_commit(&acc_full[g]);
+            }
+            tc::mma_commit(&empty_a[sa]);
+            tc::mma_commit(&empty_b[sb]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ weight loader ============================================
+    if (lane == 0) {
+      uint32_t chunk = 0;
+      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int k = 0; k < p.n_layers; ++k) {
+          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * (p.n_pass > 1 ? 2 : 1);
+          const uint32_t stride = (uint32_t)p.L[k] * p.Hp[k] * 4;
+          const uint8_t* src = p.wpack + p.wpack_off[k];
+          for (int i = 0; i < F; ++i, ++chunk) {
+            const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+            tc::mbar_wait(&empty_b[sb], pb ^ 1);
+            tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
+            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[sb]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tensor-core self test: C[128,N] = A[128,K] * Bimg^T with single-pass bf16 (isolates descriptor /
+// TMEM-layout mistakes from the CIN logic).  Bimg is a packed image from cin_tc_pack_kernel.
+// ------------------------------------------------------------------------------------------
+template <bool kATmem>
+__global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ bimg,
+                                                              float* __restrict__ C, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* smem_b = smem;                                   // N*K*2
+  uint8_t* smem_a = smem + 128 * 64 * 2;                    // 128*K*2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * 128 * 64 * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bars[0], 128);   // full_a
+    tc::mbar_init(&bars[1], 1);     // full_b
+    tc::mbar_init(&bars[2], 1);     // acc_full
+    tc::fence_barrier_init();
+  }
+  if (warp == 4) tc::tmem_alloc(tmem_slot, 256);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+    const int t = threadIdx.x;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    if (t == 0) {
+      tc::mbar_arrive_expect_tx(&bars[1], (uint32_t)N * K * 2);
+      tc::bulk_g2s(smem_b, bimg, (uint32_t)N * K * 2, &bars[1]);
+    }
+    for (int jb = 0; jb < K / 16; ++jb) {
+      uint32_t hi[8];
+      for (int q = 0; q < 8; ++q) hi[q] = tc::pack_bf16x2(A[t * K + jb * 16 + 2 * q], A[t * K + jb * 16 + 2 * q + 1]);
+      if constexpr (kATmem) {
+        tc::tmem_st8(tmem_base + lane_base + 128 + jb * 8, hi);
+      } else {
+        const int row_off = (t >> 3) * 128 + (t & 7) * 16;
+        *reinterpret_cast<uint4*>(smem_a + (2 * jb) * 2048 + row_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(smem_a + (2 * jb + 1) * 2048 + row_off) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+      }
+    }
+    if constexpr (kATmem) {
+      tc::tmem_wait_st();
+      tc::fence_before_thread_sync();
+    } else {
+      tc::fence_proxy_async_smem();
+    }
+    tc::mbar_arrive(&bars[0]);
+    tc::mbar_wait(&bars[2], 0);
+    tc::fence_after_thread_sync();
+    for (int cb = 0; cb < N / 16; ++cb) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem_base + lane_base + cb * 16, v);
+      tc::tmem_wait_ld();
+      for (int j = 0; j < 16; ++j) C[t * N + cb * 16 + j] = __uint_as_float(v[j]);
+    }
+    tc::fence_before_thread_sync();
+  } else if (lane == 0) {
+    tc::mbar_wait(&bars[1], 0);
+    tc::mbar_wait(&bars[0], 0);
+    tc::fence_after_thread_sync();
+    const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)N);
+    const uint32_t lbo_b = (uint32_t)(N >> 3) * 128;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t desc_b = tc::make_smem_desc(tc::smem_u32(smem_b) + ks * 2 * lbo_b, lbo_b, 128);
+      if constexpr (kATmem)
+        tc::mma_ts(tmem_base, tmem_base + 128 + ks * 8, desc_b, idesc, ks != 0);
+      else
+        tc::mma_ss(tmem_base, tc::make_smem_desc(tc::smem_u32(smem_a) + ks * 4096, 2048, 128), desc_b, idesc, ks != 0);
+    }
+    tc::mma_commit(&bars[2]);
+  }
+  __syncwarp();
+  __syncthreads();
+  if (warp == 4) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int g_tc_variant = 1;   // 1: A operand through TMEM (default), 0: through shared memory
+
+static bool d_supported(int D) { return D == 4 || D == 8 || D == 16 || D == 32; }
+
+bool cin_tc_supported(const CinShape& s) {
+  if (!d_supported(s.D)) return false;
+  if (s.F > kMaxHp || s.F < 1) return false;
+  for (int k = 0; k < s.n_layers; ++k) {
+    if (s.L[k] % 16 || s.L[k] > kMaxL) return false;
+    if (round_up(s.H[k], 16) > kMaxHp) return false;
+  }
+  // shared-memory budget of the default variant
+  int bstage = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    const int bytes = 4 * s.L[k] * round_up(s.H[k], 16);
+    if (bytes > bstage) bstage = bytes;
+  }
+  const TcSmemLayout lay = g_tc_variant ? tc_layout<true>(bstage, s.F, s.D) : tc_layout<false>(bstage, s.F, s.D);
+  return lay.total <= 227 * 1024;
+}
+
+static size_t wpack_bytes(const CinShape& s) {
+  size_t b = 0;
+  for (int k = 0; k < s.n_layers; ++k) b += (size_t)s.F * s.L[k] * round_up(s.H[k], 16) * 4;
+  return b;
+}
+
+size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B); }
+
+size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
+  size_t fwd = wpack_bytes(s) + 1024;
+  size_t bwd = training ? cin_fp32_workspace_bytes(s, B, 1) : 0;   // backward: fp32 formulation (this round)
+  return fwd > bwd ? fwd : bwd;
+}
+
+template <int D, bool kATmem>
+static int launch_fwd(const CinTcParams& p, int smem_bytes, cudaStream_t st) {
+  auto kern = cin_tc_fwd_kernel<D, kATmem>;
+  DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int R = 128 / D;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+  int grid = sm_count();
+  if (grid > n_super) grid = n_super;
+  kern<<<grid, kTcThreads, smem_bytes, st>>>(p);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
+               const float* weights, const float* bias, float* pooled, void* saved, void* workspace,
+               size_t workspace_bytes, int B, int act, int n_pass, int* status, cudaStream_t st) {
+  if (workspace_bytes < wpack_bytes(s)) {
+    set_error("dtb_cin_fwd: workspace too small for the packed weights");
+    return DTB_ERR_INVALID_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(table) % 16) || (reinterpret_cast<uintptr_t>(workspace) % 16)) {
+    set_error("dtb_cin_fwd: table / workspace must be 16-byte aligned");
+    return DTB_ERR_INVALID_ARG;
+  }
+  CinTcParams p{};
+  p.idx = idx; p.table = table; p.row_offsets = row_offsets;
+  p.wpack = reinterpret_cast<uint8_t*>(workspace);
+  p.bias = bias; p.pooled = pooled; p.saved = reinterpret_cast<float*>(saved); p.status = status;
+  p.B = B; p.F = s.F; p.n_layers = s.n_layers; p.act = act; p.n_pass = n_pass; p.P = s.P;
+  size_t woff = 0, soff = (size_t)B * s.D * s.F;
+  int bstage = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], 16);
+    p.pool_lo[k] = s.pool_lo[k]; p.pool_n[k] = s.pool_n[k]; p.pcol0[k] = s.pcol0[k];
+    p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
+    p.wpack_off[k] = woff;
+    p.saved_off[k] = soff;
+    p.bias_off[k] = s.b_off[k];
+    const size_t chunk = (size_t)s.L[k] * p.Hp[k] * 4;
+    // pack layer k
+    const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    cin_tc_pack_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], reinterpret_cast<uint8_t*>(workspace) + woff,
+                                               s.F, s.H[k], p.Hp[k], s.L[k]);
+    DTB_LAUNCH_OK();
+    woff += chunk * s.F;
+    soff += (size_t)B * s.D * s.L[k];
+    if ((int)chunk > bstage) bstage = (int)chunk;
+  }
+  p.b_stage_bytes = bstage;
+  const bool a_tmem = g_tc_variant != 0;
+  const TcSmemLayout lay = a_tmem ? tc_layout<true>(bstage, s.F, s.D) : tc_layout<false>(bstage, s.F, s.D);
+#define DTB_TC_LAUNCH(DD)                                                          \
+  case DD:                                                                         \
+    return a_tmem ? launch_fwd<DD, true>(p, lay.total, st) : launch_fwd<DD, false>(p, lay.total, st);
+  switch (s.D) {
+    DTB_TC_LAUNCH(4)
+    DTB_TC_LAUNCH(8)
+    DTB_TC_LAUNCH(16)
+    DTB_TC_LAUNCH(32)
+    default:
+      set_error("dtb_cin_fwd: embedding dim %d unsupported by the tensor-core kernel", s.D);
+      return DTB_ERR_UNSUPPORTED;
+  }
+#undef DTB_TC_LAUNCH
+}
+
+int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
+               const float* weights, const float* d_pooled, const void* saved, float* grad_table,
+               float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
+               int n_pass, cudaStream_t st) {
+  (void)n_pass;
+  // The forward kernel saved x0t / T_k in the fp32 path's layout: the exact-fp32 backward consumes it.
+  return cin_fp32_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
+                      workspace, workspace_bytes, B, act, st);
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+extern "C" {
+
+// test hooks (declared in include/deeptables_b200.h)
+int dtb_cin_tc_set_variant(int a_operand_in_tmem) {
+  g_tc_variant = a_operand_in_tmem ? 1 : 0;
+  return DTB_OK;
+}
+
+int dtb_tc_selftest(const float* A, const float* Bmat, float* C, void* workspace, int N, int K, int a_operand_in_tmem,
+                    void* stream) {
+  DTB_CHECK_ARG(A && Bmat && C && workspace, "NULL argument");
+  DTB_CHECK_ARG(N % 16 == 0 && N >= 16 && N <= 128 && K % 16 == 0 && K >= 16 && K <= 64, "N<=128, K<=64, x16");
+  cudaStream_t st = (cudaStream_t)stream;
+  // Bmat is [K, N] row-major (a CIN filter with F = 1, H = K): pack -> image (hi | lo)
+  cin_tc_pack_kernel<<<32, 256, 0, st>>>(Bmat, reinterpret_cast<uint8_t*>(workspace), 1, K, K, N);
+  DTB_LAUNCH_OK();
+  const int smem = 2 * 128 * 64 * 2 + 64;
+  if (a_operand_in_tmem) {
+    DTB_CUDA_OK(cudaFuncSetAttribute(tc_selftest_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_selftest_kernel<true><<<1, 160, smem, st>>>(A, reinterpret_cast<uint8_t*>(workspace), C, N, K);
+  } else {
+    DTB_CUDA_OK(cudaFuncSetAttribute(tc_selftest_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc_selftest_kernel<false><<<1, 160, smem, st>>>(A, reinterpret_cast<uint8_t*>(workspace), C, N, K);
+  }
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+}  // extern "C"

@@ -243,6 +243,8 @@ class DeepModel:
             if dense_layer is not None and cfg.dense_dropout > 0:
                 dense_layer = L.Dropout(cfg.dense_dropout, name='dropout_dense_input')(dense_layer)
             flatten_emb_layer = _LazyFlat(scope, embeddings) if self.n_fields else None
+            if capture and 'flatten_embeddings' in capture and flatten_emb_layer is not None:
+                flatten_emb_layer._get()
             # concat_embedding_dense + bn_concat_emb_dense (reference deepmodel.py:348-361)
             if block is not None:
                 x = E.ConcatEmbDenseFn.apply(self.table.anchor, dense_layer, block)

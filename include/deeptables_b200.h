@@ -168,6 +168,12 @@ int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
 #define DTB_CIN_TC_BF16X3 2
 #define DTB_CIN_TC_BF16X1 3
 int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct);
+/* Test hooks for the tensor-core path.  set_variant: 1 (default) feeds the on-the-fly A operand to
+ * tcgen05.mma through TMEM, 0 through shared memory.  selftest: C[128,N] = bf16(A[128,K]) @
+ * bf16(Bmat[K,N]) with one M=128 UMMA tile (N <= 128, K <= 64, multiples of 16); workspace >= 4*N*K bytes. */
+int dtb_cin_tc_set_variant(int a_operand_in_tmem);
+int dtb_tc_selftest(const float* A, const float* Bmat, float* C, void* workspace, int N, int K,
+                    int a_operand_in_tmem, void* stream);
 
 /* ---- Cross (layers.py:417-436) on a dense [B,W] input ------------------------------------- */
 /* x_{l+1} = x0*(x_l . w_l) + x_l + b_l ; kernels/biases [n_layers, W]; Y [B,W].

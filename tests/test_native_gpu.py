@@ -17,11 +17,24 @@ def nat():
     return _native
 
 
+_KEEP = []     # ctypes only sees raw pointers: keep every device tensor of a test alive until it ends
+
+
+@pytest.fixture(autouse=True)
+def _keepalive():
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=None):
     t = torch.as_tensor(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.cuda()
+    t = t.cuda()
+    _KEEP.append(t)
+    return t
 
 
 def make_table(vocab, d, seed=0):
@@ -414,3 +427,111 @@ def test_cross_fwd_bwd(nat, b, w, n):
     wb = np.stack([gg.numpy()[:, 0] for gg in grads[1 + n:]])
     np.testing.assert_allclose(dK.cpu().numpy(), wk, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(wk).max()))
     np.testing.assert_allclose(dB.cpu().numpy(), wb, rtol=1e-3, atol=1e-4 * max(1.0, np.abs(wb).max()))
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) path
+# ---------------------------------------------------------------------------------------------
+def _bf16(x):
+    return torch.tensor(x).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize('a_in_tmem', [1, 0])
+@pytest.mark.parametrize('n,k', [(128, 64), (32, 16), (64, 32)])
+def test_tc_selftest_gemm(nat, a_in_tmem, n, k):
+    """One M=128 UMMA tile: validates the instruction / shared-memory descriptors, the TMEM
+    operand layout and the accumulator read-back against an exact bf16-input reference."""
+    g = np.random.default_rng(20)
+    a = g.normal(size=(128, k)).astype(np.float32)
+    bm = g.normal(size=(k, n)).astype(np.float32)
+    c = torch.zeros(128, n, device='cuda')
+    ws = torch.zeros(4 * n * k, dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_tc_selftest(P(dev(a)), P(dev(bm)), P(c), P(ws), n, k, a_in_tmem, None))
+    torch.cuda.synchronize()
+    want = _bf16(a).astype(np.float64) @ _bf16(bm).astype(np.float64)
+    np.testing.assert_allclose(c.cpu().numpy(), want, rtol=1e-5, atol=1e-4)
+
+
+TC_CASES = [  # (F, D, sizes, direct, bias, act, B)
+    (26, 16, (128, 128, 128), False, False, 1, 37),      # headline shape, ragged tail (37 rows)
+    (26, 16, (32, 32, 16), False, False, 1, 64),
+    (10, 8, (64, 32), False, True, 1, 50),
+    (4, 4, (16, 16), True, False, 1, 70),
+    (3, 32, (32, 16), False, True, 0, 9),
+    (1, 16, (16,), False, False, 1, 33),
+]
+
+
+@pytest.mark.parametrize('f,d,sizes,direct,use_bias,act,b', TC_CASES)
+@pytest.mark.parametrize('variant', [1, 0])
+@pytest.mark.parametrize('precision', [2, 3])
+def test_cin_tensor_core_forward(nat, f, d, sizes, direct, use_bias, act, b, variant, precision):
+    sizes_c = nat.int_array(sizes)
+    n = len(sizes)
+    nat.lib.dtb_cin_tc_set_variant(variant)
+    try:
+        if not nat.lib.dtb_cin_tc_supported(f, d, sizes_c, n, int(direct)):
+            pytest.skip('shape not supported by this tensor-core variant')
+        vocab = [9 + i for i in range(f)]
+        tabs, flat, offs = make_table(vocab, d, seed=21)
+        idx = make_idx(vocab, b, seed=22)
+        g = np.random.default_rng(23)
+        fns = L.cin_field_nums(f, sizes, direct)
+        filt = [(g.normal(size=(f * fns[k], s)) / np.sqrt(f * fns[k])).astype(np.float32) for k, s in enumerate(sizes)]
+        bias = [g.normal(size=s).astype(np.float32) * 0.1 for s in sizes] if use_bias else None
+        wcat = np.concatenate([x.reshape(-1) for x in filt])
+        pw = L.cin_pooled_width(f, dict(cross_layer_size=sizes, direct=direct))
+        pooled = torch.full((b, pw), float('nan'), device='cuda')
+        ws_bytes = nat.lib.dtb_cin_workspace_bytes(b, f, d, sizes_c, n, int(direct), 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+        saved = torch.empty(nat.lib.dtb_cin_saved_bytes(b, f, d, sizes_c, n, int(direct)), dtype=torch.uint8, device='cuda')
+        d_b = dev(np.concatenate(bias)) if use_bias else None
+        nat.check(nat.lib.dtb_cin_fwd(P(dev(idx)), P(dev(flat)), P(dev(offs)), P(dev(wcat)), P(d_b), P(pooled), P(saved),
+                                      P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, precision, None, None))
+        torch.cuda.synchronize()
+        x = torch.cat(L.embedding_lookup([torch.tensor(t, dtype=torch.float64) for t in tabs], torch.tensor(idx)), dim=1)
+        want = _cin_oracle(x, sizes, direct, [torch.tensor(w_, dtype=torch.float64) for w_ in filt],
+                           [torch.tensor(b_, dtype=torch.float64) for b_ in bias] if use_bias else None, act).numpy()
+        got = pooled.cpu().numpy()
+        scale = np.abs(want).max()
+        err = np.abs(got - want).max() / scale
+        # bf16x3 split: fp32-grade; single bf16 pass: ~2^-8 per operand
+        assert err < (2e-5 if precision == 2 else 2e-2), f'max err / scale = {err:.3e}'
+        if precision == 2:
+            np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-4 * scale)
+    finally:
+        nat.lib.dtb_cin_tc_set_variant(1)
+
+
+def test_cin_tensor_core_full_batch_properties(nat):
+    """BASELINE size (65 536 rows, 26x16, CIN 128x128x128): the oracle is too slow, so check
+    size-independent properties: duplicated rows give identical outputs, a row permutation permutes
+    the output, and a sample of rows matches the exact-fp32 GPU formulation."""
+    f, d, sizes, b = 26, 16, (128, 128, 128), 65536
+    sizes_c = nat.int_array(sizes)
+    vocab = [1000] * f
+    tabs, flat, offs = make_table(vocab, d, seed=31)
+    idx = make_idx(vocab, b, seed=32)
+    idx[1::2] = idx[0::2]                                   # every odd row duplicates the even row before it
+    g = np.random.default_rng(33)
+    fns = L.cin_field_nums(f, sizes, False)
+    wcat = np.concatenate([(g.normal(size=(f * fns[k], s)) / np.sqrt(f * fns[k])).astype(np.float32).reshape(-1)
+                           for k, s in enumerate(sizes)])
+    d_tab, d_offs, d_w = dev(flat), dev(offs), dev(wcat)
+
+    def run(ix, precision, rows):
+        pooled = torch.empty(rows, 256, device='cuda')
+        ws_bytes = nat.lib.dtb_cin_workspace_bytes(rows, f, d, sizes_c, 3, 0, 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+        nat.check(nat.lib.dtb_cin_fwd(P(dev(ix)), P(d_tab), P(d_offs), P(d_w), None, P(pooled), None, P(ws), ws_bytes,
+                                      rows, f, d, sizes_c, 3, 0, 1, precision, None, None))
+        return pooled
+    out = run(idx, 2, b)
+    assert torch.equal(out[0::2], out[1::2])
+    perm = np.random.default_rng(34).permutation(b)
+    out_p = run(idx[perm], 2, b)
+    assert torch.equal(out_p, out[torch.as_tensor(perm, device='cuda')])
+    sample = np.arange(0, b, 97)[:512]
+    ref = run(idx[sample], 1, len(sample))
+    scale = float(ref.abs().max())
+    torch.testing.assert_close(out[torch.as_tensor(sample, device='cuda')], ref, rtol=1e-3, atol=1e-4 * scale)
