@@ -30,7 +30,6 @@ namespace dtb {
 constexpr int kMaxL = 128;      // feature maps per layer (UMMA N)
 constexpr int kMaxHp = 64;      // padded hidden fields per layer (K chunk)
 constexpr int kTcThreads = 320;
-constexpr int kStagesA = 2;
 constexpr int kAccCols = 128;   // TMEM columns per accumulator tile
 constexpr int kTmemCols = 512;
 
@@ -50,6 +49,7 @@ struct CinTcParams {
   unsigned long long saved_off[kCinMaxLayers];   // float offset of T_k inside saved
   unsigned long long bias_off[kCinMaxLayers];
   int b_stage_bytes;                              // bytes reserved per weight stage in smem
+  int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -81,48 +81,62 @@ __global__ void cin_tc_pack_kernel(const float* __restrict__ w, uint8_t* __restr
 // ------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------
+// A pipeline granule ("sub-chunk") = one x0 field i x 32 hidden fields j = two K=16 UMMA steps.
+// A operand of a granule in TMEM: 16 columns hi + 16 columns lo per tile; kStagesA granules x 2 tiles
+// in flight = 256 columns, next to the two 128-column accumulators.  The weight chunk of field i (all
+// Hp hidden fields, hi+lo, <= 32 KB) is one bulk copy and serves both tiles and both granules.
+constexpr int kSubK = 32;
+constexpr int kStagesA = 4;
+constexpr int kStagesB = 4;
+constexpr int kACols = kSubK / 2;                 // TMEM columns of one bf16 [128 x 32] operand block
+
 struct TcSmemLayout {
-  int b_off, a_off, x0_off, bar_off, total;
+  int b_off, x0_off, bar_off, total;
 };
 
-template <bool kATmem>
-__host__ __device__ inline TcSmemLayout tc_layout(int b_stage_bytes, int F, int D) {
-  const int stages_b = kATmem ? 4 : 2;
+__host__ __device__ inline TcSmemLayout tc_layout(int b_stage_bytes, int F) {
   TcSmemLayout l;
   l.b_off = 0;
-  l.a_off = stages_b * b_stage_bytes;
-  const int a_bytes = kATmem ? 0 : kStagesA * 2 * (2 * 128 * kMaxHp * 2);   // [stage][tile][hi|lo]
-  l.x0_off = l.a_off + a_bytes;
-  l.bar_off = l.x0_off + 2 * 128 * F * 4;                                    // x0s[tile][r][i][d]
+  l.x0_off = kStagesB * b_stage_bytes;
+  l.bar_off = l.x0_off + 2 * 128 * F * 4;          // x0s[tile][r][i][d]
   l.bar_off = (l.bar_off + 15) / 16 * 16;
   l.total = l.bar_off + 256;
   return l;
 }
 
-template <int D, bool kATmem>
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int D>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_constant__ CinTcParams p) {
   constexpr int R = 128 / D;                 // batch rows per M=128 tile
-  constexpr int kStagesB = kATmem ? 4 : 2;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const TcSmemLayout lay = tc_layout<kATmem>(p.b_stage_bytes, p.F, D);
+  const TcSmemLayout lay = tc_layout(p.b_stage_bytes, p.F);
   uint8_t* smem_b = smem + lay.b_off;
-  uint8_t* smem_a = smem + lay.a_off;
   float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
-  uint64_t* full_a = bars;                        // [tile][stage] -> 4
-  uint64_t* empty_a = bars + 4;                   // [stage]       -> 2
-  uint64_t* full_b = bars + 6;                    // [stage]       -> 4
-  uint64_t* empty_b = bars + 10;                  // [stage]       -> 4
-  uint64_t* acc_full = bars + 14;                 // [tile]        -> 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* full_a = bars;                        // [tile][stage] -> 8
+  uint64_t* empty_a = bars + 8;                   // [stage]       -> 4
+  uint64_t* full_b = bars + 12;                   // [stage]       -> 4
+  uint64_t* empty_b = bars + 16;                  // [stage]       -> 4
+  uint64_t* acc_full = bars + 20;                 // [tile]        -> 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = p.F;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
 
   if (threadIdx.x == 0) {
-    for (int g = 0; g < 2; ++g)
-      for (int s = 0; s < kStagesA; ++s) tc::mbar_init(&full_a[g * kStagesA + s], 128);
+    for (int i = 0; i < 2 * kStagesA; ++i) tc::mbar_init(&full_a[i], 4);   // one arrival per producer warp
     for (int s = 0; s < kStagesA; ++s) tc::mbar_init(&empty_a[s], 1);
     for (int s = 0; s < kStagesB; ++s) {
       tc::mbar_init(&full_b[s], 1);
@@ -145,13 +159,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
     const int r = t / D, d = t % D;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float* x0g = x0s + (size_t)g * 128 * F;         // [r][i][d]
-    uint32_t chunk = 0, layer_cnt = 0;
+    uint32_t gran = 0, layer_cnt = 0;
     float h[kMaxHp];
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       const int row0 = (st * 2 + g) * R;
       const int b = row0 + r;
       // ---- gather this tile's x0 block: R rows x F fields x D floats, 16-byte pieces ----------
-      if constexpr (D % 4 == 0) {
+      {
         constexpr int Q = D / 4;
         for (int e = t; e < R * F * Q; e += 128) {
           const int rr = e / (F * Q);
@@ -175,49 +189,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
       }
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
-        for (int i = 0; i < F; ++i, ++chunk) {
-          const uint32_t sa = chunk % kStagesA, pa = (chunk / kStagesA) & 1;
-          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+        for (int i = 0; i < F; ++i) {
           const float xi = x0g[((size_t)r * F + i) * D + d];
-          if constexpr (kATmem) {
-            tc::fence_after_thread_sync();
-            const uint32_t a_col = 2 * kAccCols + ((sa * 2 + g) * 2) * (kMaxHp / 2);
 #pragma unroll
-            for (int jb = 0; jb < kMaxHp / 16; ++jb) {
-              if (jb * 16 < Hp) {
-                uint32_t hi[8], lo[8];
+          for (int half = 0; half < kMaxHp / kSubK; ++half) {
+            if (half * kSubK < Hp) {
+              const uint32_t sa = gran % kStagesA, pa = (gran / kStagesA) & 1;
+              ++gran;
+              // 32 products of this granule -> packed bf16x2 hi / lo (all computed before the async
+              // tcgen05.st are issued, so every store reads registers of its own)
+              uint32_t zh[kACols], zl[kACols];
+              if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  tc::split_bf16x2(xi * h[jb * 16 + 2 * q], xi * h[jb * 16 + 2 * q + 1], hi[q], lo[q]);
-                tc::tmem_st8(tmem_base + lane_base + a_col + jb * 8, hi);
-                if (p.n_pass > 1) tc::tmem_st8(tmem_base + lane_base + a_col + kMaxHp / 2 + jb * 8, lo);
+                for (int q = 0; q < kACols; ++q)
+                  tc::split_bf16x2(xi * h[half * kSubK + 2 * q], xi * h[half * kSubK + 2 * q + 1], zh[q], zl[q]);
               }
-            }
-            tc::tmem_wait_st();
-            tc::fence_before_thread_sync();
-          } else {
-            uint8_t* a_hi = smem_a + (size_t)((sa * 2 + g) * 2) * (128 * kMaxHp * 2);
-            uint8_t* a_lo = a_hi + 128 * kMaxHp * 2;
-            const int row_off = (t >> 3) * 128 + (t & 7) * 16;
-#pragma unroll
-            for (int jb = 0; jb < kMaxHp / 16; ++jb) {
-              if (jb * 16 < Hp) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  tc::split_bf16x2(xi * h[jb * 16 + 2 * q], xi * h[jb * 16 + 2 * q + 1], hi[q], lo[q]);
-                // 16 K-elements = two 16-byte core-matrix rows (K cores 2*jb and 2*jb+1)
-                *reinterpret_cast<uint4*>(a_hi + (2 * jb) * 2048 + row_off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(a_hi + (2 * jb + 1) * 2048 + row_off) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+              tc::mbar_wait(&empty_a[sa], pa ^ 1);
+              tc::fence_after_thread_sync();
+              if (!(p.dbg & 1)) {
+                const uint32_t a_col = tmem_base + lane_base + 2 * kAccCols + ((sa * 2 + g) * 2) * kACols;
+                tc::tmem_st8v(a_col, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
+                tc::tmem_st8v(a_col + 8, zh[8], zh[9], zh[10], zh[11], zh[12], zh[13], zh[14], zh[15]);
                 if (p.n_pass > 1) {
-                  *reinterpret_cast<uint4*>(a_lo + (2 * jb) * 2048 + row_off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                  *reinterpret_cast<uint4*>(a_lo + (2 * jb + 1) * 2048 + row_off) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                  tc::tmem_st8v(a_col + kACols, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
+                  tc::tmem_st8v(a_col + kACols + 8, zl[8], zl[9], zl[10], zl[11], zl[12], zl[13], zl[14], zl[15]);
                 }
+                tc::tmem_wait_st();
               }
+              tc::fence_before_thread_sync();
+              __syncwarp();
+              if (lane == 0) tc::mbar_arrive(&full_a[g * kStagesA + sa]);
             }
-            tc::fence_proxy_async_smem();
           }
-          tc::mbar_arrive(&full_a[g * kStagesA + sa]);
         }
         // ---- epilogue of layer k: this thread's accumulator row -> bias/act -> h / pooled / saved
         tc::mbar_wait(&acc_full[g], layer_cnt & 1);
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
         float* sv = (p.saved && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
 #pragma unroll
         for (int cb = 0; cb < kMaxL / 16; ++cb) {
-          if (cb * 16 < L) {
+          if (cb * 16 < L && !(p.dbg & 4)) {
             uint32_t v[16];
             tc::tmem_ld16(tmem_base + lane_base + g * kAccCols + cb * 16, v);
             tc::tmem_wait_ld();
@@ -248,17 +251,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(sv + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
-            // sum over the D lanes that share a batch row (xor-shuffle inside D-aligned lane groups)
+            // sum over the D lanes that share a batch row.  Reduce-scatter butterfly: at offset `off` a
+            // lane keeps the half of its live columns selected by its bit `off` and adds the partner's
+            // copy of that half, so after log2(D) steps lane d holds the total of column (block + d):
+            // D-1 shuffles per D columns instead of D*log2(D), and a coalesced store.
+            if constexpr (D <= 16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = cb * 16 + j;
-              if (col >= pool_lo && col < pool_lo + pool_n) {      // warp-uniform
-                float s = o[j];
+              for (int blk = 0; blk < 16 / D; ++blk) {
+                const int col0 = cb * 16 + blk * D;
+                if (col0 + D > pool_lo && col0 < pool_lo + pool_n) {     // warp-uniform
+                  float w[D];
 #pragma unroll
-                for (int off = 1; off < D && off < 32; off <<= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-                if (D > 32) {   // not instantiated (D <= 32 supported)
+                  for (int j = 0; j < D; ++j) w[j] = o[blk * D + j];
+#pragma unroll
+                  for (int off = D / 2; off >= 1; off >>= 1) {
+                    const bool up = (d & off) != 0;
+#pragma unroll
+                    for (int j = 0; j < off; ++j) {
+                      const float send = up ? w[j] : w[j + off];
+                      const float keep = up ? w[j + off] : w[j];
+                      w[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                  }
+                  const int col = col0 + d;
+                  if (b < p.B && col >= pool_lo && col < pool_lo + pool_n)
+                    p.pooled[(size_t)b * p.P + p.pcol0[k] + (col - pool_lo)] = w[0];
                 }
-                if (d == 0 && b < p.B) p.pooled[(size_t)b * p.P + p.pcol0[k] + (col - pool_lo)] = s;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = cb * 16 + j;
+                if (col >= pool_lo && col < pool_lo + pool_n) {      // warp-uniform
+                  float sum = o[j];
+#pragma unroll
+                  for (int off = 1; off < 32; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                  if (d == 0 && b < p.B) p.pooled[(size_t)b * p.P + p.pcol0[k] + (col - pool_lo)] = sum;
+                }
               }
             }
           }
@@ -275,48 +304,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
     }
   } else if (warp == 8) {
     // ================================ MMA issuer ===============================================
-    if (lane == 0) {
-      uint32_t chunk = 0;
-      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
-        for (int k = 0; k < p.n_layers; ++k) {
-          const int Hp = p.Hp[k], L = p.L[k];
-          const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)L);
-          const uint32_t lbo_b = (uint32_t)(L >> 3) * 128;       // K-direction core stride of the W image
-          const uint32_t img_b = (uint32_t)L * Hp * 2;           // bytes of one (hi or lo) image
-          for (int i = 0; i < F; ++i, ++chunk) {
-            const uint32_t sa = chunk % kStagesA, pa = (chunk / kStagesA) & 1;
-            const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
-            tc::mbar_wait(&full_b[sb], pb);
-            const uint32_t b_addr = tc::smem_u32(smem_b + (size_t)sb * p.b_stage_bytes);
+    // The whole warp walks the schedule (warp-uniform values -> uniform registers); one elected lane
+    // issues the tcgen05 instructions.
+    const bool leader = elect_one_sync();
+    const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
+    uint32_t gran = 0, chunk = 0;
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int k = 0; k < p.n_layers; ++k) {
+        const int Hp = p.Hp[k], L = p.L[k];
+        const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)L);
+        const uint32_t lbo_b = (uint32_t)(L >> 3) * 128;       // K-direction core stride of the W image
+        const uint32_t img_b = (uint32_t)L * Hp * 2;           // bytes of one (hi or lo) image
+        // static part of the W descriptor: LBO, SBO = 128 B, version 1, no swizzle
+        const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        const int n_pass = (p.dbg & 2) ? 0 : p.n_pass;
+        for (int i = 0; i < F; ++i, ++chunk) {
+          const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+          tc::mbar_wait(&full_b[sb], pb);
+          const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
+          for (int half = 0; half * kSubK < Hp; ++half, ++gran) {
+            const uint32_t sa = gran % kStagesA, pa = (gran / kStagesA) & 1;
+            const bool last = (i == F - 1) && ((half + 1) * kSubK >= Hp);
+#pragma unroll
             for (int g = 0; g < 2; ++g) {
               tc::mbar_wait(&full_a[g * kStagesA + sa], pa);
               tc::fence_after_thread_sync();
-              const uint32_t d_tmem = tmem_base + g * kAccCols;
-              for (int pass = 0; pass < p.n_pass; ++pass) {
-                // pass 0: A_hi*B_hi ; 1: A_lo*B_hi ; 2: A_hi*B_lo
-                const int a_lo = (pass == 1), b_lo = (pass == 2);
-                for (int ks = 0; ks < Hp / 16; ++ks) {
-                  const uint32_t acc = (i | pass | ks) != 0;
-                  const uint64_t desc_b = tc::make_smem_desc(b_addr + b_lo * img_b + ks * 2 * lbo_b, lbo_b, 128);
-                  if constexpr (kATmem) {
-                    const uint32_t a_col = 2 * kAccCols + ((sa * 2 + g) * 2 + a_lo) * (kMaxHp / 2) + ks * 8;
-                    tc::mma_ts(d_tmem, tmem_base + a_col, desc_b, idesc, acc);
-                  } else {
-                    const uint32_t a_addr =
-                        tc::smem_u32(smem_a + (size_t)((sa * 2 + g) * 2 + a_lo) * (128 * kMaxHp * 2)) + ks * 4096;
-                    tc::mma_ss(d_tmem, tc::make_smem_desc(a_addr, 2048, 128), desc_b, idesc, acc);
+              if (leader) {
+                const uint32_t d_tmem = tmem_base + g * kAccCols;
+                const uint32_t a_base = tmem_base + 2 * kAccCols + ((sa * 2 + g) * 2) * kACols;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                  if (pass < n_pass) {
+                    // pass 0: A_hi*B_hi ; 1: A_lo*B_hi ; 2: A_hi*B_lo
+                    const uint32_t a_addr = a_base + (pass == 1 ? kACols : 0);
+                    const uint32_t b_img = b_addr + (pass == 2 ? img_b : 0) + (uint32_t)half * 4 * lbo_b;
+#pragma unroll
+                    for (int ks = 0; ks < kSubK / 16; ++ks) {
+                      const uint32_t acc = (uint32_t)((i | half | pass | ks) != 0);
+                      const uint64_t desc_b = desc_hi | (uint64_t)(((b_img + ks * 2 * lbo_b) >> 4) & 0x3FFF);
+                      tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, acc);
+                    }
                   }
                 }
+                if (last) tc::mma_commit(&acc_full[g]);
               }
-              if (i == F - 1) tc::mma_commit(&acc_full[g]);
+              __syncwarp();
             }
-            tc::mma_commit(&empty_a[sa]);
-            tc::mma_commit(&empty_b[sb]);
+            if (leader) tc::mma_commit(&empty_a[sa]);
+            __syncwarp();
           }
+          if (leader) tc::mma_commit(&empty_b[sb]);
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // ================================ weight loader ============================================
     if (lane == 0) {
@@ -429,7 +470,8 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int g_tc_variant = 1;   // 1: A operand through TMEM (default), 0: through shared memory
+static int g_tc_variant = 1;
+static int g_tc_dbg = 0;   // 1: A operand through TMEM (default), 0: through shared memory
 
 static bool d_supported(int D) { return D == 4 || D == 8 || D == 16 || D == 32; }
 
@@ -438,21 +480,20 @@ bool cin_tc_supported(const CinShape& s) {
   if (s.F > kMaxHp || s.F < 1) return false;
   for (int k = 0; k < s.n_layers; ++k) {
     if (s.L[k] % 16 || s.L[k] > kMaxL) return false;
-    if (round_up(s.H[k], 16) > kMaxHp) return false;
+    if (round_up(s.H[k], kSubK) > kMaxHp) return false;
   }
   // shared-memory budget of the default variant
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
-    const int bytes = 4 * s.L[k] * round_up(s.H[k], 16);
+    const int bytes = 4 * s.L[k] * round_up(s.H[k], kSubK);
     if (bytes > bstage) bstage = bytes;
   }
-  const TcSmemLayout lay = g_tc_variant ? tc_layout<true>(bstage, s.F, s.D) : tc_layout<false>(bstage, s.F, s.D);
-  return lay.total <= 227 * 1024;
+  return tc_layout(bstage, s.F).total <= 227 * 1024;
 }
 
 static size_t wpack_bytes(const CinShape& s) {
   size_t b = 0;
-  for (int k = 0; k < s.n_layers; ++k) b += (size_t)s.F * s.L[k] * round_up(s.H[k], 16) * 4;
+  for (int k = 0; k < s.n_layers; ++k) b += (size_t)s.F * s.L[k] * round_up(s.H[k], kSubK) * 4;
   return b;
 }
 
@@ -464,9 +505,9 @@ size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
   return fwd > bwd ? fwd : bwd;
 }
 
-template <int D, bool kATmem>
+template <int D>
 static int launch_fwd(const CinTcParams& p, int smem_bytes, cudaStream_t st) {
-  auto kern = cin_tc_fwd_kernel<D, kATmem>;
+  auto kern = cin_tc_fwd_kernel<D>;
   DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int R = 128 / D;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
@@ -496,7 +537,7 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   size_t woff = 0, soff = (size_t)B * s.D * s.F;
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
-    p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], 16);
+    p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], kSubK);
     p.pool_lo[k] = s.pool_lo[k]; p.pool_n[k] = s.pool_n[k]; p.pcol0[k] = s.pcol0[k];
     p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
     p.wpack_off[k] = woff;
@@ -515,11 +556,11 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
     if ((int)chunk > bstage) bstage = (int)chunk;
   }
   p.b_stage_bytes = bstage;
-  const bool a_tmem = g_tc_variant != 0;
-  const TcSmemLayout lay = a_tmem ? tc_layout<true>(bstage, s.F, s.D) : tc_layout<false>(bstage, s.F, s.D);
-#define DTB_TC_LAUNCH(DD)                                                          \
-  case DD:                                                                         \
-    return a_tmem ? launch_fwd<DD, true>(p, lay.total, st) : launch_fwd<DD, false>(p, lay.total, st);
+  p.dbg = g_tc_dbg;
+  const TcSmemLayout lay = tc_layout(bstage, s.F);
+#define DTB_TC_LAUNCH(DD) \
+  case DD:                \
+    return launch_fwd<DD>(p, lay.total, st);
   switch (s.D) {
     DTB_TC_LAUNCH(4)
     DTB_TC_LAUNCH(8)
@@ -550,7 +591,8 @@ extern "C" {
 
 // test hooks (declared in include/deeptables_b200.h)
 int dtb_cin_tc_set_variant(int a_operand_in_tmem) {
-  g_tc_variant = a_operand_in_tmem ? 1 : 0;
+  g_tc_dbg = (a_operand_in_tmem >> 8) & 0xff;     // profiling switches ride in bits 8..15
+  g_tc_variant = (a_operand_in_tmem & 0xff) ? 1 : 0;
   return DTB_OK;
 }
 

