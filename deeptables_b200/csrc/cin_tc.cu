@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(160, 1) tc_selftest_kernel(const float* __rest
 // host side
 // ------------------------------------------------------------------------------------------
 static int g_tc_variant = 1;
-static int g_tc_dbg = 0;   // 1: A operand through TMEM (default), 0: through shared memory
+static int g_tc_dbg = 0;
+static int g_tc_bwd_fp32 = 0;   // test hook: run the exact-fp32 backward after the tensor-core forward   // 1: A operand through TMEM (default), 0: through shared memory
 
 static bool d_supported(int D) { return D == 4 || D == 8 || D == 16 || D == 32; }
 
@@ -499,10 +500,15 @@ static size_t wpack_bytes(const CinShape& s) {
 
 size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B); }
 
+size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B);
 size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
-  size_t fwd = wpack_bytes(s) + 1024;
-  size_t bwd = training ? cin_fp32_workspace_bytes(s, B, 1) : 0;   // backward: fp32 formulation (this round)
-  return fwd > bwd ? fwd : bwd;
+  size_t need = wpack_bytes(s) + 1024;
+  if (training) {
+    const size_t a = cin_tc_bwd_workspace_bytes(s, B), b = cin_fp32_workspace_bytes(s, B, 1);
+    need = need > a ? need : a;
+    need = need > b ? need : b;     // the exact-fp32 backward stays selectable (tests, unsupported shapes)
+  }
+  return need;
 }
 
 template <int D>
@@ -573,16 +579,6 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
 #undef DTB_TC_LAUNCH
 }
 
-int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
-               const float* weights, const float* d_pooled, const void* saved, float* grad_table,
-               float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
-               int n_pass, cudaStream_t st) {
-  (void)n_pass;
-  // The forward kernel saved x0t / T_k in the fp32 path's layout: the exact-fp32 backward consumes it.
-  return cin_fp32_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
-                      workspace, workspace_bytes, B, act, st);
-}
-
 }  // namespace dtb
 
 using namespace dtb;
@@ -592,6 +588,7 @@ extern "C" {
 // test hooks (declared in include/deeptables_b200.h)
 int dtb_cin_tc_set_variant(int a_operand_in_tmem) {
   g_tc_dbg = (a_operand_in_tmem >> 8) & 0xff;     // profiling switches ride in bits 8..15
+  g_tc_bwd_fp32 = (a_operand_in_tmem >> 16) & 1;  // bit 16: exact-fp32 backward
   g_tc_variant = (a_operand_in_tmem & 0xff) ? 1 : 0;
   return DTB_OK;
 }
@@ -617,3 +614,695 @@ int dtb_tc_selftest(const float* A, const float* Bmat, float* C, void* workspace
 }
 
 }  // extern "C"
+
+// ==========================================================================================
+// Backward on the tensor cores
+// ==========================================================================================
+// dgrad (per 2 x 128-row super tile, layers last -> first):
+//   dC_k = (d_pooled part + dh_{k+1}) * act'(T_k)            [thread-local: row m = (b,d)]
+//   dZ_{k,i}[m, j] = sum_l dC_k[m,l] W_k[(i,j), l]           [UMMA: A = dC (TMEM, written once per layer),
+//                                                             B = W_{k,i} K-major in l, N = Hp, K = L]
+//   dx0[m,i] += sum_j dZ[m,j] h_k[m,j] ;  dh_k[m,j] += dZ[m,j] x0[m,i]     [epilogue, registers]
+//   dC_k is also written to HBM as bf16 hi/lo MN-major tiles for the wgrad kernel.
+// wgrad (per layer, grid = i-tile pairs x row splits):
+//   dW_k[(i,j), l] = sum_m x0[m,i] h_k[m,j] dC_k[m,l]        [UMMA: A[(i,j), m] built in TMEM from smem tiles
+//                                                             of x0t / h_k, B = dC tiles (MN-major, bulk copy)]
+namespace dtb {
+
+struct CinTcBwdParams {
+  const int32_t* idx;
+  const float* table;
+  const int64_t* row_offsets;
+  const uint8_t* wpack;       // transposed pack (B[n=j][k=l])
+  const float* d_pooled;
+  const float* saved;
+  float* grad_table;
+  uint8_t* dc_tiles;
+  int B, F, n_layers, act, n_pass, P;
+  int L[kCinMaxLayers], H[kCinMaxLayers], Hp[kCinMaxLayers];
+  int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
+  unsigned long long wpack_off[kCinMaxLayers], saved_off[kCinMaxLayers], dc_off[kCinMaxLayers];
+  int b_stage_bytes;
+};
+
+// weights -> per chunk i: [hi | lo] image of B[n=j][k=l] = W[(i*H + j), l], canonical K-major no swizzle
+__global__ void cin_tc_pack_t_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
+                                     int L) {
+  const int64_t per_chunk = (int64_t)L * Hp;
+  const int64_t total = per_chunk * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / per_chunk);
+    const int rem = (int)(t - (int64_t)i * per_chunk);
+    const int j = rem / L, l = rem - j * L;       // l fastest: coalesced reads
+    const float v = j < H ? w[((int64_t)i * H + j) * L + l] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const int64_t off = ((int64_t)(l >> 3) * (Hp >> 3) + (j >> 3)) * 128 + (j & 7) * 16 + (l & 7) * 2;
+    uint8_t* base = out + (int64_t)i * per_chunk * 4;
+    *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(base + per_chunk * 2 + off) = lo;
+  }
+}
+
+struct TcBwdSmemLayout {
+  int b_off, x0_off, dx_off, bar_off, total;
+};
+__host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int F) {
+  TcBwdSmemLayout l;
+  l.b_off = 0;
+  l.x0_off = kStagesB * b_stage_bytes;
+  l.dx_off = l.x0_off + 2 * 128 * F * 4;
+  l.bar_off = l.dx_off + 2 * 128 * F * 4;
+  l.bar_off = (l.bar_off + 15) / 16 * 16;
+  l.total = l.bar_off + 256;
+  return l;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
+  constexpr int R = 128 / D;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TcBwdSmemLayout lay = tc_bwd_layout(p.b_stage_bytes, p.F);
+  uint8_t* smem_b = smem + lay.b_off;
+  float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
+  float* dxs = reinterpret_cast<float*>(smem + lay.dx_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* a_ready = bars;          // [tile]            2
+  uint64_t* full_b = bars + 2;       // [stage]           4
+  uint64_t* empty_b = bars + 6;      // [stage]           4
+  uint64_t* acc_full = bars + 10;    // [tile][buf]       4
+  uint64_t* acc_empty = bars + 14;   // [tile][buf]       4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = p.F;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&a_ready[0], 4);
+    tc::mbar_init(&a_ready[1], 4);
+    for (int s = 0; s < kStagesB; ++s) {
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty_b[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;
+    const int r = t / D, d = t % D;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_tile = tmem_base + lane_base + g * 256;   // A: [0,64) hi [64,128) lo ; acc: 128 + buf*64
+    float* x0g = x0s + (size_t)g * 128 * F;    // [r][i][d]
+    float* dxg = dxs + (size_t)g * 128 * F;    // [i][t]
+    uint32_t acc_cnt = 0;
+    float h[kMaxHp], dh[kMaxHp];
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int row0 = (st * 2 + g) * R;
+      const int b = row0 + r;
+      const bool valid = b < p.B;
+      const size_t m_pad = (size_t)(st * 2 + g) * 128 + t;    // == b*D + d
+      {
+        constexpr int Q = D / 4;
+        for (int e = t; e < R * F * Q; e += 128) {
+          const int rr = e / (F * Q);
+          const int rem = e - rr * F * Q;
+          const int i = rem / Q, q = rem - i * Q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + rr < p.B) {
+            const int64_t rb = table_row(p.row_offsets, i, __ldg(p.idx + (int64_t)(row0 + rr) * F + i), D, nullptr);
+            if (rb >= 0) v = ldg_stream_f4(p.table + rb + (q << 2));
+          }
+          *reinterpret_cast<float4*>(x0g + ((size_t)rr * F + i) * D + (q << 2)) = v;
+        }
+        for (int i = 0; i < F; ++i) dxg[i * 128 + t] = 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+#pragma unroll
+      for (int j = 0; j < kMaxHp; ++j) dh[j] = 0.f;
+      for (int k = p.n_layers - 1; k >= 0; --k) {
+        const int L = p.L[k], Hp = p.Hp[k];
+        const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
+        // ---- dC_k row -> TMEM A operand (hi|lo) + HBM tiles for wgrad ---------------------------
+        const float* Trow = p.saved + p.saved_off[k] + m_pad * L;
+        const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
+        uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
+#pragma unroll
+        for (int cb = 0; cb < kMaxL / 16; ++cb) {
+          if (cb * 16 < L) {
+            float tv[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 q4 = valid ? *reinterpret_cast<const float4*>(Trow + cb * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              tv[j] = q4.x; tv[j + 1] = q4.y; tv[j + 2] = q4.z; tv[j + 3] = q4.w;
+            }
+            float dc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = cb * 16 + j;
+              float gsum = 0.f;
+              if (valid && col >= pool_lo && col < pool_lo + pool_n) gsum = __ldg(dprow + (col - pool_lo));
+              if (col < kMaxHp) {
+                if (col < hid_n) gsum += dh[col];
+              }
+              if (p.act == DTB_ACT_RELU && !(tv[j] > 0.f)) gsum = 0.f;
+              dc[j] = valid ? gsum : 0.f;
+            }
+            uint32_t zh[8], zl[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tc::split_bf16x2(dc[2 * q], dc[2 * q + 1], zh[q], zl[q]);
+            tc::tmem_st8v(t_tile + cb * 8, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
+            tc::tmem_st8v(t_tile + 64 + cb * 8, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
+            *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+            *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
+            *reinterpret_cast<uint4*>(dcblk + 32 * L + (cb * 2) * 256) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
+            *reinterpret_cast<uint4*>(dcblk + 32 * L + (cb * 2 + 1) * 256) = make_uint4(zl[4], zl[5], zl[6], zl[7]);
+            tc::tmem_wait_st();
+          }
+        }
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&a_ready[g]);
+        // ---- h_k (this row's slice) and a fresh dh accumulator ------------------------------------
+        if (k > 0) {
+          const int Hk = p.H[k];
+          const float* prow = p.saved + p.saved_off[k - 1] + m_pad * p.L[k - 1];
+#pragma unroll
+          for (int j = 0; j < kMaxHp; j += 4) {
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && j < Hk) q4 = *reinterpret_cast<const float4*>(prow + j);   // H_k is a multiple of 4 (L/2, L % 16 == 0)
+            h[j] = q4.x; h[j + 1] = q4.y; h[j + 2] = q4.z; h[j + 3] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kMaxHp; ++j) h[j] = (j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxHp; ++j) dh[j] = 0.f;
+        for (int i = 0; i < F; ++i) {
+          const uint32_t buf = acc_cnt & 1, par = (acc_cnt >> 1) & 1;
+          ++acc_cnt;
+          const float xi = x0g[((size_t)r * F + i) * D + d];
+          tc::mbar_wait(&acc_full[g * 2 + buf], par);
+          tc::fence_after_thread_sync();
+          float dx = 0.f;
+#pragma unroll
+          for (int cb = 0; cb < kMaxHp / 16; ++cb) {
+            if (cb * 16 < Hp) {
+              uint32_t v[16];
+              tc::tmem_ld16(t_tile + 128 + buf * 64 + cb * 16, v);
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float dz = __uint_as_float(v[j]);
+                dx = fmaf(dz, h[cb * 16 + j], dx);
+                dh[cb * 16 + j] = fmaf(dz, xi, dh[cb * 16 + j]);
+              }
+            }
+          }
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[g * 2 + buf]);
+          dxg[i * 128 + t] += dx;
+        }
+        if (k == 0) {
+#pragma unroll
+          for (int j = 0; j < kMaxHp; ++j)
+            if (j < F) dxg[j * 128 + t] += dh[j];     // h_0 is x0 itself
+        }
+      }
+      // ---- scatter dx0 of this tile into the embedding gradient ------------------------------------
+      if (valid) {
+        for (int i = 0; i < F; ++i) {
+          const int64_t rb = table_row(p.row_offsets, i, __ldg(p.idx + (int64_t)b * F + i), D, nullptr);
+          if (rb >= 0) atomicAdd(p.grad_table + rb + d, dxg[i * 128 + t]);
+        }
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+    }
+  } else if (warp == 8) {
+    const bool leader = elect_one_sync();
+    const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
+    uint32_t chunk = 0, cnt0 = 0, cnt1 = 0, layer_cnt = 0;
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
+        const int Hp = p.Hp[k], L = p.L[k];
+        const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)Hp);
+        const uint32_t lbo_b = (uint32_t)(Hp >> 3) * 128;
+        const uint32_t img_b = (uint32_t)L * Hp * 2;
+        const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        for (int i = 0; i < F; ++i, ++chunk) {
+          const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+          tc::mbar_wait(&full_b[sb], pb);
+          const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (i == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
+            const uint32_t c = g ? cnt1 : cnt0;
+            const uint32_t buf = c & 1, par = (c >> 1) & 1;
+            if (g) ++cnt1; else ++cnt0;
+            tc::mbar_wait(&acc_empty[g * 2 + buf], par ^ 1);
+            tc::fence_after_thread_sync();
+            if (leader) {
+              const uint32_t a_base = tmem_base + g * 256;
+              const uint32_t d_tmem = a_base + 128 + buf * 64;
+#pragma unroll
+              for (int pass = 0; pass < 3; ++pass) {
+                if (pass < p.n_pass) {
+                  const uint32_t a_addr = a_base + (pass == 1 ? 64 : 0);
+                  const uint32_t b_img = b_addr + (pass == 2 ? img_b : 0);
+#pragma unroll
+                  for (int ks = 0; ks < kMaxL / 16; ++ks) {
+                    if (ks * 16 < L) {
+                      const uint64_t desc_b = desc_hi | (uint64_t)(((b_img + ks * 2 * lbo_b) >> 4) & 0x3FFF);
+                      tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, (uint32_t)((pass | ks) != 0));
+                    }
+                  }
+                }
+              }
+              tc::mma_commit(&acc_full[g * 2 + buf]);
+            }
+            __syncwarp();
+          }
+          if (leader) tc::mma_commit(&empty_b[sb]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t chunk = 0;
+      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int k = p.n_layers - 1; k >= 0; --k) {
+          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * (p.n_pass > 1 ? 2 : 1);
+          const uint32_t stride = (uint32_t)p.L[k] * p.Hp[k] * 4;
+          const uint8_t* src = p.wpack + p.wpack_off[k];
+          for (int i = 0; i < F; ++i, ++chunk) {
+            const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+            tc::mbar_wait(&empty_b[sb], pb ^ 1);
+            tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
+            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[sb]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// wgrad kernel (one launch per layer)
+// ------------------------------------------------------------------------------------------
+constexpr int kWgThreads = 384;     // warps 0-3 / 4-7: A producers of tile 0 / 1 (+ final epilogue), 8: MMA, 9: dC bulk loader,
+                                    // 10-11: h / x0 tile loaders
+constexpr int kWgStageRows = 64;    // GEMM-K (batch x dim rows) per pipeline stage = 4 UMMA k-steps
+constexpr int kWgStages = 3;
+constexpr int kWgStagesA = 2;
+
+struct CinTcWgradParams {
+  const float* x0t;          // [M_pad, F]
+  const float* hsrc;         // [M_pad, ldh] (T_{k-1}, or x0t for layer 0)
+  const uint8_t* dc_tiles;   // layer k blocks of 16 rows: [hi 32*L B | lo 32*L B]
+  float* d_w;                // [F*H, L] accumulate
+  int ldh, F, H, Hp, L, n_pass;
+  int m_valid;               // rows (b,d) that exist: B*D
+  int n_stage_total;         // ceil(M_pad / 64)
+  int stages_per_split;
+};
+
+struct WgSmemLayout {
+  int b_off, h_off, x_off, bar_off, total, b_bytes, h_bytes, x_bytes;
+};
+__host__ __device__ inline WgSmemLayout wg_layout(int L, int Hp, int F) {
+  WgSmemLayout l;
+  l.b_bytes = 4 * 64 * L;                       // 4 blocks of 16 rows, hi + lo
+  l.h_bytes = kWgStageRows * Hp * 4;
+  l.x_bytes = (kWgStageRows * F * 4 + 15) / 16 * 16;
+  l.b_off = 0;
+  l.h_off = kWgStages * l.b_bytes;
+  l.x_off = l.h_off + kWgStages * l.h_bytes;
+  l.bar_off = l.x_off + kWgStages * l.x_bytes;
+  l.total = l.bar_off + 256;
+  return l;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __grid_constant__ CinTcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const WgSmemLayout lay = wg_layout(p.L, p.Hp, p.F);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* full_b = bars;            // [stage] 3   dC tiles landed (tx)
+  uint64_t* empty_b = bars + 3;       // [stage] 3   MMA done with the dC tiles
+  uint64_t* full_h = bars + 6;        // [stage] 3   h / x0 tiles written (2 loader warps)
+  uint64_t* empty_h = bars + 9;       // [stage] 3   all 8 producer warps done reading them
+  uint64_t* full_a = bars + 12;       // [tile][stageA] 4
+  uint64_t* empty_a = bars + 16;      // [stageA] 2
+  uint64_t* acc_done = bars + 18;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = p.F, H = p.H, Hp = p.Hp, L = p.L;
+  const int ipt = 128 / Hp;                              // x0 fields per 128-row tile
+  const int s_begin = blockIdx.y * p.stages_per_split;
+  int s_end = s_begin + p.stages_per_split;
+  if (s_end > p.n_stage_total) s_end = p.n_stage_total;
+  const int n_st = s_end > s_begin ? s_end - s_begin : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty_b[s], 1);
+      tc::mbar_init(&full_h[s], 2);
+      tc::mbar_init(&empty_h[s], 8);
+    }
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&full_a[i], 4);
+    tc::mbar_init(&empty_a[0], 1);
+    tc::mbar_init(&empty_a[1], 1);
+    tc::mbar_init(acc_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ---- A producers: lane row = (il, j): A[row, m] = x0[m, i] * h[m, j] ---------------------------
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;
+    const int il = t / Hp, j = t - il * Hp;
+    const int i = (blockIdx.x * 2 + g) * ipt + il;
+    const bool live = (i < F) && (j < H);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
+      const uint32_t sa = s % kWgStagesA, pa = (s / kWgStagesA) & 1;
+      const float* hs = reinterpret_cast<const float*>(smem + lay.h_off + sh * lay.h_bytes);
+      const float* xs = reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes);
+      tc::mbar_wait(&full_h[sh], ph);
+      uint32_t zh[32], zl[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        float z0 = 0.f, z1 = 0.f;
+        if (live) {
+          z0 = xs[(2 * q) * F + i] * hs[(2 * q) * Hp + j];
+          z1 = xs[(2 * q + 1) * F + i] * hs[(2 * q + 1) * Hp + j];
+        }
+        tc::split_bf16x2(z0, z1, zh[q], zl[q]);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty_h[sh]);
+      tc::mbar_wait(&empty_a[sa], pa ^ 1);
+      tc::fence_after_thread_sync();
+      const uint32_t a_col = tmem_base + lane_base + 256 + (sa * 2 + g) * 64;   // per k-step: 8 hi + 8 lo columns
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        tc::tmem_st8v(a_col + ks * 16, zh[ks * 8 + 0], zh[ks * 8 + 1], zh[ks * 8 + 2], zh[ks * 8 + 3], zh[ks * 8 + 4],
+                      zh[ks * 8 + 5], zh[ks * 8 + 6], zh[ks * 8 + 7]);
+        tc::tmem_st8v(a_col + ks * 16 + 8, zl[ks * 8 + 0], zl[ks * 8 + 1], zl[ks * 8 + 2], zl[ks * 8 + 3], zl[ks * 8 + 4],
+                      zl[ks * 8 + 5], zl[ks * 8 + 6], zl[ks * 8 + 7]);
+      }
+      tc::tmem_wait_st();
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_a[g * kWgStagesA + sa]);
+    }
+    // ---- epilogue: accumulator row -> dW[(i,j), :] ---------------------------------------------------
+    if (n_st > 0) {
+      tc::mbar_wait(acc_done, 0);
+      tc::fence_after_thread_sync();
+      float* dst = p.d_w + ((size_t)i * H + j) * L;
+#pragma unroll
+      for (int cb = 0; cb < kMaxL / 16; ++cb) {
+        if (cb * 16 < L) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem_base + lane_base + g * kAccCols + cb * 16, v);
+          tc::tmem_wait_ld();
+          if (live) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) atomicAdd(dst + cb * 16 + q, __uint_as_float(v[q]));
+          }
+        }
+      }
+      tc::fence_before_thread_sync();
+    }
+  } else if (warp == 8) {
+    const bool leader = elect_one_sync();
+    const uint32_t idesc = tc::make_idesc_bf16_bmn(128, (uint32_t)L);
+    // dC tile descriptor (MN-major): LBO = 128 B (k-group), SBO = 256 B (n-group)
+    const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t smem_b_u32 = tc::smem_u32(smem + lay.b_off);
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sb = s % kWgStages, pb = (s / kWgStages) & 1;
+      const uint32_t sa = s % kWgStagesA, pa = (s / kWgStagesA) & 1;
+      tc::mbar_wait(&full_b[sb], pb);
+      const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)lay.b_bytes;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        tc::mbar_wait(&full_a[g * kWgStagesA + sa], pa);
+        tc::fence_after_thread_sync();
+        if (leader) {
+          const uint32_t d_tmem = tmem_base + g * kAccCols;
+          const uint32_t a_base = tmem_base + 256 + (sa * 2 + g) * 64;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+              if (pass < p.n_pass) {
+                // pass 0: Z_hi*dC_hi ; 1: Z_lo*dC_hi ; 2: Z_hi*dC_lo
+                const uint32_t a_addr = a_base + ks * 16 + (pass == 1 ? 8 : 0);
+                const uint32_t blk = b_addr + ks * (64 * L) + (pass == 2 ? 32 * L : 0);
+                const uint64_t desc_b = desc_hi | (uint64_t)((blk >> 4) & 0x3FFF);
+                tc::mma_ts(d_tmem, a_addr, desc_b, idesc, (uint32_t)((s | ks | pass) != 0));
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (leader) {
+        tc::mma_commit(&empty_a[sa]);
+        tc::mma_commit(&empty_b[sb]);
+        if (s == n_st - 1) tc::mma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)lay.b_bytes;
+      for (int s = 0; s < n_st; ++s) {
+        const uint32_t sb = s % kWgStages, pb = (s / kWgStages) & 1;
+        tc::mbar_wait(&empty_b[sb], pb ^ 1);
+        tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
+        tc::bulk_g2s(smem + lay.b_off + sb * lay.b_bytes, p.dc_tiles + (size_t)(s_begin + s) * bytes, bytes, &full_b[sb]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- h / x0 tile loaders (64 threads): global rows -> smem [m][Hp] / [m][F] --------------------
+    const int lt = threadIdx.x - 320;
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
+      float* hs = reinterpret_cast<float*>(smem + lay.h_off + sh * lay.h_bytes);
+      float* xs = reinterpret_cast<float*>(smem + lay.x_off + sh * lay.x_bytes);
+      tc::mbar_wait(&empty_h[sh], ph ^ 1);
+      const size_t m0 = (size_t)(s_begin + s) * kWgStageRows;
+      const int hq = Hp / 4;
+      for (int e = lt; e < kWgStageRows * hq; e += 64) {
+        const int mm = e / hq, q = e - mm * hq;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((int64_t)(m0 + mm) < p.m_valid && q * 4 < H) {
+          const float* src = p.hsrc + (m0 + mm) * p.ldh + q * 4;
+          if (q * 4 + 4 <= H && (p.ldh % 4) == 0) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            v.x = src[0];
+            if (q * 4 + 1 < H) v.y = src[1];
+            if (q * 4 + 2 < H) v.z = src[2];
+            if (q * 4 + 3 < H) v.w = src[3];
+          }
+        }
+        *reinterpret_cast<float4*>(hs + mm * Hp + q * 4) = v;
+      }
+      for (int e = lt; e < kWgStageRows * F; e += 64) {
+        const int mm = e / F;
+        xs[e] = ((int64_t)(m0 + mm) < p.m_valid) ? p.x0t[m0 * F + e] : 0.f;
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_h[sh]);
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// d_bias[l] += sum over rows of dC (hi + lo of the tiles): only when the CIN has biases
+__global__ void cin_tc_dbias_kernel(const uint8_t* __restrict__ dc_tiles, float* __restrict__ d_bias, int L,
+                                    int n_blocks16) {
+  // thread per (block of 16 rows, l); tile layout: [n_grp][k_grp 2][8 rows][8 l]
+  const int64_t total = (int64_t)n_blocks16 * L;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t blk = t / L;
+    const int l = (int)(t - blk * L);
+    const uint8_t* base = dc_tiles + blk * (int64_t)(64 * L) + (l >> 3) * 256 + (l & 7) * 2;
+    float s = 0.f;
+    for (int hl = 0; hl < 2; ++hl)
+      for (int m = 0; m < 16; ++m)
+        s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(base + hl * 32 * L + (m >> 3) * 128 + (m & 7) * 16));
+    if (s != 0.f) atomicAdd(d_bias + l, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side of the backward
+// ------------------------------------------------------------------------------------------
+static size_t dc_bytes(const CinShape& s, int B, size_t* off /* per layer */) {
+  const int R = 128 / s.D;
+  const size_t n_super = ((size_t)B + 2 * R - 1) / (2 * R);
+  const size_t m_pad = n_super * 256;
+  size_t total = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    if (off) off[k] = total;
+    total += (m_pad / 16) * (size_t)(64 * s.L[k]);
+  }
+  return total;
+}
+
+size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B) { return wpack_bytes(s) + 1024 + dc_bytes(s, B, nullptr) + 1024; }
+
+template <int D>
+static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
+  auto kern = cin_tc_dgrad_kernel<D>;
+  DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int R = 128 / D;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+  int grid = sm_count();
+  if (grid > n_super) grid = n_super;
+  kern<<<grid, kTcThreads, smem_bytes, st>>>(p);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+static bool cin_tc_bwd_supported(const CinShape& s) {
+  if (!cin_tc_supported(s)) return false;
+  int bstage = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    const int bytes = 4 * s.L[k] * round_up(s.H[k], kSubK);
+    if (bytes > bstage) bstage = bytes;
+    if (s.H[k] % 4 && k > 0) return false;
+    if (wg_layout(s.L[k], round_up(s.H[k], kSubK), s.F).total > 227 * 1024) return false;
+  }
+  return tc_bwd_layout(bstage, s.F).total <= 227 * 1024;
+}
+
+int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
+               const float* weights, const float* d_pooled, const void* saved, float* grad_table,
+               float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
+               int n_pass, cudaStream_t st) {
+  if (!cin_tc_bwd_supported(s) || g_tc_bwd_fp32)
+    return cin_fp32_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
+                        workspace, workspace_bytes, B, act, st);
+  if (workspace_bytes < cin_tc_bwd_workspace_bytes(s, B)) {
+    set_error("dtb_cin_bwd: workspace too small for the tensor-core backward");
+    return DTB_ERR_INVALID_ARG;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  const size_t wp = (wpack_bytes(s) + 1023) / 1024 * 1024;
+  CinTcBwdParams p{};
+  p.idx = idx; p.table = table; p.row_offsets = row_offsets;
+  p.wpack = ws; p.d_pooled = d_pooled; p.saved = reinterpret_cast<const float*>(saved);
+  p.grad_table = grad_table; p.dc_tiles = ws + wp;
+  p.B = B; p.F = s.F; p.n_layers = s.n_layers; p.act = act; p.n_pass = n_pass; p.P = s.P;
+  size_t dc_off[kCinMaxLayers];
+  dc_bytes(s, B, dc_off);
+  size_t woff = 0, soff = (size_t)B * s.D * s.F;
+  int bstage = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], kSubK);
+    p.pool_lo[k] = s.pool_lo[k]; p.pool_n[k] = s.pool_n[k]; p.pcol0[k] = s.pcol0[k];
+    p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
+    p.wpack_off[k] = woff; p.saved_off[k] = soff; p.dc_off[k] = dc_off[k];
+    const size_t chunk = (size_t)s.L[k] * p.Hp[k] * 4;
+    const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    cin_tc_pack_t_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k]);
+    DTB_LAUNCH_OK();
+    woff += chunk * s.F;
+    soff += (size_t)B * s.D * s.L[k];
+    if ((int)chunk > bstage) bstage = (int)chunk;
+  }
+  p.b_stage_bytes = bstage;
+  const TcBwdSmemLayout lay = tc_bwd_layout(bstage, s.F);
+  int rc;
+  switch (s.D) {
+    case 4: rc = launch_dgrad<4>(p, lay.total, st); break;
+    case 8: rc = launch_dgrad<8>(p, lay.total, st); break;
+    case 16: rc = launch_dgrad<16>(p, lay.total, st); break;
+    case 32: rc = launch_dgrad<32>(p, lay.total, st); break;
+    default: set_error("dtb_cin_bwd: embedding dim %d unsupported", s.D); return DTB_ERR_UNSUPPORTED;
+  }
+  if (rc != DTB_OK) return rc;
+  // ---- wgrad, one launch per layer ------------------------------------------------------------
+  const int R = 128 / s.D;
+  const size_t n_super = ((size_t)B + 2 * R - 1) / (2 * R);
+  const size_t m_pad = n_super * 256;
+  const float* x0t = reinterpret_cast<const float*>(saved);
+  size_t toff = (size_t)B * s.D * s.F;
+  for (int k = 0; k < s.n_layers; ++k) {
+    CinTcWgradParams w{};
+    w.x0t = x0t;
+    w.hsrc = k == 0 ? x0t : x0t + toff - (size_t)B * s.D * s.L[k - 1];
+    w.ldh = k == 0 ? s.F : s.L[k - 1];
+    w.dc_tiles = p.dc_tiles + dc_off[k];
+    w.d_w = d_weights + s.w_off[k];
+    w.F = s.F; w.H = s.H[k]; w.Hp = p.Hp[k]; w.L = s.L[k]; w.n_pass = n_pass;
+    w.m_valid = B * s.D;
+    w.n_stage_total = (int)(m_pad / kWgStageRows);
+    const int ipt = 128 / w.Hp;
+    const int n_tiles = (s.F + ipt - 1) / ipt;
+    const int n_pairs = (n_tiles + 1) / 2;
+    int splits = sm_count() / n_pairs;
+    if (splits < 1) splits = 1;
+    if (splits > w.n_stage_total) splits = w.n_stage_total;
+    w.stages_per_split = (w.n_stage_total + splits - 1) / splits;
+    splits = (w.n_stage_total + w.stages_per_split - 1) / w.stages_per_split;
+    const WgSmemLayout wl = wg_layout(w.L, w.Hp, w.F);
+    DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
+    cin_tc_wgrad_kernel<<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
+    DTB_LAUNCH_OK();
+    if (d_bias) {
+      const int n_blocks16 = (int)(m_pad / 16);
+      int blocks = (int)(((int64_t)n_blocks16 * w.L + 255) / 256);
+      if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+      cin_tc_dbias_kernel<<<blocks, 256, 0, st>>>(w.dc_tiles, d_bias + s.b_off[k], w.L, n_blocks16);
+      DTB_LAUNCH_OK();
+    }
+    toff += (size_t)B * s.D * s.L[k];
+  }
+  return DTB_OK;
+}
+
+}  // namespace dtb

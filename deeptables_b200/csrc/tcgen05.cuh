@@ -117,6 +117,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);  // m_dim
 }
 
+// same, B operand MN-major (element (n,k): 8 n contiguous per 16-byte row, 8 k-rows per core matrix;
+// LBO = byte distance between k-groups of 8, SBO = between n-groups of 8)
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t N) {
+  return make_idesc_bf16(M, N) | (1u << 16);   // b_major = MN
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                        uint32_t accumulate) {

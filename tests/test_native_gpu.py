@@ -536,3 +536,69 @@ def test_cin_tensor_core_full_batch_properties(nat):
     ref = run(idx[sample], 1, len(sample))
     scale = float(ref.abs().max())
     torch.testing.assert_close(out[torch.as_tensor(sample, device='cuda')], ref, rtol=1e-3, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize('f,d,sizes,direct,use_bias,act,b', TC_CASES)
+def test_cin_tensor_core_backward(nat, f, d, sizes, direct, use_bias, act, b):
+    """dgrad + wgrad on tcgen05 (bf16x3) against the oracle's autograd."""
+    sizes_c = nat.int_array(sizes)
+    n = len(sizes)
+    if not nat.lib.dtb_cin_tc_supported(f, d, sizes_c, n, int(direct)):
+        pytest.skip('shape not supported by the tensor-core kernels')
+    vocab = [9 + i for i in range(f)]
+    tabs, flat, offs = make_table(vocab, d, seed=41)
+    idx = make_idx(vocab, b, seed=42)
+    g = np.random.default_rng(43)
+    fns = L.cin_field_nums(f, sizes, direct)
+    filt = [(g.normal(size=(f * fns[k], s)) / np.sqrt(f * fns[k])).astype(np.float32) for k, s in enumerate(sizes)]
+    bias = [g.normal(size=s).astype(np.float32) * 0.1 for s in sizes] if use_bias else None
+    wcat = np.concatenate([x.reshape(-1) for x in filt])
+    pw = L.cin_pooled_width(f, dict(cross_layer_size=sizes, direct=direct))
+    pooled = torch.empty(b, pw, device='cuda')
+    ws_bytes = nat.lib.dtb_cin_workspace_bytes(b, f, d, sizes_c, n, int(direct), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+    saved = torch.empty(nat.lib.dtb_cin_saved_bytes(b, f, d, sizes_c, n, int(direct)), dtype=torch.uint8, device='cuda')
+    d_idx, d_tab, d_offs, d_w = dev(idx), dev(flat), dev(offs), dev(wcat)
+    d_b = dev(np.concatenate(bias)) if use_bias else None
+    nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(pooled), P(saved), P(ws), ws_bytes,
+                                  b, f, d, sizes_c, n, int(direct), act, 2, None, None))
+    dp = g.normal(size=(b, pw)).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    dw = torch.zeros(wcat.shape, device='cuda')
+    dbias = torch.zeros(sum(sizes), device='cuda') if use_bias else None
+    d_dp = dev(dp)
+    nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt), P(dw), P(dbias),
+                                  P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None))
+    torch.cuda.synchronize()
+    # (1) same saved activations (=> identical relu masks) through the exact-fp32 backward: the two
+    #     backward implementations must agree to bf16x3 precision
+    gt2 = torch.zeros(flat.shape, device='cuda')
+    dw2 = torch.zeros(wcat.shape, device='cuda')
+    db2 = torch.zeros(sum(sizes), device='cuda') if use_bias else None
+    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 16))
+    try:
+        nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt2), P(dw2), P(db2),
+                                      P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None))
+        torch.cuda.synchronize()
+    finally:
+        nat.lib.dtb_cin_tc_set_variant(1)
+    et = float((gt - gt2).abs().max() / gt2.abs().max())
+    ew = float((dw - dw2).abs().max() / dw2.abs().max())
+    assert et < 5e-5 and ew < 5e-5, f'tensor-core vs fp32 backward: embedding grad {et:.2e}, filter grad {ew:.2e}'
+    if use_bias:
+        eb = float((dbias - db2).abs().max() / db2.abs().max())
+        assert eb < 5e-5, f'bias grad {eb:.2e}'
+    # (2) against the oracle's autograd.  A relu unit whose pre-activation is within rounding of zero
+    #     may flip between the bf16x3 forward and the float64 oracle, so this bound is looser.
+    t64 = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tabs]
+    x = torch.cat(L.embedding_lookup(t64, torch.tensor(idx)), dim=1)
+    f64 = [torch.tensor(w_, dtype=torch.float64, requires_grad=True) for w_ in filt]
+    b64 = [torch.tensor(b_, dtype=torch.float64, requires_grad=True) for b_ in bias] if use_bias else None
+    want = _cin_oracle(x, sizes, direct, f64, b64, act)
+    loss = (want * torch.tensor(dp, dtype=torch.float64)).sum()
+    grads = torch.autograd.grad(loss, t64 + f64 + (b64 or []), allow_unused=True)
+    want_t = torch.cat(grads[:f], dim=0).numpy()
+    want_w = np.concatenate([gg.numpy().reshape(-1) for gg in grads[f:f + n]])
+    et = np.abs(gt.cpu().numpy() - want_t).max() / np.abs(want_t).max()
+    ew = np.abs(dw.cpu().numpy() - want_w).max() / np.abs(want_w).max()
+    assert et < 1e-2 and ew < 1e-2, f'vs oracle: embedding grad err {et:.2e}, filter grad err {ew:.2e} (relative to max)'
