@@ -989,7 +989,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     for (int s = 0; s < kWgStages; ++s) {
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty_b[s], 1);
-      tc::mbar_init(&full_h[s], 2);
+      tc::mbar_init(&full_h[s], 1);
       tc::mbar_init(&empty_h[s], 8);
     }
     for (int i = 0; i < 4; ++i) tc::mbar_init(&full_a[i], 4);
@@ -1011,20 +1011,22 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     const int il = t / Hp, j = t - il * Hp;
     const int i = (blockIdx.x * 2 + g) * ipt + il;
     const bool live = (i < F) && (j < H);
+    const bool h_is_x = (p.hsrc == p.x0t);
+    const int hstride = h_is_x ? F : Hp;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int s = 0; s < n_st; ++s) {
       const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
       const uint32_t sa = s % kWgStagesA, pa = (s / kWgStagesA) & 1;
-      const float* hs = reinterpret_cast<const float*>(smem + lay.h_off + sh * lay.h_bytes);
       const float* xs = reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes);
+      const float* hs = h_is_x ? xs : reinterpret_cast<const float*>(smem + lay.h_off + sh * lay.h_bytes);
       tc::mbar_wait(&full_h[sh], ph);
       uint32_t zh[32], zl[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         float z0 = 0.f, z1 = 0.f;
         if (live) {
-          z0 = xs[(2 * q) * F + i] * hs[(2 * q) * Hp + j];
-          z1 = xs[(2 * q + 1) * F + i] * hs[(2 * q + 1) * Hp + j];
+          z0 = xs[(2 * q) * F + i] * hs[(2 * q) * hstride + j];
+          z1 = xs[(2 * q + 1) * F + i] * hs[(2 * q + 1) * hstride + j];
         }
         tc::split_bf16x2(z0, z1, zh[q], zl[q]);
       }
@@ -1117,37 +1119,45 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ---- h / x0 tile loaders (64 threads): global rows -> smem [m][Hp] / [m][F] --------------------
-    const int lt = threadIdx.x - 320;
-    for (int s = 0; s < n_st; ++s) {
-      const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
-      float* hs = reinterpret_cast<float*>(smem + lay.h_off + sh * lay.h_bytes);
-      float* xs = reinterpret_cast<float*>(smem + lay.x_off + sh * lay.x_bytes);
-      tc::mbar_wait(&empty_h[sh], ph ^ 1);
-      const size_t m0 = (size_t)(s_begin + s) * kWgStageRows;
-      const int hq = Hp / 4;
-      for (int e = lt; e < kWgStageRows * hq; e += 64) {
-        const int mm = e / hq, q = e - mm * hq;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((int64_t)(m0 + mm) < p.m_valid && q * 4 < H) {
-          const float* src = p.hsrc + (m0 + mm) * p.ldh + q * 4;
-          if (q * 4 + 4 <= H && (p.ldh % 4) == 0) {
-            v = *reinterpret_cast<const float4*>(src);
-          } else {
-            v.x = src[0];
-            if (q * 4 + 1 < H) v.y = src[1];
-            if (q * 4 + 2 < H) v.z = src[2];
-            if (q * 4 + 3 < H) v.w = src[3];
+    // ---- h / x0 tile loader (warp 10): bulk async copies, completion on full_h via tx bytes ------
+    // x0t rows of a stage are contiguous in HBM (64*F floats, 16-byte aligned because 64*F*4 % 16 == 0);
+    // h rows are H floats (H % 4 == 0) at stride ldh.  Layer 0 has h == x0: producers read the x tile.
+    if (warp == 10) {
+      const bool h_is_x = (p.hsrc == p.x0t);
+      const uint32_t x_bytes = (uint32_t)(kWgStageRows * F * 4);
+      const uint32_t row_bytes = (uint32_t)(H * 4);
+      for (int s = 0; s < n_st; ++s) {
+        const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
+        float* hs = reinterpret_cast<float*>(smem + lay.h_off + sh * lay.h_bytes);
+        float* xs = reinterpret_cast<float*>(smem + lay.x_off + sh * lay.x_bytes);
+        tc::mbar_wait(&empty_h[sh], ph ^ 1);
+        const size_t m0 = (size_t)(s_begin + s) * kWgStageRows;
+        if ((int64_t)(m0 + kWgStageRows) <= (int64_t)p.m_valid) {
+          if (lane == 0) {
+            tc::mbar_arrive_expect_tx(&full_h[sh], x_bytes + (h_is_x ? 0u : (uint32_t)kWgStageRows * row_bytes));
+            tc::bulk_g2s(xs, p.x0t + m0 * F, x_bytes, &full_h[sh]);
           }
+          __syncwarp();
+          if (!h_is_x) {
+            for (int mm = lane; mm < kWgStageRows; mm += 32)
+              tc::bulk_g2s(hs + mm * Hp, p.hsrc + (m0 + mm) * p.ldh, row_bytes, &full_h[sh]);
+          }
+        } else {
+          // ragged last stage: bounds-checked scalar fill, plain arrival
+          for (int e = lane; e < kWgStageRows * F; e += 32) {
+            const int mm = e / F;
+            xs[e] = ((int64_t)(m0 + mm) < p.m_valid) ? p.x0t[m0 * F + e] : 0.f;
+          }
+          if (!h_is_x) {
+            for (int e = lane; e < kWgStageRows * H; e += 32) {
+              const int mm = e / H, jj = e - mm * H;
+              hs[mm * Hp + jj] = ((int64_t)(m0 + mm) < p.m_valid) ? p.hsrc[(m0 + mm) * p.ldh + jj] : 0.f;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&full_h[sh]);
         }
-        *reinterpret_cast<float4*>(hs + mm * Hp + q * 4) = v;
       }
-      for (int e = lt; e < kWgStageRows * F; e += 64) {
-        const int mm = e / F;
-        xs[e] = ((int64_t)(m0 + mm) < p.m_valid) ? p.x0t[m0 * F + e] : 0.f;
-      }
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&full_h[sh]);
     }
   }
   tc::fence_before_thread_sync();
