@@ -7,7 +7,7 @@ import time with the build command, and every op raises ``RuntimeError`` carryin
 import ctypes
 import os
 import re
-from ctypes import c_int, c_int64, c_longlong, c_float, c_void_p, c_size_t, c_char_p, POINTER
+from ctypes import c_int, c_int64, c_longlong, c_float, c_double, c_void_p, c_size_t, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_native', 'libdeeptables_b200.so')
@@ -41,12 +41,12 @@ _SIGNATURES = {
     'dtb_dense_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_dense_bwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_loss_fwd_bwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
-    'dtb_adam_dense': (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, P]),
-    'dtb_adam_rows_catchup': (c_int, [P, P, P, P, P, P, P, c_int, c_float, c_float, c_float,
+    'dtb_adam_dense': (c_int, [P, P, P, P, c_int64, c_float, c_double, c_double, c_float, c_int, P]),
+    'dtb_adam_rows_catchup': (c_int, [P, P, P, P, P, P, P, c_int, c_double, c_double, c_float,
                                       c_int, c_int, c_int, P]),
-    'dtb_adam_rows_apply': (c_int, [P, P, P, P, P, P, P, P, c_int, c_float, c_float, c_float,
+    'dtb_adam_rows_apply': (c_int, [P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_float,
                                     c_int, c_int, c_int, P]),
-    'dtb_adam_rows_flush': (c_int, [P, P, P, P, P, c_int, c_float, c_float, c_float, c_int64, c_int, P]),
+    'dtb_adam_rows_flush': (c_int, [P, P, P, P, P, c_int, c_double, c_double, c_float, c_int64, c_int, P]),
     'dtb_cin_saved_bytes': (c_size_t, [c_int, c_int, c_int, _IP, c_int, c_int]),
     'dtb_cin_workspace_bytes': (c_size_t, [c_int, c_int, c_int, _IP, c_int, c_int, c_int]),
     'dtb_cin_fwd': (c_int, [P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, _IP, c_int, c_int,
@@ -60,8 +60,8 @@ _SIGNATURES = {
     'dtb_cross_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_pnn_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     'dtb_pnn_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dtb_attention_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
-    'dtb_attention_bwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dtb_attention_core_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
+    'dtb_attention_core_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, P]),
 }
 
 

@@ -129,14 +129,14 @@ using namespace dtb;
 extern "C" {
 
 int dtb_adam_rows_catchup(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
-                          int32_t* last_step, const float* alpha_table, int upto, float beta1, float beta2,
+                          int32_t* last_step, const float* alpha_table, int upto, double beta1, double beta2,
                           float eps, int B, int F, int D, void* stream) {
   DTB_CHECK_ARG(idx && row_offsets && table && m && v && last_step && alpha_table, "NULL argument");
   DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128) for the row-wise Adam");
   if (B <= 0 || F <= 0 || upto <= 0) return DTB_OK;
   const int64_t total = (int64_t)B * F * (D / 4);
   adam_rows_kernel<0><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
-      idx, row_offsets, table, m, v, nullptr, last_step, alpha_table, upto, 1.f - beta1, 1.f - beta2, eps, B,
+      idx, row_offsets, table, m, v, nullptr, last_step, alpha_table, upto, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, B,
       F, D);
   DTB_LAUNCH_OK();
   return DTB_OK;
@@ -144,7 +144,7 @@ int dtb_adam_rows_catchup(const int32_t* idx, const int64_t* row_offsets, float*
 
 int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
                         float* grad_table, int32_t* last_step, const float* alpha_table, int step,
-                        float beta1, float beta2, float eps, int B, int F, int D, void* stream) {
+                        double beta1, double beta2, float eps, int B, int F, int D, void* stream) {
   DTB_CHECK_ARG(idx && row_offsets && table && m && v && grad_table && last_step && alpha_table,
                 "NULL argument");
   DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128) for the row-wise Adam");
@@ -152,20 +152,20 @@ int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* t
   if (B <= 0 || F <= 0) return DTB_OK;
   const int64_t total = (int64_t)B * F * (D / 4);
   adam_rows_kernel<1><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
-      idx, row_offsets, table, m, v, grad_table, last_step, alpha_table, step, 1.f - beta1, 1.f - beta2, eps,
+      idx, row_offsets, table, m, v, grad_table, last_step, alpha_table, step, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
       B, F, D);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }
 
 int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step, const float* alpha_table,
-                        int upto, float beta1, float beta2, float eps, int64_t n_rows, int D, void* stream) {
+                        int upto, double beta1, double beta2, float eps, int64_t n_rows, int D, void* stream) {
   DTB_CHECK_ARG(table && m && v && last_step && alpha_table, "NULL argument");
   DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128) for the row-wise Adam");
   if (n_rows <= 0 || upto <= 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   adam_rows_flush_kernel<<<rows_grid(n_rows * (D / 4)), 256, 0, st>>>(
-      table, m, v, last_step, alpha_table, upto, 1.f - beta1, 1.f - beta2, eps, n_rows, D);
+      table, m, v, last_step, alpha_table, upto, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, n_rows, D);
   DTB_LAUNCH_OK();
   set_last_step_kernel<<<rows_grid(n_rows), 256, 0, st>>>(last_step, n_rows, upto);
   DTB_LAUNCH_OK();

@@ -300,9 +300,8 @@ __global__ void loss_kernel(const float* __restrict__ z, const float* __restrict
 // Adam (dense)
 // ------------------------------------------------------------------------------------------
 __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                                  float* __restrict__ g, int64_t n, float alpha, float b1, float b2,
+                                  float* __restrict__ g, int64_t n, float alpha, float omb1, float omb2,
                                   float eps, int zero_grad) {
-  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
@@ -462,12 +461,13 @@ int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_we
   return DTB_OK;
 }
 
-int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, float beta1, float beta2,
+int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, double beta1, double beta2,
                    float eps, int zero_grad, void* stream) {
   DTB_CHECK_ARG(p && m && v && g, "NULL argument");
   if (n <= 0) return DTB_OK;
-  adam_dense_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, alpha, beta1, beta2, eps,
-                                                                  zero_grad);
+  // keras multiplies by the python double (1 - beta) rounded to fp32, not by 1.f - float(beta)
+  adam_dense_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, n, alpha, (float)(1.0 - beta1),
+                                                                  (float)(1.0 - beta2), eps, zero_grad);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

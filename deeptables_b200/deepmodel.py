@@ -23,7 +23,7 @@ from typing import Union
 import numpy as np
 import torch
 
-from . import consts, deepnets, engine as E, layers as L
+from . import consts, deepnets, dp, engine as E, layers as L
 from ._native import ptr, check, stream_ptr
 from . import _native as N
 
@@ -214,10 +214,7 @@ class DeepModel:
         with torch.no_grad():
             self._forward(cat, cont, training=False, describe=True)
         self._scope.freeze()
-        if self._dist:      # identical replicas: rank 0's initial weights win
-            torch.distributed.broadcast(self._scope.flat_p, 0)
-            if self.table is not None:
-                torch.distributed.broadcast(self.table.weight, 0)
+        dp.broadcast_parameters([self._scope.flat_p, self.table.weight if self.table is not None else None])
         self._loss_acc = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.model = KerasLikeModel(self)
         return self.model
@@ -328,8 +325,7 @@ class DeepModel:
             self._catch_up(cat, self._step)
         z = self._forward(cat, cont, training=True)
         prob, dz = E.loss_forward_backward(z, y, self.task, sample_weight, True, self._loss_acc)
-        if self._dist:
-            dz.mul_(1.0 / self.world_size)
+        dp.scale_for_mean(dz)
         z.backward(dz)
         step = self._step + 1
         alpha = E.adam_alpha(step)
@@ -354,20 +350,12 @@ class DeepModel:
         return prob
 
     def _exchange_gradients(self, cat):
-        """Data-parallel gradient exchange (the loss gradient was pre-scaled by 1/world_size, so SUM
-        gives MirroredStrategy's global-batch mean): ONE all-reduce bucket for the dense weights, one
-        for the embedding gradient, plus an all-gather of the ids so every rank's row-wise Adam visits
-        the union of touched rows."""
-        dist = torch.distributed
-        scope, t = self._scope, self.table
-        dist.all_reduce(scope.flat_g)
-        if t is None:
-            return cat
-        gathered = [torch.empty_like(cat) for _ in range(self.world_size)]
-        dist.all_gather(gathered, cat)
-        union = torch.cat(gathered, dim=0)
-        dist.all_reduce(t.grad)
-        self._catch_up(union, self._step)     # rows first touched by another rank this step
+        """Data-parallel exchange (dp.py): dense bucket + table gradient all-reduce, ids all-gather;
+        rows first touched by another rank this step are caught up before the row-wise Adam."""
+        t = self.table
+        union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat)
+        if t is not None:
+            self._catch_up(union, self._step)
         return union
 
     def predict_step(self, cat, cont):

@@ -448,32 +448,32 @@ class PNNFn(torch.autograd.Function):
         return _TableBackwardMixin.finish_tensor_table(t), dk, None, None, None, None
 
 
-class AttentionFn(torch.autograd.Function):
-    """MultiheadAttention.call up to (not including) its BatchNormalization (layers.py:115-150)."""
+class AttentionCoreFn(torch.autograd.Function):
+    """MultiheadAttention.call between the projections and the BatchNormalization
+    (layers.py:129-150): per-head softmax(QK^T/sqrt(dh))V + residual, relu."""
 
     @staticmethod
-    def forward(ctx, x, wqkvr, bqkvr, heads, use_residual):
-        x = _f32(x)
-        b, f, d = x.shape
-        y = torch.empty_like(x)
-        check(N.lib.dtb_attention_fwd(ptr(x), ptr(wqkvr), ptr(bqkvr), ptr(y), b, f, d, heads, int(use_residual),
-                                      stream_ptr()), 'attention_fwd')
-        ctx.save_for_backward(x, wqkvr, bqkvr)
+    def forward(ctx, qkvr, heads, use_residual):
+        qkvr = _f32(qkvr)
+        b, f, d4 = qkvr.shape
+        d = d4 // 4
+        y = torch.empty(b, f, d, dtype=torch.float32, device=qkvr.device)
+        check(N.lib.dtb_attention_core_fwd(ptr(qkvr), ptr(y), b, f, d, heads, int(use_residual), stream_ptr()),
+              'attention_core_fwd')
+        ctx.save_for_backward(qkvr, y)
         ctx.cfg = (heads, int(use_residual))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wqkvr, bqkvr = ctx.saved_tensors
-        b, f, d = x.shape
+        qkvr, y = ctx.saved_tensors
+        b, f, d4 = qkvr.shape
         heads, use_res = ctx.cfg
         dy = _f32(dy)
-        dx = torch.empty_like(x)
-        dw = torch.zeros_like(wqkvr)
-        db = torch.zeros_like(bqkvr)
-        check(N.lib.dtb_attention_bwd(ptr(x), ptr(wqkvr), ptr(bqkvr), ptr(dy), ptr(dx), ptr(dw), ptr(db), b, f, d,
-                                      heads, use_res, stream_ptr()), 'attention_bwd')
-        return dx, dw, db, None, None
+        dq = torch.empty_like(qkvr)
+        check(N.lib.dtb_attention_core_bwd(ptr(qkvr), ptr(y), ptr(dy), ptr(dq), b, f, d4 // 4, heads, use_res,
+                                           stream_ptr()), 'attention_core_bwd')
+        return dq, None, None
 
 
 TASK_CODES = {'binary': 0, 'multilabel': 0, 'regression': 1, 'multiclass': 2}

@@ -335,8 +335,9 @@ class MultiheadAttention(Layer):
         for proj in ('dense_Q', 'dense_K', 'dense_V', 'dense_residual'):
             ws.append(scope.param(f'{self.name}/{proj}/kernel', (d, d), 'he_uniform'))
             bs.append(scope.param(f'{self.name}/{proj}/bias', (d,), 'zeros'))
-        out = E.AttentionFn.apply(x, torch.stack(ws), torch.stack(bs), int(self.num_heads),
-                                  bool(self.use_residual))
+        # the four relu(Dense) projections as ONE GEMM: kernels side by side -> [B, F, 4D] = [Q|K|V|R]
+        qkvr = E.DenseFn.apply(x, torch.cat(ws, dim=1), torch.cat(bs), E.ACT_CODES['relu'])
+        out = E.AttentionCoreFn.apply(qkvr, int(self.num_heads), bool(self.use_residual))
         with scope.name_prefix(self.name):
             return BatchNormalization(name='batch_normalize')(out)
 

@@ -116,8 +116,8 @@ int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_we
 /* ---- keras Adam (deepmodel.py:321-322), dense semantics ---------------------------------- */
 /* m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= m*alpha/(sqrt(v)+eps), alpha computed by caller
  * as lr*sqrt(1-b2^t)/(1-b1^t).  If zero_grad != 0, g is zeroed after use. */
-int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, float beta1,
-                   float beta2, float eps, int zero_grad, void* stream);
+int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, double beta1,
+                   double beta2, float eps, int zero_grad, void* stream);
 
 /* Exact-lazy row-wise Adam for embedding tables (same arithmetic as dtb_adam_dense applied to
  * every row every step, but rows whose gradient is zero are caught up only when next touched).
@@ -128,14 +128,14 @@ int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alph
  *            the grad row, set last_step = step. */
 int dtb_adam_rows_catchup(const int32_t* idx, const int64_t* row_offsets, float* table, float* m,
                           float* v, int32_t* last_step, const float* alpha_table, int upto,
-                          float beta1, float beta2, float eps, int B, int F, int D, void* stream);
+                          double beta1, double beta2, float eps, int B, int F, int D, void* stream);
 int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* table, float* m,
                         float* v, float* grad_table, int32_t* last_step, const float* alpha_table,
-                        int step, float beta1, float beta2, float eps, int B, int F, int D,
+                        int step, double beta1, double beta2, float eps, int B, int F, int D,
                         void* stream);
 /* Bring every row of the table up to date (before save / export / dense evaluation). */
 int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step,
-                        const float* alpha_table, int upto, float beta1, float beta2, float eps,
+                        const float* alpha_table, int upto, double beta1, double beta2, float eps,
                         int64_t n_rows, int D, void* stream);
 
 /* ---- CIN (layers.py:638-734), gather fused ------------------------------------------------ */
@@ -194,14 +194,14 @@ int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
                 const float* op_kernel, const float* d_ip, const float* d_op, float* grad_table,
                 float* d_op_kernel, int B, int F, int D, int kernel_type, void* stream);
 
-/* ---- MultiheadAttention interacting layer (layers.py:115-150), pre-BatchNorm --------------- */
-/* X[B,F,D] -> Y[B,F,D] = relu(softmax(QK^T/sqrt(dh)) V + residual), Q/K/V/res = relu(XW+b).
- * Wqkvr: [4, D, D] (Q,K,V,residual kernels, each [in,out]); bqkvr: [4, D]. */
-int dtb_attention_fwd(const float* X, const float* Wqkvr, const float* bqkvr, float* Y, int B, int F,
-                      int D, int heads, int use_residual, void* stream);
-int dtb_attention_bwd(const float* X, const float* Wqkvr, const float* bqkvr, const float* dY,
-                      float* dX, float* dWqkvr, float* dbqkvr, int B, int F, int D, int heads,
-                      int use_residual, void* stream);
+/* ---- MultiheadAttention core (layers.py:129-150), between the projections and the BN ------- */
+/* qkvr [B, F, 4*D]: the four relu(Dense) projections of each field row, concatenated [Q|K|V|R]
+ * (one dtb_dense_fwd with the four kernels side by side).  Y[B,F,D] = relu(concat_h softmax(Q_h
+ * K_h^T / sqrt(D/heads)) V_h + R).  Backward: d_qkvr [B,F,4*D] (overwritten). */
+int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int heads,
+                           int use_residual, void* stream);
+int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, float* d_qkvr, int B,
+                           int F, int D, int heads, int use_residual, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,73 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes exercise deeptables_b200/dp.py (the exact
+functions DeepModel.train_step calls between backward and Adam)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, results):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from deeptables_b200 import dp
+        assert dp.is_distributed() and dp.world_size() == world
+        g = torch.Generator().manual_seed(100 + rank)
+        # per-rank "local batch mean" gradients
+        dz = torch.ones(4, 1)
+        dp.scale_for_mean(dz)
+        assert torch.allclose(dz, torch.full((4, 1), 1.0 / world))
+        flat = torch.randn(10, generator=g)
+        table = torch.zeros(16, 2)
+        ids = torch.tensor([[rank, 3 + rank], [5, 7 + rank]], dtype=torch.int32)     # row 5 touched by both
+        offs = torch.tensor([0, 6])
+        for b in range(2):
+            for f in range(2):
+                table[offs[f] + ids[b, f]] += 1.0 + rank
+        flat_local, table_local = flat.clone(), table.clone()
+        union = dp.exchange(flat, table, ids)
+        # reference: gather everything and sum
+        gathered_flat = [torch.empty(10) for _ in range(world)]
+        dist.all_gather(gathered_flat, flat_local)
+        gathered_tab = [torch.empty(16, 2) for _ in range(world)]
+        dist.all_gather(gathered_tab, table_local)
+        assert torch.allclose(flat, sum(gathered_flat))
+        assert torch.allclose(table, sum(gathered_tab))
+        assert union.shape == (2 * world, 2)
+        assert torch.equal(union[2 * rank:2 * rank + 2], ids)
+        # union covers every touched row
+        touched = (table.abs().sum(dim=1) > 0).nonzero().flatten().tolist()
+        rows = sorted({int(offs[f] + union[b, f]) for b in range(union.shape[0]) for f in range(2)})
+        assert touched == rows
+        w = torch.full((3,), float(rank))
+        dp.broadcast_parameters([w, None])
+        assert torch.equal(w, torch.zeros(3))
+        results[rank] = 'ok'
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_exchange_world2_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(2, port, results), nprocs=2, join=True)
+    assert dict(results) == {0: 'ok', 1: 'ok'}
+
+
+def test_dp_single_process_is_identity():
+    from deeptables_b200 import dp
+    assert not dp.is_distributed() and dp.world_size() == 1
+    ids = torch.tensor([[1, 2]], dtype=torch.int32)
+    g = torch.ones(3)
+    assert dp.exchange(g, torch.zeros(2, 2), ids) is ids
+    assert torch.equal(dp.scale_for_mean(torch.ones(2)), torch.ones(2))

@@ -38,7 +38,8 @@ def batch(vocab, n_cont, b, seed=0):
 
 
 NET_SETS = [['linear'], ['fm_nets'], ['dnn_nets'], ['cin_nets'], ['cross_nets'], ['dcn_nets'], ['cross_dnn_nets'],
-            ['linear', 'fm_nets', 'dnn_nets'], ['linear', 'cin_nets', 'dnn_nets']]
+            ['linear', 'fm_nets', 'dnn_nets'], ['linear', 'cin_nets', 'dnn_nets'], ['autoint_nets'], ['pnn_nets'],
+            ['ipnn_nets'], ['opnn_nets'], ['fm_nets', 'cin_nets', 'cross_nets', 'autoint_nets', 'pnn_nets']]
 
 
 @pytest.mark.parametrize('nets', NET_SETS)

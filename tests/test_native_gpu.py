@@ -602,3 +602,67 @@ def test_cin_tensor_core_backward(nat, f, d, sizes, direct, use_bias, act, b):
     et = np.abs(gt.cpu().numpy() - want_t).max() / np.abs(want_t).max()
     ew = np.abs(dw.cpu().numpy() - want_w).max() / np.abs(want_w).max()
     assert et < 1e-2 and ew < 1e-2, f'vs oracle: embedding grad err {et:.2e}, filter grad err {ew:.2e} (relative to max)'
+
+
+# ---------------------------------------------------------------------------------------------
+# PNN products and the AutoInt attention core
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('f,d,b', [(26, 16, 70), (5, 4, 33), (2, 8, 9), (7, 3, 20)])
+@pytest.mark.parametrize('ktype', ['mat', 'vec', 'num'])
+def test_pnn_fwd_bwd(nat, f, d, b, ktype):
+    vocab = [11 + i for i in range(f)]
+    tabs, flat, offs = make_table(vocab, d, seed=51)
+    idx = make_idx(vocab, b, seed=52)
+    idx[1] = idx[0]
+    g = np.random.default_rng(53)
+    pairs = f * (f - 1) // 2
+    shape = {'mat': (d, pairs, d), 'vec': (pairs, d), 'num': (pairs, 1)}[ktype]
+    kern = (g.normal(size=shape) / np.sqrt(d)).astype(np.float32)
+    kt = {'mat': 0, 'vec': 1, 'num': 2}[ktype]
+    d_idx, d_tab, d_offs, d_k = dev(idx), dev(flat), dev(offs), dev(kern)
+    ip = torch.empty(b, pairs, device='cuda')
+    op = torch.empty(b, pairs, device='cuda')
+    nat.check(nat.lib.dtb_pnn_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_k), P(ip), P(op), b, f, d, kt, None, None))
+    t64 = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tabs]
+    emb = L.embedding_lookup(t64, torch.tensor(idx))
+    k64 = torch.tensor(kern, dtype=torch.float64, requires_grad=True)
+    want_ip = L.inner_product(emb)
+    want_op = L.outer_product(emb, k64, ktype)
+    np.testing.assert_allclose(ip.cpu().numpy(), want_ip.detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(op.cpu().numpy(), want_op.detach().numpy(), rtol=1e-4, atol=1e-5)
+    g_ip = g.normal(size=(b, pairs)).astype(np.float32)
+    g_op = g.normal(size=(b, pairs)).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    dk = torch.zeros(kern.shape, device='cuda')
+    nat.check(nat.lib.dtb_pnn_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_k), P(dev(g_ip)), P(dev(g_op)), P(gt), P(dk), b, f, d,
+                                  kt, None))
+    loss = (want_ip * torch.tensor(g_ip, dtype=torch.float64)).sum() + (want_op * torch.tensor(g_op, dtype=torch.float64)).sum()
+    grads = torch.autograd.grad(loss, t64 + [k64])
+    want_t = torch.cat(grads[:-1], dim=0).numpy()
+    np.testing.assert_allclose(gt.cpu().numpy(), want_t, rtol=1e-3, atol=1e-4 * np.abs(want_t).max())
+    np.testing.assert_allclose(dk.cpu().numpy(), grads[-1].numpy(), rtol=1e-3, atol=1e-4 * np.abs(grads[-1].numpy()).max())
+
+
+@pytest.mark.parametrize('b,f,d,heads,res', [(40, 26, 32, 4, True), (17, 5, 4, 1, True), (9, 7, 16, 2, False), (3, 1, 8, 8, True)])
+def test_attention_core_fwd_bwd(nat, b, f, d, heads, res):
+    g = np.random.default_rng(54)
+    qkvr = np.maximum(g.normal(size=(b, f, 4 * d)), 0).astype(np.float32)       # relu outputs
+    y = torch.empty(b, f, d, device='cuda')
+    d_in = dev(qkvr)
+    nat.check(nat.lib.dtb_attention_core_fwd(P(d_in), P(y), b, f, d, heads, int(res), None))
+    x64 = torch.tensor(qkvr, dtype=torch.float64, requires_grad=True)
+    q, k, v, r = torch.split(x64, d, dim=-1)
+    q_ = torch.cat(torch.chunk(q, heads, dim=2), dim=0)
+    k_ = torch.cat(torch.chunk(k, heads, dim=2), dim=0)
+    v_ = torch.cat(torch.chunk(v, heads, dim=2), dim=0)
+    w = torch.softmax(q_ @ k_.transpose(1, 2) / (k_.shape[-1] ** 0.5), dim=-1)
+    out = torch.cat(torch.chunk(w @ v_, heads, dim=0), dim=2)
+    if res:
+        out = out + r
+    want = torch.relu(out)
+    np.testing.assert_allclose(y.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
+    dy = g.normal(size=(b, f, d)).astype(np.float32)
+    dq = torch.empty(b, f, 4 * d, device='cuda')
+    nat.check(nat.lib.dtb_attention_core_bwd(P(d_in), P(y), P(dev(dy)), P(dq), b, f, d, heads, int(res), None))
+    (gx,) = torch.autograd.grad((want * torch.tensor(dy, dtype=torch.float64)).sum(), [x64])
+    np.testing.assert_allclose(dq.cpu().numpy(), gx.numpy(), rtol=1e-3, atol=1e-4 * max(1.0, float(gx.abs().max())))
