@@ -7,7 +7,7 @@ import time with the build command, and every op raises ``RuntimeError`` carryin
 import ctypes
 import os
 import re
-from ctypes import c_int, c_int64, c_longlong, c_float, c_double, c_void_p, c_size_t, c_char_p, POINTER
+from ctypes import c_int, c_int64, c_longlong, c_ulonglong, c_float, c_double, c_void_p, c_size_t, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, '_native', 'libdeeptables_b200.so')
@@ -40,6 +40,7 @@ _SIGNATURES = {
     'dtb_batchnorm_bwd': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, P]),
     'dtb_dense_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_dense_bwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_dropout': (c_int, [P, P, c_int64, c_float, c_ulonglong, P]),
     'dtb_loss_fwd_bwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_adam_dense': (c_int, [P, P, P, P, c_int64, c_float, c_double, c_double, c_float, c_int, P]),
     'dtb_adam_rows_catchup': (c_int, [P, P, P, P, P, P, P, c_int, c_double, c_double, c_float,

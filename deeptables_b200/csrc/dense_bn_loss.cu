@@ -297,6 +297,23 @@ __global__ void loss_kernel(const float* __restrict__ z, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// Dropout (keras Dropout / SpatialDropout1D on (B,1,D) field embeddings == element-wise): counter-based
+// mask, so forward and backward regenerate the same bits from (seed, element index); nothing is stored.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return (uint32_t)x;
+}
+
+__global__ void dropout_kernel(const float* __restrict__ X, float* __restrict__ Y, int64_t n, uint32_t threshold,
+                               float scale, uint64_t seed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    Y[i] = mix32(seed * 0x9E3779B97F4A7C15ULL + (uint64_t)i) >= threshold ? X[i] * scale : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
 // Adam (dense)
 // ------------------------------------------------------------------------------------------
 __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
@@ -457,6 +474,16 @@ int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_we
   if (blocks > cap) blocks = cap;
   loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, y_true, sample_weight, prob, dz, loss_sum, rows,
                                                         cols, task);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_dropout(const float* X, float* Y, int64_t n, float rate, unsigned long long seed, void* stream) {
+  DTB_CHECK_ARG(X && Y, "NULL argument");
+  DTB_CHECK_ARG(rate >= 0.f && rate < 1.f, "rate must be in [0, 1)");
+  if (n <= 0) return DTB_OK;
+  const uint32_t threshold = (uint32_t)((double)rate * 4294967296.0);
+  dropout_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(X, Y, n, threshold, 1.f / (1.f - rate), seed);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -44,6 +44,12 @@ class _Scope:
         self.anchor = torch.zeros(1, dtype=torch.float32, device=self.device, requires_grad=True)
         self._counters = {}
         self._prefix = []
+        self._seed_counter = 0
+
+    def next_seed(self):
+        """Fresh dropout seed per call site and per pass (drawn from the model's generator stream)."""
+        self._seed_counter += 1
+        return (int(self.generator.initial_seed()) * 1000003 + self._seed_counter) & 0xFFFFFFFFFFFF
 
     def _begin_pass(self):
         self._counters = {}
@@ -230,11 +236,13 @@ class DeepModel:
             embeddings = []
             block = None
             if self.n_fields:
-                if cfg.embedding_dropout > 0 and training:
-                    raise NotImplementedError(
-                        'embedding_dropout > 0 in training is not supported by the fused gather kernels yet; '
-                        'pass embedding_dropout=0 (SURVEY.md section 7: parity/benchmark runs use 0)')
                 block = E.FieldBlock(cat, self.table)
+                if cfg.embedding_dropout > 0 and training:
+                    # SpatialDropout1D per field (reference layers.py:878-901): the mask must be shared by
+                    # every consumer, so this (non-default-for-benchmarks) mode materialises the dropped
+                    # block once and feeds the same fused kernels through the tensor-backed table facade
+                    dropped = E.DropoutFn.apply(block.materialize(), cfg.embedding_dropout, scope.next_seed())
+                    block = E.FieldBlock.from_tensor(dropped)
                 embeddings = E.EmbeddingList(block)
             dense_layer = cont
             if dense_layer is not None and cfg.dense_dropout > 0:
@@ -244,7 +252,7 @@ class DeepModel:
                 flatten_emb_layer._get()
             # concat_embedding_dense + bn_concat_emb_dense (reference deepmodel.py:348-361)
             if block is not None:
-                x = E.ConcatEmbDenseFn.apply(self.table.anchor, dense_layer, block)
+                x = E.ConcatEmbDenseFn.apply(block.table.anchor, dense_layer, block)
             elif dense_layer is not None:
                 x = dense_layer
             else:

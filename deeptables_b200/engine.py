@@ -311,6 +311,25 @@ def batchnorm_infer(x, gamma, beta, moving_mean, moving_var):
     return y
 
 
+class DropoutFn(torch.autograd.Function):
+    """keras Dropout / SpatialDropout1D on field embeddings: counter-based mask, nothing stored."""
+
+    @staticmethod
+    def forward(ctx, x, rate, seed):
+        x = _f32(x)
+        y = torch.empty_like(x)
+        check(N.lib.dtb_dropout(ptr(x), ptr(y), x.numel(), float(rate), int(seed), stream_ptr()), 'dropout')
+        ctx.cfg = (float(rate), int(seed))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _f32(dy)
+        dx = torch.empty_like(dy)
+        check(N.lib.dtb_dropout(ptr(dy), ptr(dx), dy.numel(), ctx.cfg[0], ctx.cfg[1], stream_ptr()), 'dropout_bwd')
+        return dx, None, None
+
+
 ACT_CODES = {None: 0, 'linear': 0, 'relu': 1}
 
 

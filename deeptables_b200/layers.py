@@ -157,7 +157,7 @@ class Dropout(Layer):
 
     def call(self, scope, x):
         if self.rate > 0 and scope.training:
-            return torch.nn.functional.dropout(_materialize(x), self.rate, True)
+            return E.DropoutFn.apply(_materialize(x), self.rate, scope.next_seed())
         return x
 
 

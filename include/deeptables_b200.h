@@ -104,6 +104,12 @@ int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, i
 int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, float* dX, float* dW,
                   float* dbias, int rows, int in_dim, int out_dim, int act, void* stream);
 
+/* ---- Dropout (keras Dropout, deepmodel.py:430, deepnets.py:426; SpatialDropout1D on the (B,1,D)
+ * field embeddings, layers.py:878-901, is element-wise too) -------------------------------------- */
+/* Y[i] = keep(seed, i) ? X[i]/(1-rate) : 0 with a counter-based mask: calling it again on dLoss/dY with
+ * the same seed IS the backward.  Y may alias X. */
+int dtb_dropout(const float* X, float* Y, int64_t n, float rate, unsigned long long seed, void* stream);
+
 /* ---- losses on the task_output pre-activation (deepmodel.py:319-346, 436-457) ------------ */
 /* task: 0 binary/multilabel (sigmoid + BCE, probabilities clipped to [1e-7,1-1e-7] as keras),
  *       1 regression (identity + MSE), 2 multiclass (softmax + CCE, y one-hot).

@@ -165,3 +165,23 @@ def test_fit_steps_arithmetic_and_history_keys():
     assert model._step == 2 * (80 // 32)                          # steps_per_epoch = len(X)//bs
     ev = model.evaluate(df, y, batch_size=64)
     assert 'loss' in ev and 'auc' in ev
+
+
+def test_embedding_and_dense_dropout_train_and_are_off_at_inference():
+    # reference defaults: embedding_dropout=0.3 (config.py:84); dropout must only act in training
+    vocab, n_cont, b = [30, 20, 10, 25], 3, 512
+    model, conf = build(['linear', 'fm_nets', 'cin_nets', 'dnn_nets'], vocab, 4, n_cont, embedding_dropout=0.3,
+                        dense_dropout=0.2)
+    idx, cont, y = batch(vocab, n_cont, b)
+    ti, tc = torch.tensor(idx).cuda(), torch.tensor(cont).cuda()
+    p1, p2 = model.predict_step(ti, tc), model.predict_step(ti, tc)
+    assert torch.equal(p1, p2)                                   # inference: deterministic, no mask
+    losses = [model.train_on_batch(idx, cont, y) for _ in range(40)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+    # the mask really drops ~30 %: compare a training-mode forward against inference on fresh weights
+    from deeptables_b200 import engine as E
+    x = torch.ones(1 << 16, device='cuda')
+    yk = E.DropoutFn.apply(x, 0.3, 123)
+    kept = float((yk > 0).float().mean())
+    assert abs(kept - 0.7) < 0.01 and abs(float(yk.max()) - 1 / 0.7) < 1e-5
+    assert torch.equal(yk, E.DropoutFn.apply(x, 0.3, 123)) and not torch.equal(yk, E.DropoutFn.apply(x, 0.3, 124))
