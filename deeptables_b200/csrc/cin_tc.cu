@@ -47,6 +47,7 @@ struct CinTcParams {
   int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
   unsigned long long wpack_off[kCinMaxLayers];   // byte offset of layer k's chunk images
   unsigned long long saved_off[kCinMaxLayers];   // float offset of T_k inside saved
+  unsigned long long hc_off[kCinMaxLayers];      // float offset of the compact copy of h_{k+1} = T_k[:, :hid_n] (0 = none)
   unsigned long long bias_off[kCinMaxLayers];
   int b_stage_bytes;                              // bytes reserved per weight stage in smem
   int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
@@ -229,6 +230,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
         const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
         const float* bias = p.bias ? p.bias + p.bias_off[k] : nullptr;
         float* sv = (p.saved && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
+        // compact copy of the hidden half for the wgrad kernel (rows contiguous => one bulk copy per stage)
+        float* hc = (sv && hid_n > 0) ? p.saved + p.hc_off[k] + ((size_t)b * D + d) * hid_n : nullptr;
 #pragma unroll
         for (int cb = 0; cb < kMaxL / 16; ++cb) {
           if (cb * 16 < L && !(p.dbg & 4)) {
@@ -250,6 +253,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(sv + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+            if (hc) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                if (cb * 16 + j < hid_n)      // hid_n % 4 == 0 (checked on the host)
+                  *reinterpret_cast<float4*>(hc + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
             // sum over the D lanes that share a batch row.  Reduce-scatter butterfly: at offset `off` a
             // lane keeps the half of its live columns selected by its bit `off` and adds the partner's
@@ -482,6 +491,7 @@ bool cin_tc_supported(const CinShape& s) {
   for (int k = 0; k < s.n_layers; ++k) {
     if (s.L[k] % 16 || s.L[k] > kMaxL) return false;
     if (round_up(s.H[k], kSubK) > kMaxHp) return false;
+    if (k > 0 && s.H[k] % 4) return false;
   }
   // shared-memory budget of the default variant
   int bstage = 0;
@@ -498,7 +508,12 @@ static size_t wpack_bytes(const CinShape& s) {
   return b;
 }
 
-size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B); }
+static size_t hc_floats(const CinShape& s, int B) {
+  size_t n = 0;
+  for (int k = 1; k < s.n_layers; ++k) n += (size_t)B * s.D * s.H[k];
+  return n;
+}
+size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B) + hc_floats(s, B) * sizeof(float); }
 
 size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B);
 size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
@@ -541,6 +556,7 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   p.bias = bias; p.pooled = pooled; p.saved = reinterpret_cast<float*>(saved); p.status = status;
   p.B = B; p.F = s.F; p.n_layers = s.n_layers; p.act = act; p.n_pass = n_pass; p.P = s.P;
   size_t woff = 0, soff = (size_t)B * s.D * s.F;
+  size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float);
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
     p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], kSubK);
@@ -548,6 +564,8 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
     p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
     p.wpack_off[k] = woff;
     p.saved_off[k] = soff;
+    p.hc_off[k] = hoff;
+    hoff += (size_t)B * s.D * p.hid_n[k];
     p.bias_off[k] = s.b_off[k];
     const size_t chunk = (size_t)s.L[k] * p.Hp[k] * 4;
     // pack layer k
@@ -1012,7 +1030,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     const int i = (blockIdx.x * 2 + g) * ipt + il;
     const bool live = (i < F) && (j < H);
     const bool h_is_x = (p.hsrc == p.x0t);
-    const int hstride = h_is_x ? F : Hp;
+    const int hstride = h_is_x ? F : H;       // compact tiles: row stride = H
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int s = 0; s < n_st; ++s) {
       const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
@@ -1136,12 +1154,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
           if (lane == 0) {
             tc::mbar_arrive_expect_tx(&full_h[sh], x_bytes + (h_is_x ? 0u : (uint32_t)kWgStageRows * row_bytes));
             tc::bulk_g2s(xs, p.x0t + m0 * F, x_bytes, &full_h[sh]);
+            if (!h_is_x) tc::bulk_g2s(hs, p.hsrc + m0 * H, (uint32_t)kWgStageRows * row_bytes, &full_h[sh]);   // ldh == H
           }
           __syncwarp();
-          if (!h_is_x) {
-            for (int mm = lane; mm < kWgStageRows; mm += 32)
-              tc::bulk_g2s(hs + mm * Hp, p.hsrc + (m0 + mm) * p.ldh, row_bytes, &full_h[sh]);
-          }
         } else {
           // ragged last stage: bounds-checked scalar fill, plain arrival
           for (int e = lane; e < kWgStageRows * F; e += 32) {
@@ -1151,7 +1166,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
           if (!h_is_x) {
             for (int e = lane; e < kWgStageRows * H; e += 32) {
               const int mm = e / H, jj = e - mm * H;
-              hs[mm * Hp + jj] = ((int64_t)(m0 + mm) < p.m_valid) ? p.hsrc[(m0 + mm) * p.ldh + jj] : 0.f;
+              hs[mm * H + jj] = ((int64_t)(m0 + mm) < p.m_valid) ? p.hsrc[(m0 + mm) * p.ldh + jj] : 0.f;
             }
           }
           __syncwarp();
@@ -1281,11 +1296,13 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   const size_t m_pad = n_super * 256;
   const float* x0t = reinterpret_cast<const float*>(saved);
   size_t toff = (size_t)B * s.D * s.F;
+  size_t hc_pos = cin_fp32_saved_bytes(s, B) / sizeof(float);
   for (int k = 0; k < s.n_layers; ++k) {
     CinTcWgradParams w{};
     w.x0t = x0t;
-    w.hsrc = k == 0 ? x0t : x0t + toff - (size_t)B * s.D * s.L[k - 1];
-    w.ldh = k == 0 ? s.F : s.L[k - 1];
+    w.hsrc = k == 0 ? x0t : x0t + hc_pos;     // compact [M, H_k] copy written by the forward kernel
+    w.ldh = k == 0 ? s.F : s.H[k];
+    if (k > 0) hc_pos += (size_t)B * s.D * s.H[k];
     w.dc_tiles = p.dc_tiles + dc_off[k];
     w.d_w = d_weights + s.w_off[k];
     w.F = s.F; w.H = s.H[k]; w.Hp = p.Hp[k]; w.L = s.L[k]; w.n_pass = n_pass;
