@@ -47,7 +47,8 @@ struct CinTcParams {
   int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
   unsigned long long wpack_off[kCinMaxLayers];   // byte offset of layer k's chunk images
   unsigned long long saved_off[kCinMaxLayers];   // float offset of T_k inside saved
-  unsigned long long hc_off[kCinMaxLayers];      // float offset of the compact copy of h_{k+1} = T_k[:, :hid_n] (0 = none)
+  unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed copy of h_{k+1} = T_k[:, :hid_n]
+  unsigned long long xb_off;                     // float offset of the block-transposed copy of x0
   unsigned long long bias_off[kCinMaxLayers];
   int b_stage_bytes;                              // bytes reserved per weight stage in smem
   int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
@@ -90,6 +91,7 @@ constexpr int kSubK = 32;
 constexpr int kStagesA = 4;
 constexpr int kStagesB = 4;
 constexpr int kACols = kSubK / 2;                 // TMEM columns of one bf16 [128 x 32] operand block
+constexpr int kWgPad = 68;                        // row stride (floats) of the block-transposed tiles the wgrad kernel reads
 
 struct TcSmemLayout {
   int b_off, x0_off, bar_off, total;
@@ -184,9 +186,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
       // ---- h_0 = x0 (zero padded to Hp[0]) ; training: save x0t ------------------------------
 #pragma unroll
       for (int j = 0; j < kMaxHp; ++j) h[j] = (j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
-      if (p.saved && b < p.B) {
-        float* dst = p.saved + ((size_t)b * D + d) * F;
-        for (int j = 0; j < F; ++j) dst[j] = x0g[((size_t)r * F + j) * D + d];
+      if (p.saved) {
+        if (b < p.B) {
+          float* dst = p.saved + ((size_t)b * D + d) * F;
+          for (int j = 0; j < F; ++j) dst[j] = x0g[((size_t)r * F + j) * D + d];
+        }
+        // block-transposed copy for the wgrad kernel: [m / 64][field][68] (rows of a 64-row stage contiguous
+        // along m, padded to 68 floats so LDS.128 across fields is conflict-free); padded rows get zeros
+        const size_t m_pad = (size_t)(st * 2 + g) * 128 + t;
+        float* xb = p.saved + p.xb_off + (m_pad >> 6) * (size_t)(F * kWgPad) + (m_pad & 63);
+        for (int j = 0; j < F; ++j) xb[j * kWgPad] = x0g[((size_t)r * F + j) * D + d];
       }
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
@@ -230,8 +239,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
         const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
         const float* bias = p.bias ? p.bias + p.bias_off[k] : nullptr;
         float* sv = (p.saved && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
-        // compact copy of the hidden half for the wgrad kernel (rows contiguous => one bulk copy per stage)
-        float* hc = (sv && hid_n > 0) ? p.saved + p.hc_off[k] + ((size_t)b * D + d) * hid_n : nullptr;
+        // block-transposed copy of the hidden half for the wgrad kernel ([m / 64][j][68], zeros in padded rows)
+        float* hb = nullptr;
+        if (p.saved && hid_n > 0) {
+          const size_t m_pad = (size_t)(st * 2 + g) * 128 + t;
+          hb = p.saved + p.hb_off[k] + (m_pad >> 6) * (size_t)(hid_n * kWgPad) + (m_pad & 63);
+        }
 #pragma unroll
         for (int cb = 0; cb < kMaxL / 16; ++cb) {
           if (cb * 16 < L && !(p.dbg & 4)) {
@@ -254,11 +267,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(sv + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             }
-            if (hc) {
+            if (hb) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                if (cb * 16 + j < hid_n)      // hid_n % 4 == 0 (checked on the host)
-                  *reinterpret_cast<float4*>(hc + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              for (int j = 0; j < 16; ++j)
+                if (cb * 16 + j < hid_n) hb[(cb * 16 + j) * kWgPad] = o[j];     // x0 == 0 for padded rows => o == act(bias): harmless, dC == 0 there
             }
             // sum over the D lanes that share a batch row.  Reduce-scatter butterfly: at offset `off` a
             // lane keeps the half of its live columns selected by its bit `off` and adds the partner's
@@ -508,12 +520,17 @@ static size_t wpack_bytes(const CinShape& s) {
   return b;
 }
 
-static size_t hc_floats(const CinShape& s, int B) {
-  size_t n = 0;
-  for (int k = 1; k < s.n_layers; ++k) n += (size_t)B * s.D * s.H[k];
+static size_t m_pad_rows(const CinShape& s, int B) {
+  const int R = 128 / s.D;
+  return (((size_t)B + 2 * R - 1) / (2 * R)) * 256;
+}
+static size_t bt_floats(const CinShape& s, int B) {      // block-transposed copies: x0 and h_k (k >= 1)
+  const size_t blocks = m_pad_rows(s, B) / 64;
+  size_t n = blocks * s.F * kWgPad;
+  for (int k = 1; k < s.n_layers; ++k) n += blocks * s.H[k] * kWgPad;
   return n;
 }
-size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B) + hc_floats(s, B) * sizeof(float); }
+size_t cin_tc_saved_bytes(const CinShape& s, int B) { return cin_fp32_saved_bytes(s, B) + bt_floats(s, B) * sizeof(float); }
 
 size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B);
 size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
@@ -556,7 +573,9 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   p.bias = bias; p.pooled = pooled; p.saved = reinterpret_cast<float*>(saved); p.status = status;
   p.B = B; p.F = s.F; p.n_layers = s.n_layers; p.act = act; p.n_pass = n_pass; p.P = s.P;
   size_t woff = 0, soff = (size_t)B * s.D * s.F;
-  size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float);
+  const size_t bt_blocks = m_pad_rows(s, B) / 64;
+  p.xb_off = cin_fp32_saved_bytes(s, B) / sizeof(float);
+  size_t hoff = p.xb_off + bt_blocks * s.F * kWgPad;
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
     p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], kSubK);
@@ -564,8 +583,8 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
     p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
     p.wpack_off[k] = woff;
     p.saved_off[k] = soff;
-    p.hc_off[k] = hoff;
-    hoff += (size_t)B * s.D * p.hid_n[k];
+    p.hb_off[k] = hoff;
+    hoff += bt_blocks * p.hid_n[k] * kWgPad;
     p.bias_off[k] = s.b_off[k];
     const size_t chunk = (size_t)s.L[k] * p.Hp[k] * 4;
     // pack layer k
@@ -956,12 +975,11 @@ constexpr int kWgStages = 3;
 constexpr int kWgStagesA = 2;
 
 struct CinTcWgradParams {
-  const float* x0t;          // [M_pad, F]
-  const float* hsrc;         // [M_pad, ldh] (T_{k-1}, or x0t for layer 0)
+  const float* xb;           // block-transposed x0:  [M_pad/64][F][68]
+  const float* hb;           // block-transposed h_k: [M_pad/64][H][68]  (== xb for layer 0)
   const uint8_t* dc_tiles;   // layer k blocks of 16 rows: [hi 32*L B | lo 32*L B]
   float* d_w;                // [F*H, L] accumulate
-  int ldh, F, H, Hp, L, n_pass;
-  int m_valid;               // rows (b,d) that exist: B*D
+  int F, H, Hp, L, n_pass;
   int n_stage_total;         // ceil(M_pad / 64)
   int stages_per_split;
 };
@@ -972,8 +990,8 @@ struct WgSmemLayout {
 __host__ __device__ inline WgSmemLayout wg_layout(int L, int Hp, int F) {
   WgSmemLayout l;
   l.b_bytes = 4 * 64 * L;                       // 4 blocks of 16 rows, hi + lo
-  l.h_bytes = kWgStageRows * Hp * 4;
-  l.x_bytes = (kWgStageRows * F * 4 + 15) / 16 * 16;
+  l.h_bytes = Hp * kWgPad * 4;
+  l.x_bytes = F * kWgPad * 4;
   l.b_off = 0;
   l.h_off = kWgStages * l.b_bytes;
   l.x_off = l.h_off + kWgStages * l.h_bytes;
@@ -1029,8 +1047,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     const int il = t / Hp, j = t - il * Hp;
     const int i = (blockIdx.x * 2 + g) * ipt + il;
     const bool live = (i < F) && (j < H);
-    const bool h_is_x = (p.hsrc == p.x0t);
-    const int hstride = h_is_x ? F : H;       // compact tiles: row stride = H
+    const bool h_is_x = (p.hb == p.xb);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     for (int s = 0; s < n_st; ++s) {
       const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
@@ -1038,15 +1055,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
       const float* xs = reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes);
       const float* hs = h_is_x ? xs : reinterpret_cast<const float*>(smem + lay.h_off + sh * lay.h_bytes);
       tc::mbar_wait(&full_h[sh], ph);
+      // this lane's x0 field row and hidden-field row of the stage, 64 consecutive batch*dim rows each
+      const float4* xrow = reinterpret_cast<const float4*>(xs + (live ? i : 0) * kWgPad);
+      const float4* hrow = reinterpret_cast<const float4*>(hs + (live ? j : 0) * kWgPad);
       uint32_t zh[32], zl[32];
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        float z0 = 0.f, z1 = 0.f;
-        if (live) {
-          z0 = xs[(2 * q) * F + i] * hs[(2 * q) * hstride + j];
-          z1 = xs[(2 * q + 1) * F + i] * hs[(2 * q + 1) * hstride + j];
-        }
-        tc::split_bf16x2(z0, z1, zh[q], zl[q]);
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 xv = xrow[q4], hv = hrow[q4];
+        const float sc = live ? 1.f : 0.f;
+        tc::split_bf16x2(xv.x * hv.x * sc, xv.y * hv.y * sc, zh[2 * q4], zl[2 * q4]);
+        tc::split_bf16x2(xv.z * hv.z * sc, xv.w * hv.w * sc, zh[2 * q4 + 1], zl[2 * q4 + 1]);
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&empty_h[sh]);
@@ -1137,43 +1155,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     }
     __syncwarp();
   } else {
-    // ---- h / x0 tile loader (warp 10): bulk async copies, completion on full_h via tx bytes ------
-    // x0t rows of a stage are contiguous in HBM (64*F floats, 16-byte aligned because 64*F*4 % 16 == 0);
-    // h rows are H floats (H % 4 == 0) at stride ldh.  Layer 0 has h == x0: producers read the x tile.
-    if (warp == 10) {
-      const bool h_is_x = (p.hsrc == p.x0t);
-      const uint32_t x_bytes = (uint32_t)(kWgStageRows * F * 4);
-      const uint32_t row_bytes = (uint32_t)(H * 4);
+    // ---- x0 / h tile loader (warp 10): one bulk async copy each per 64-row stage ------------------
+    if (warp == 10 && lane == 0) {
+      const bool h_is_x = (p.hb == p.xb);
+      const uint32_t x_bytes = (uint32_t)lay.x_bytes, h_bytes = (uint32_t)(H * kWgPad * 4);
       for (int s = 0; s < n_st; ++s) {
         const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
-        float* hs = reinterpret_cast<float*>(smem + lay.h_off + sh * lay.h_bytes);
-        float* xs = reinterpret_cast<float*>(smem + lay.x_off + sh * lay.x_bytes);
         tc::mbar_wait(&empty_h[sh], ph ^ 1);
-        const size_t m0 = (size_t)(s_begin + s) * kWgStageRows;
-        if ((int64_t)(m0 + kWgStageRows) <= (int64_t)p.m_valid) {
-          if (lane == 0) {
-            tc::mbar_arrive_expect_tx(&full_h[sh], x_bytes + (h_is_x ? 0u : (uint32_t)kWgStageRows * row_bytes));
-            tc::bulk_g2s(xs, p.x0t + m0 * F, x_bytes, &full_h[sh]);
-            if (!h_is_x) tc::bulk_g2s(hs, p.hsrc + m0 * H, (uint32_t)kWgStageRows * row_bytes, &full_h[sh]);   // ldh == H
-          }
-          __syncwarp();
-        } else {
-          // ragged last stage: bounds-checked scalar fill, plain arrival
-          for (int e = lane; e < kWgStageRows * F; e += 32) {
-            const int mm = e / F;
-            xs[e] = ((int64_t)(m0 + mm) < p.m_valid) ? p.x0t[m0 * F + e] : 0.f;
-          }
-          if (!h_is_x) {
-            for (int e = lane; e < kWgStageRows * H; e += 32) {
-              const int mm = e / H, jj = e - mm * H;
-              hs[mm * H + jj] = ((int64_t)(m0 + mm) < p.m_valid) ? p.hsrc[(m0 + mm) * p.ldh + jj] : 0.f;
-            }
-          }
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&full_h[sh]);
-        }
+        const size_t blk = (size_t)(s_begin + s);
+        tc::mbar_arrive_expect_tx(&full_h[sh], x_bytes + (h_is_x ? 0u : h_bytes));
+        tc::bulk_g2s(smem + lay.x_off + sh * lay.x_bytes, p.xb + blk * (size_t)(F * kWgPad), x_bytes, &full_h[sh]);
+        if (!h_is_x)
+          tc::bulk_g2s(smem + lay.h_off + sh * lay.h_bytes, p.hb + blk * (size_t)(H * kWgPad), h_bytes, &full_h[sh]);
       }
     }
+    __syncwarp();
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -1296,17 +1292,17 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   const size_t m_pad = n_super * 256;
   const float* x0t = reinterpret_cast<const float*>(saved);
   size_t toff = (size_t)B * s.D * s.F;
-  size_t hc_pos = cin_fp32_saved_bytes(s, B) / sizeof(float);
+  const size_t bt_blocks = m_pad / 64;
+  const size_t xb_pos = cin_fp32_saved_bytes(s, B) / sizeof(float);
+  size_t hb_pos = xb_pos + bt_blocks * s.F * kWgPad;
   for (int k = 0; k < s.n_layers; ++k) {
     CinTcWgradParams w{};
-    w.x0t = x0t;
-    w.hsrc = k == 0 ? x0t : x0t + hc_pos;     // compact [M, H_k] copy written by the forward kernel
-    w.ldh = k == 0 ? s.F : s.H[k];
-    if (k > 0) hc_pos += (size_t)B * s.D * s.H[k];
+    w.xb = x0t + xb_pos;
+    w.hb = k == 0 ? w.xb : x0t + hb_pos;      // block-transposed copies written by the forward kernel
+    if (k > 0) hb_pos += bt_blocks * s.H[k] * kWgPad;
     w.dc_tiles = p.dc_tiles + dc_off[k];
     w.d_w = d_weights + s.w_off[k];
     w.F = s.F; w.H = s.H[k]; w.Hp = p.Hp[k]; w.L = s.L[k]; w.n_pass = n_pass;
-    w.m_valid = B * s.D;
     w.n_stage_total = (int)(m_pad / kWgStageRows);
     const int ipt = 128 / w.Hp;
     const int n_tiles = (s.F + ipt - 1) / ipt;
