@@ -48,6 +48,8 @@ _SIGNATURES = {
     'dtb_adam_rows_apply': (c_int, [P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_float,
                                     c_int, c_int, c_int, P]),
     'dtb_adam_rows_flush': (c_int, [P, P, P, P, P, c_int, c_double, c_double, c_float, c_int64, c_int, P]),
+    'dtb_grad_rows_pack': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_grad_rows_unpack': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_cin_saved_bytes': (c_size_t, [c_int, c_int, c_int, _IP, c_int, c_int]),
     'dtb_cin_workspace_bytes': (c_size_t, [c_int, c_int, c_int, _IP, c_int, c_int, c_int]),
     'dtb_cin_fwd': (c_int, [P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, _IP, c_int, c_int,

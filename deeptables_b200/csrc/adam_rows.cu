@@ -173,3 +173,100 @@ int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step, co
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Data-parallel exchange of the embedding gradient without moving the dense [sum V, D] buffer:
+//   pack   : every (b,f) reference claims its row once per step (atomicMax on claim[row]); the owner
+//            MOVES the accumulated gradient row into packed[b,f,:] (and zeroes the table row), every
+//            other reference of the same row writes zeros.  packed is what the ranks all-gather.
+//   unpack : add one rank's packed rows into the local gradient table.  Within one launch at most one
+//            reference per row carries data, so plain read-modify-write is race-free, and calling it
+//            for rank 0,1,..,W-1 in order gives the same bits on every replica.
+// ------------------------------------------------------------------------------------------
+namespace dtb {
+
+__global__ void grad_rows_pack_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ row_offsets,
+                                      float* __restrict__ grad, int32_t* __restrict__ claim, float* __restrict__ packed,
+                                      int step, int B, int F, int D) {
+  const int Q = D >> 2;
+  const int64_t total = (int64_t)B * F * Q;
+  const int64_t total_pad = (total + 31) / 32 * 32;
+  const int lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_pad;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = i < total;
+    const int64_t ref = live ? i / Q : 0;
+    const int q = (int)(i - ref * Q);
+    const int b = (int)(ref / F), f = (int)(ref - (int64_t)b * F);
+    int64_t row = -1;
+    if (live) {
+      const int id = __ldg(idx + (int64_t)b * F + f);
+      const int64_t lo = row_offsets[f];
+      if (id >= 0 && id < row_offsets[f + 1] - lo) row = lo + id;
+    }
+    int old = 0x7fffffff;
+    if (row >= 0 && q == 0) old = atomicMax(claim + row, step);
+    old = __shfl_sync(0xffffffffu, old, lane - q);
+    if (!live) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0 && old < step) {
+      float4* src = reinterpret_cast<float4*>(grad + row * D + (q << 2));
+      v = *src;
+      *src = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    *reinterpret_cast<float4*>(packed + ref * D + (q << 2)) = v;
+  }
+}
+
+__global__ void grad_rows_unpack_kernel(const int32_t* __restrict__ idx, const int64_t* __restrict__ row_offsets,
+                                        const float* __restrict__ packed, float* __restrict__ grad, int B, int F,
+                                        int D) {
+  const int Q = D >> 2;
+  const int64_t total = (int64_t)B * F * Q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ref = i / Q;
+    const int q = (int)(i - ref * Q);
+    const int b = (int)(ref / F), f = (int)(ref - (int64_t)b * F);
+    const float4 v = *reinterpret_cast<const float4*>(packed + ref * D + (q << 2));
+    if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;   // non-owner reference (or a zero gradient)
+    const int id = __ldg(idx + (int64_t)b * F + f);
+    const int64_t lo = row_offsets[f];
+    if (id < 0 || id >= row_offsets[f + 1] - lo) continue;
+    float4* dst = reinterpret_cast<float4*>(grad + (lo + id) * D + (q << 2));
+    float4 g = *dst;
+    g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+    *dst = g;
+  }
+}
+
+}  // namespace dtb
+
+extern "C" {
+
+int dtb_grad_rows_pack(const int32_t* idx, const int64_t* row_offsets, float* grad_table, int32_t* claim,
+                       float* packed, int step, int B, int F, int D, void* stream) {
+  DTB_CHECK_ARG(idx && row_offsets && grad_table && claim && packed, "NULL argument");
+  DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128)");
+  DTB_CHECK_ARG(step >= 1, "step is 1-based");
+  if (B <= 0 || F <= 0) return DTB_OK;
+  const int64_t total = (int64_t)B * F * (D / 4);
+  grad_rows_pack_kernel<<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(idx, row_offsets, grad_table, claim, packed,
+                                                                             step, B, F, D);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_grad_rows_unpack(const int32_t* idx, const int64_t* row_offsets, const float* packed, float* grad_table, int B,
+                         int F, int D, void* stream) {
+  DTB_CHECK_ARG(idx && row_offsets && grad_table && packed, "NULL argument");
+  DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128)");
+  if (B <= 0 || F <= 0) return DTB_OK;
+  const int64_t total = (int64_t)B * F * (D / 4);
+  grad_rows_unpack_kernel<<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(idx, row_offsets, packed, grad_table, B, F,
+                                                                               D);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+}  // extern "C"

@@ -361,7 +361,22 @@ class DeepModel:
         """Data-parallel exchange (dp.py): dense bucket + table gradient all-reduce, ids all-gather;
         rows first touched by another rank this step are caught up before the row-wise Adam."""
         t = self.table
-        union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat)
+        pack = unpack = None
+        if t is not None and t.lazy_adam:
+            step = self._step + 1
+            if t.claim is None:
+                t.claim = torch.zeros(t.total_rows, dtype=torch.int32, device=self.device)
+
+            def pack():
+                packed = torch.empty(cat.shape[0], t.n_fields, t.dim, dtype=torch.float32, device=self.device)
+                check(N.lib.dtb_grad_rows_pack(ptr(cat), ptr(t.row_offsets), ptr(t.grad), ptr(t.claim), ptr(packed),
+                                               step, cat.shape[0], t.n_fields, t.dim, stream_ptr()), 'grad_rows_pack')
+                return packed
+
+            def unpack(ids, packed):
+                check(N.lib.dtb_grad_rows_unpack(ptr(ids), ptr(t.row_offsets), ptr(packed), ptr(t.grad), ids.shape[0],
+                                                 t.n_fields, t.dim, stream_ptr()), 'grad_rows_unpack')
+        union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat, pack, unpack)
         if t is not None:
             self._catch_up(union, self._step)
         return union

@@ -48,6 +48,7 @@ class EmbeddingTable:
         self.m = None
         self.v = None
         self.last_step = None
+        self.claim = None          # per-row claim stamps of the data-parallel row exchange
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         # lazy row-wise Adam needs dim = 4*2^k; otherwise dense Adam over the whole table
         q = self.dim // 4

@@ -144,6 +144,17 @@ int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step,
                         const float* alpha_table, int upto, double beta1, double beta2, float eps,
                         int64_t n_rows, int D, void* stream);
 
+/* Data-parallel exchange of the embedding gradient by rows (deepmodel.py:88-103: MirroredStrategy
+ * exchanges embedding gradients as IndexedSlices too).  pack: every (b,f) reference claims its row once
+ * per step (claim[row] = step); the owner MOVES the accumulated gradient row into packed[b,f,:] and zeroes
+ * the table row, other references of that row write zeros.  unpack: adds one rank's packed rows into the
+ * local gradient table; at most one reference per row carries data, so no atomics are needed and
+ * calling it for rank 0..W-1 in order yields identical bits on every replica. */
+int dtb_grad_rows_pack(const int32_t* idx, const int64_t* row_offsets, float* grad_table, int32_t* claim,
+                       float* packed /* [B,F,D] */, int step, int B, int F, int D, void* stream);
+int dtb_grad_rows_unpack(const int32_t* idx, const int64_t* row_offsets, const float* packed,
+                         float* grad_table, int B, int F, int D, void* stream);
+
 /* ---- CIN (layers.py:638-734), gather fused ------------------------------------------------ */
 /* Shapes: F0 = F fields, D, n_layers layer sizes L[k] (host array), direct flag; H[0]=F,
  * H[k+1] = direct ? L[k] : L[k]/2 (all L[k]); K[k] = F*H[k].

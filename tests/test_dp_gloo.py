@@ -48,6 +48,32 @@ def _worker(rank, world, port, results):
         touched = (table.abs().sum(dim=1) > 0).nonzero().flatten().tolist()
         rows = sorted({int(offs[f] + union[b, f]) for b in range(union.shape[0]) for f in range(2)})
         assert touched == rows
+        # row-wise exchange path (what DeepModel uses on GPU through dtb_grad_rows_pack/unpack),
+        # emulated on CPU tensors: owner-of-row semantics, rank-ordered adds
+        table2 = table_local.clone()
+        flat2 = flat_local.clone()
+
+        def pack():
+            packed = torch.zeros(2, 2, 2)
+            seen = set()
+            for b in range(2):
+                for f in range(2):
+                    r = int(offs[f] + ids[b, f])
+                    if r not in seen:
+                        seen.add(r)
+                        packed[b, f] = table2[r]
+                        table2[r] = 0
+            return packed
+        order = []
+
+        def unpack(ids_w, packed_w):
+            order.append(int(ids_w[0, 0]))
+            for b in range(2):
+                for f in range(2):
+                    table2[int(offs[f] + ids_w[b, f])] += packed_w[b, f]
+        union2 = dp.exchange(flat2, table2, ids, pack, unpack)
+        assert torch.equal(union2, union) and torch.allclose(table2, table) and torch.allclose(flat2, flat)
+        assert order == list(range(world))            # ranks applied in rank order on every replica
         w = torch.full((3,), float(rank))
         dp.broadcast_parameters([w, None])
         assert torch.equal(w, torch.zeros(3))
