@@ -314,9 +314,28 @@ class DeepModel:
             self._alpha = torch.tensor(vals, dtype=torch.float32, device=self.device)
         return self._alpha
 
+    def _select_table_optimizer(self, n_refs):
+        """Row-wise exact-lazy Adam visits every touched row (the UNION over ranks in data parallel);
+        the dense sweep reads the whole table.  Both give identical bits, so pick the cheaper one:
+        lazy while the references per step are a small fraction of the table, dense beyond that
+        (large world sizes).  Switching flushes / re-stamps ``last_step`` so the trajectory is unchanged."""
+        t = self.table
+        want_lazy = bool(t.lazy_adam and n_refs * 6 <= t.total_rows)
+        if getattr(self, '_table_mode_override', None) is not None:       # test hook
+            want_lazy = bool(t.lazy_adam and self._table_mode_override == 'lazy')
+        if want_lazy == t.lazy_active:
+            return
+        if t.lazy_active:                       # lazy -> dense: bring every row up to date first
+            t.lazy_active = True
+            self.flush_optimizer_state()
+            t.lazy_active = False
+        else:                                   # dense -> lazy: every row is current as of this step
+            t.last_step.fill_(self._step)
+            t.lazy_active = True
+
     def _catch_up(self, cat, upto):
         t = self.table
-        if t is None or not t.lazy_adam or t.last_step is None or upto <= 0:
+        if t is None or not t.lazy_active or t.last_step is None or upto <= 0:
             return
         check(N.lib.dtb_adam_rows_catchup(ptr(cat), ptr(t.row_offsets), ptr(t.weight), ptr(t.m), ptr(t.v),
                                           ptr(t.last_step), ptr(self._alpha_table(upto)), upto, E.ADAM_B1,
@@ -330,6 +349,7 @@ class DeepModel:
         t = self.table
         if t is not None:
             t.ensure_training_state()
+            self._select_table_optimizer(self.world_size * cat.shape[0] * t.n_fields)
             self._catch_up(cat, self._step)
         z = self._forward(cat, cont, training=True)
         prob, dz = E.loss_forward_backward(z, y, self.task, sample_weight, True, self._loss_acc)
@@ -344,7 +364,7 @@ class DeepModel:
                                    scope.flat_p.numel(), alpha, E.ADAM_B1, E.ADAM_B2, E.ADAM_EPS, 1,
                                    stream_ptr()), 'adam_dense')
         if t is not None:
-            if t.lazy_adam:
+            if t.lazy_active:
                 a = self._alpha_table(step)
                 check(N.lib.dtb_adam_rows_apply(ptr(union_cat), ptr(t.row_offsets), ptr(t.weight), ptr(t.m),
                                                 ptr(t.v), ptr(t.grad), ptr(t.last_step), ptr(a), step, E.ADAM_B1,
@@ -378,7 +398,7 @@ class DeepModel:
                                                  t.n_fields, t.dim, stream_ptr()), 'grad_rows_unpack')
         union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat, pack, unpack)
         if t is not None:
-            self._catch_up(union, self._step)
+            self._catch_up(union, self._step)     # lazy mode: rows first touched by another rank this step
         return union
 
     def predict_step(self, cat, cont):
@@ -621,7 +641,7 @@ class DeepModel:
     def flush_optimizer_state(self):
         """Bring every embedding row up to date (lazy Adam) -- before export / save."""
         t = self.table
-        if t is not None and t.lazy_adam and t.last_step is not None and self._step > 0:
+        if t is not None and t.lazy_active and t.last_step is not None and self._step > 0:
             check(N.lib.dtb_adam_rows_flush(ptr(t.weight), ptr(t.m), ptr(t.v), ptr(t.last_step),
                                             ptr(self._alpha_table(self._step)), self._step, E.ADAM_B1, E.ADAM_B2,
                                             E.ADAM_EPS, t.total_rows, t.dim, stream_ptr()), 'adam_rows_flush')

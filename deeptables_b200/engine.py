@@ -53,6 +53,7 @@ class EmbeddingTable:
         # lazy row-wise Adam needs dim = 4*2^k; otherwise dense Adam over the whole table
         q = self.dim // 4
         self.lazy_adam = bool(lazy_adam and self.dim % 4 == 0 and 1 <= q <= 32 and (q & (q - 1)) == 0)
+        self.lazy_active = self.lazy_adam     # which optimiser form is live (DeepModel._select_table_optimizer)
         # autograd anchor: fused ops take it as an input so their backward always runs
         self.anchor = torch.zeros(1, dtype=torch.float32, device=self.device, requires_grad=True)
 

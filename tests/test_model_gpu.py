@@ -185,3 +185,24 @@ def test_embedding_and_dense_dropout_train_and_are_off_at_inference():
     kept = float((yk > 0).float().mean())
     assert abs(kept - 0.7) < 0.01 and abs(float(yk.max()) - 1 / 0.7) < 1e-5
     assert torch.equal(yk, E.DropoutFn.apply(x, 0.3, 123)) and not torch.equal(yk, E.DropoutFn.apply(x, 0.3, 124))
+
+
+def test_lazy_and_dense_table_optimizer_switch_is_transparent():
+    """The table optimiser runs either as the row-wise exact-lazy Adam or as the dense sweep, chosen by
+    cost; both are the same Keras Adam, so forcing either form, or flipping between them mid-training,
+    must not change the trajectory."""
+    vocab, n_cont, b = [400, 300, 500], 2, 32
+    results = {}
+    for name, schedule in (('lazy', ['lazy'] * 8), ('dense', ['dense'] * 8),
+                           ('mixed', ['lazy', 'lazy', 'dense', 'dense', 'lazy', 'dense', 'lazy', 'lazy'])):
+        model, conf = build(['linear', 'fm_nets', 'dnn_nets'], vocab, 4, n_cont, seed=9)
+        modes = []
+        for step, mode in enumerate(schedule):
+            model._table_mode_override = mode
+            model.train_on_batch(*batch(vocab, n_cont, b, seed=step))
+            modes.append(model.table.lazy_active)
+        assert modes == [m == 'lazy' for m in schedule]
+        results[name] = {k: v.clone() for k, v in model.state_dict().items()}
+    for k in results['lazy']:
+        for other in ('dense', 'mixed'):
+            torch.testing.assert_close(results['lazy'][k], results[other][k], rtol=1e-5, atol=1e-7, msg=f'{other}:{k}')
