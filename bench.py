@@ -178,7 +178,9 @@ def run_reference(args):
 
 
 def time_cin_kernel(model, cat, peaks):
-    """Roofline of the dominant kernel: CIN forward, timed alone with CUDA events on its stream."""
+    """Roofline of the dominant kernel family: the CIN forward kernel exactly as the train step runs it
+    (training mode: activations saved), timed alone with CUDA events on its stream, L2 flushed between
+    launches; plus the CIN backward (dgrad + 3 wgrad launches) for information."""
     import torch
     from deeptables_b200 import _native as N
     from deeptables_b200._native import ptr
@@ -187,34 +189,59 @@ def time_cin_kernel(model, cat, peaks):
     sizes_c = N.int_array(CIN_SIZES)
     weights = torch.cat([model._scope.params[f'cin/f_{k}'].detach().reshape(-1) for k in range(3)]).contiguous()
     pooled = torch.empty(b, 256, device=cat.device)
-    ws_bytes = N.lib.dtb_cin_workspace_bytes(b, F_FIELDS, EMB_DIM, sizes_c, 3, 0, 0)
+    d_pooled = torch.randn(b, 256, device=cat.device) * 1e-3
+    ws_bytes = N.lib.dtb_cin_workspace_bytes(b, F_FIELDS, EMB_DIM, sizes_c, 3, 0, 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cat.device)
+    saved = torch.empty(N.lib.dtb_cin_saved_bytes(b, F_FIELDS, EMB_DIM, sizes_c, 3, 0), dtype=torch.uint8, device=cat.device)
+    dw = torch.zeros_like(weights)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=cat.device)
     precision = model.config.cin_params.get('precision', 0)
+    t.ensure_training_state()
 
-    def run():
-        N.check(N.lib.dtb_cin_fwd(ptr(cat), ptr(t.weight), ptr(t.row_offsets), ptr(weights), None, ptr(pooled), None,
+    def fwd():
+        N.check(N.lib.dtb_cin_fwd(ptr(cat), ptr(t.weight), ptr(t.row_offsets), ptr(weights), None, ptr(pooled), ptr(saved),
                                   ptr(ws), ws_bytes, b, F_FIELDS, EMB_DIM, sizes_c, 3, 0, 1, precision, None,
                                   N.stream_ptr()), 'cin_fwd')
-    for _ in range(2):
-        run()
-    times = []
-    for _ in range(5):
-        flush.zero_()                                  # > L2: weights / ids are not cache-resident
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run()
-        e1.record()
-        torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1) * 1e-3)
-    dt = sorted(times)[len(times) // 2]
+
+    def bwd():
+        N.check(N.lib.dtb_cin_bwd(ptr(cat), ptr(t.weight), ptr(t.row_offsets), ptr(weights), ptr(d_pooled), ptr(saved),
+                                  ptr(t.grad), ptr(dw), None, ptr(ws), ws_bytes, b, F_FIELDS, EMB_DIM, sizes_c, 3, 0, 1,
+                                  precision, N.stream_ptr()), 'cin_bwd')
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        times = []
+        for _ in range(5):
+            flush.zero_()                              # > L2: weights / ids / activations are not cache-resident
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e-3)
+        return sorted(times)[len(times) // 2]
+
+    dt = timed(fwd)
+    dt_b = timed(bwd)
+    t.grad.zero_()                                     # the probe's gradients must not leak into training
     tc = bool(N.lib.dtb_cin_tc_supported(F_FIELDS, EMB_DIM, sizes_c, 3, 0)) and precision != 1
     tf = b * CIN_FLOP_PER_ROW / dt / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_cin_tc_traffic.json')
+    if tc and os.path.exists(tpath) and b == 65536:
+        with open(tpath) as f:
+            tj = json.load(f)['cin_tc_fwd_kernel']
+        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
     return {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-            'frac': tf / peaks['bf16_tflops'], 'traffic': None,
-            'kernel': 'cin_fwd (tcgen05 bf16x3)' if tc else 'cin_fwd (fp32 cuBLAS formulation)',
+            'frac': tf / peaks['bf16_tflops'], 'traffic': traffic,
+            'kernel': 'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)' if tc
+            else 'cin_fwd (fp32 cuBLAS formulation)',
             'ms': dt * 1e3, 'algorithmic_flop_per_launch': b * CIN_FLOP_PER_ROW,
-            'hbm_gbs_informational': b * CIN_BYTES_PER_ROW / dt / 1e9, 'peak_source': peaks['source']}
+            'executed_tensor_tflops': tf * (3 if tc and precision != 3 else 1),
+            'hbm_gbs_informational': b * CIN_BYTES_PER_ROW / dt / 1e9, 'peak_source': peaks['source'],
+            'cin_backward': {'ms': dt_b * 1e3, 'algorithmic_tflops': 2 * b * CIN_FLOP_PER_ROW / dt_b / 1e12,
+                             'kernels': 'cin_tc_dgrad_kernel + 3 x cin_tc_wgrad_kernel'}}
 
 
 def main():
