@@ -60,7 +60,8 @@ _SIGNATURES = {
     'dtb_cin_tc_set_variant': (c_int, [c_int]),
     'dtb_tc_selftest': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_cross_fwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
-    'dtb_cross_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    'dtb_cross_bwd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'dtb_cross_bwd': (c_int, [P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, P]),
     'dtb_pnn_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     'dtb_pnn_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_attention_core_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),

@@ -49,15 +49,17 @@ cross_bwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
                  const float* __restrict__ dY, float* __restrict__ dX, float* __restrict__ d_kernels,
                  float* __restrict__ d_biases, int B, int W, int n_layers) {
   extern __shared__ float smem[];
-  // layout: [2*n_layers*W] CTA accumulators (dW, db) | per warp: x_0..x_{L-1} [L*W], g [W], gx0 [W]
-  float* acc_w = smem;
-  float* acc_b = smem + (size_t)n_layers * W;
+  // layout: per warp: dW, db accumulators [2*L*W] (a lane owns columns lane, lane+32, ...: plain
+  // read-modify-write, no atomics) | x_0..x_{L-1} [L*W], g [W], dx0 [W]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* xs = smem + (size_t)2 * n_layers * W + (size_t)wib * (n_layers + 2) * W;
+  float* wbase = smem + (size_t)wib * (3 * n_layers + 2) * W;
+  float* acc_w = wbase;
+  float* acc_b = wbase + (size_t)n_layers * W;
+  float* xs = wbase + (size_t)2 * n_layers * W;
   float* g = xs + (size_t)n_layers * W;
   float* dx0 = g + W;
-  for (int i = threadIdx.x; i < 2 * n_layers * W; i += blockDim.x) smem[i] = 0.f;
-  __syncthreads();
+  for (int i = lane; i < 2 * n_layers * W; i += 32) wbase[i] = 0.f;
+  __syncwarp();
   const int warp = blockIdx.x * kCrossWarps + wib;
   const int n_warps = gridDim.x * kCrossWarps;
   for (int row = warp; row < B; row += n_warps) {
@@ -82,8 +84,8 @@ cross_bwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
       const float sl = __ldg(s + l);
       for (int c = lane; c < W; c += 32) {
         const float gc = g[c];
-        atomicAdd(&acc_b[(size_t)l * W + c], gc);
-        atomicAdd(&acc_w[(size_t)l * W + c], xl[c] * gx0);
+        acc_b[(size_t)l * W + c] += gc;
+        acc_w[(size_t)l * W + c] += xl[c] * gx0;
         dx0[c] += gc * sl;
         g[c] = gc + __ldg(kernels + (size_t)l * W + c) * gx0;
       }
@@ -92,10 +94,184 @@ cross_bwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
     for (int c = lane; c < W; c += 32) dX[(int64_t)row * W + c] = g[c] + dx0[c];
     __syncwarp();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n_layers * W; i += blockDim.x) {
+  __syncwarp();
+  for (int i = lane; i < n_layers * W; i += 32) {
     if (acc_w[i] != 0.f) atomicAdd(d_kernels + i, acc_w[i]);
     if (acc_b[i] != 0.f) atomicAdd(d_biases + i, acc_b[i]);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Register-resident variants (W <= 32*PER): a lane keeps its PER columns of x0 / x_l / g in registers,
+// so a row costs one coalesced read and one coalesced write and the layers run out of registers.
+//
+// Backward without per-row weight-gradient traffic.  With s_l = x_l . w_l (saved by forward),
+//   x_l = x0 * A_l + Bsum_l,   A_l = 1 + sum_{l'<l} s_l',  Bsum_l = sum_{l'<l} b_l'
+//   gx_l = g_{l+1} . x0        (g_{l+1} = dLoss/dx_{l+1}),   g_l = g_{l+1} + w_l * gx_l
+// so   dW_l[c] = sum_rows x_l[c] gx_l = sum_rows X[row,c] * (A_l gx_l)(row)  +  Bsum_l[c] * sum_rows gx_l
+//      db_l[c] = sum_rows g_{l+1}[c]  = colsum(dY)[c] + sum_{l'>l} w_l'[c] * sum_rows gx_l'
+// i.e. the per-row kernel only emits dX and two [B, L] scalar tables; the weight gradients are one
+// column reduction (X^T coef, colsum dY) plus a W x L combine.
+// ------------------------------------------------------------------------------------------
+constexpr int kCrossMaxL = 8;
+
+template <int PER>
+__global__ void __launch_bounds__(256) cross_fwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
+                                                             const float* __restrict__ biases, float* __restrict__ Y,
+                                                             float* __restrict__ xw_saved, int B, int W, int n_layers) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < B; row += n_warps) {
+    float x0[PER], xl[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int c = lane + 32 * k;
+      x0[k] = c < W ? X[(int64_t)row * W + c] : 0.f;
+      xl[k] = x0[k];
+    }
+    for (int l = 0; l < n_layers; ++l) {
+      const float* w = kernels + (size_t)l * W;
+      const float* b = biases + (size_t)l * W;
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        if (c < W) dot = fmaf(xl[k], __ldg(w + c), dot);
+      }
+      dot = warp_sum(dot);
+      if (xw_saved && lane == 0) xw_saved[(int64_t)row * n_layers + l] = dot;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int c = lane + 32 * k;
+        if (c < W) xl[k] = fmaf(x0[k], dot, xl[k]) + __ldg(b + c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int c = lane + 32 * k;
+      if (c < W) Y[(int64_t)row * W + c] = xl[k];
+    }
+  }
+}
+
+template <int PER>
+__global__ void __launch_bounds__(256) cross_bwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
+                                                             const float* __restrict__ xw_saved, const float* __restrict__ dY,
+                                                             float* __restrict__ dX, float* __restrict__ coef,
+                                                             float* __restrict__ gx, int B, int W, int n_layers) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < B; row += n_warps) {
+    float x0[PER], g[PER], dx0[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int c = lane + 32 * k;
+      x0[k] = c < W ? X[(int64_t)row * W + c] : 0.f;
+      g[k] = c < W ? dY[(int64_t)row * W + c] : 0.f;
+      dx0[k] = 0.f;
+    }
+    float sl[kCrossMaxL], al[kCrossMaxL];
+    float run = 1.f;
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l) {
+      sl[l] = l < n_layers ? __ldg(xw_saved + (int64_t)row * n_layers + l) : 0.f;
+      al[l] = run;
+      run += sl[l];
+    }
+#pragma unroll
+    for (int l = kCrossMaxL - 1; l >= 0; --l) {
+      if (l < n_layers) {
+        float gx0 = 0.f;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) gx0 = fmaf(g[k], x0[k], gx0);
+        gx0 = warp_sum(gx0);
+        if (lane == 0) {
+          coef[(int64_t)row * n_layers + l] = al[l] * gx0;
+          gx[(int64_t)row * n_layers + l] = gx0;
+        }
+        const float* w = kernels + (size_t)l * W;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int c = lane + 32 * k;
+          dx0[k] = fmaf(g[k], sl[l], dx0[k]);
+          if (c < W) g[k] = fmaf(__ldg(w + c), gx0, g[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int c = lane + 32 * k;
+      if (c < W) dX[(int64_t)row * W + c] = g[k] + dx0[k];
+    }
+  }
+}
+
+// m1[c, l] += sum_rows X[row,c] coef[row,l] ; s[c] += sum_rows dY[row,c]      block = 32 columns x 8 row lanes
+__global__ void cross_colreduce_kernel(const float* __restrict__ X, const float* __restrict__ dY,
+                                       const float* __restrict__ coef, float* __restrict__ m1, float* __restrict__ s,
+                                       int B, int W, int n_layers, int rows_per_block) {
+  __shared__ float red[8][32][kCrossMaxL + 1];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r_begin = blockIdx.y * rows_per_block;
+  const int r_end = min(B, r_begin + rows_per_block);
+  float acc[kCrossMaxL + 1];
+#pragma unroll
+  for (int l = 0; l <= kCrossMaxL; ++l) acc[l] = 0.f;
+  if (c < W) {
+    for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const float x = X[(int64_t)r * W + c];
+      acc[kCrossMaxL] += dY[(int64_t)r * W + c];
+#pragma unroll
+      for (int l = 0; l < kCrossMaxL; ++l)
+        if (l < n_layers) acc[l] = fmaf(x, __ldg(coef + (int64_t)r * n_layers + l), acc[l]);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l <= kCrossMaxL; ++l) red[threadIdx.y][threadIdx.x][l] = acc[l];
+  __syncthreads();
+  if (threadIdx.y == 0 && c < W) {
+    for (int l = 0; l <= kCrossMaxL; ++l) {
+      float v = 0.f;
+      for (int j = 0; j < 8; ++j) v += red[j][threadIdx.x][l];
+      if (l < n_layers) atomicAdd(m1 + (size_t)c * n_layers + l, v);
+      else if (l == kCrossMaxL) atomicAdd(s + c, v);
+    }
+  }
+}
+
+// G[l] = sum_rows gx[row, l]
+__global__ void cross_gsum_kernel(const float* __restrict__ gx, float* __restrict__ G, int B, int n_layers) {
+  float acc[kCrossMaxL];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) acc[l] = 0.f;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x)
+#pragma unroll
+    for (int l = 0; l < kCrossMaxL; ++l)
+      if (l < n_layers) acc[l] += gx[(int64_t)r * n_layers + l];
+#pragma unroll
+  for (int l = 0; l < kCrossMaxL; ++l) {
+    const float v = warp_sum(acc[l]);
+    if ((threadIdx.x & 31) == 0 && l < n_layers && v != 0.f) atomicAdd(G + l, v);
+  }
+}
+
+__global__ void cross_combine_kernel(const float* __restrict__ m1, const float* __restrict__ s, const float* __restrict__ G,
+                                     const float* __restrict__ kernels, const float* __restrict__ biases,
+                                     float* __restrict__ d_kernels, float* __restrict__ d_biases, int W, int n_layers) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= W) return;
+  float bsum = 0.f;           // Bsum_l[c]
+  for (int l = 0; l < n_layers; ++l) {
+    d_kernels[(size_t)l * W + c] += m1[(size_t)c * n_layers + l] + bsum * G[l];
+    bsum += biases[(size_t)l * W + c];
+  }
+  float tail = 0.f;           // sum_{l'>l} w_l'[c] G_l'
+  for (int l = n_layers - 1; l >= 0; --l) {
+    d_biases[(size_t)l * W + c] += s[c] + tail;
+    tail += kernels[(size_t)l * W + c] * G[l];
   }
 }
 
@@ -110,6 +286,17 @@ int dtb_cross_fwd(const float* X, const float* kernels, const float* biases, flo
   DTB_CHECK_ARG(X && kernels && biases && Y, "NULL argument");
   DTB_CHECK_ARG(B >= 0 && W > 0 && n_layers >= 0, "bad shape");
   if (B == 0) return DTB_OK;
+  if (W <= 512 && n_layers <= kCrossMaxL) {
+    int blocks = ceil_div(B, 8);
+    const int capr = sm_count() * 8;
+    if (blocks > capr) blocks = capr;
+    if (W <= 128)
+      cross_fwd_reg_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
+    else
+      cross_fwd_reg_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
+    DTB_LAUNCH_OK();
+    return DTB_OK;
+  }
   const size_t smem = (size_t)kCrossWarps * 2 * W * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("dtb_cross_fwd: input width %d too large for the shared-memory row buffers", W);
@@ -125,13 +312,49 @@ int dtb_cross_fwd(const float* X, const float* kernels, const float* biases, flo
   return DTB_OK;
 }
 
+size_t dtb_cross_bwd_workspace_bytes(int B, int W, int n_layers) {
+  if (B <= 0 || W <= 0 || n_layers <= 0) return 0;
+  return ((size_t)2 * B * n_layers + (size_t)W * n_layers + W + n_layers) * sizeof(float) + 64;
+}
+
 int dtb_cross_bwd(const float* X, const float* kernels, const float* biases, const float* xw_saved,
-                  const float* dY, float* dX, float* d_kernels, float* d_biases, int B, int W, int n_layers,
-                  void* stream) {
+                  const float* dY, float* dX, float* d_kernels, float* d_biases, void* workspace,
+                  size_t workspace_bytes, int B, int W, int n_layers, void* stream) {
   DTB_CHECK_ARG(X && kernels && biases && xw_saved && dY && dX && d_kernels && d_biases, "NULL argument");
   DTB_CHECK_ARG(B >= 0 && W > 0 && n_layers > 0, "bad shape");
   if (B == 0) return DTB_OK;
-  const size_t smem = ((size_t)2 * n_layers * W + (size_t)kCrossWarps * (n_layers + 2) * W) * sizeof(float);
+  if (W <= 512 && n_layers <= kCrossMaxL && workspace && workspace_bytes >= dtb_cross_bwd_workspace_bytes(B, W, n_layers)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    float* coef = reinterpret_cast<float*>(workspace);
+    float* gx = coef + (size_t)B * n_layers;
+    float* m1 = gx + (size_t)B * n_layers;
+    float* s = m1 + (size_t)W * n_layers;
+    float* G = s + W;
+    DTB_CUDA_OK(cudaMemsetAsync(m1, 0, ((size_t)W * n_layers + W + n_layers) * sizeof(float), st));
+    int blocks = ceil_div(B, 8);
+    const int capr = sm_count() * 8;
+    if (blocks > capr) blocks = capr;
+    if (W <= 128)
+      cross_bwd_reg_kernel<4><<<blocks, 256, 0, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
+    else
+      cross_bwd_reg_kernel<16><<<blocks, 256, 0, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
+    DTB_LAUNCH_OK();
+    const int col_blocks = ceil_div(W, 32);
+    int row_blocks = ceil_div((int64_t)sm_count() * 8, col_blocks);
+    if (row_blocks > ceil_div(B, 64)) row_blocks = ceil_div(B, 64);
+    if (row_blocks < 1) row_blocks = 1;
+    const int rpb = ceil_div(B, row_blocks);
+    cross_colreduce_kernel<<<dim3(col_blocks, ceil_div(B, rpb)), dim3(32, 8), 0, st>>>(X, dY, coef, m1, s, B, W, n_layers, rpb);
+    DTB_LAUNCH_OK();
+    int gb = ceil_div(B, 256 * 8);
+    if (gb > sm_count()) gb = sm_count();
+    cross_gsum_kernel<<<gb < 1 ? 1 : gb, 256, 0, st>>>(gx, G, B, n_layers);
+    DTB_LAUNCH_OK();
+    cross_combine_kernel<<<ceil_div(W, 128), 128, 0, st>>>(m1, s, G, kernels, biases, d_kernels, d_biases, W, n_layers);
+    DTB_LAUNCH_OK();
+    return DTB_OK;
+  }
+  const size_t smem = (size_t)kCrossWarps * (3 * n_layers + 2) * W * sizeof(float);
   if (smem > 200 * 1024) {
     set_error("dtb_cross_bwd: width %d x %d layers exceeds the shared-memory budget", W, n_layers);
     return DTB_ERR_UNSUPPORTED;

@@ -55,7 +55,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Streaming 16-byte load that does not pollute L1 (embedding rows are touched once per kernel).
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  // L2::64B: an embedding row is 64 bytes at a random address -- do not let L2 pull the neighbouring
+  // 64 bytes of the 128-byte line from HBM (measured: 1.83x read amplification without the hint)
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;

@@ -22,8 +22,118 @@ __device__ __forceinline__ bool pow2(int x) { return x > 0 && (x & (x - 1)) == 0
 // ------------------------------------------------------------------------------------------
 // fast path: D % 4 == 0, Q = D/4 in {1,2,4,8,16,32}
 // ------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(kThreads)
 fm_linear_fwd_vec(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                  const int64_t* __restrict__ row_offsets, const float* __restrict__ dense,
+                  const float* __restrict__ w_lin, float* __restrict__ out_lin,
+                  float* __restrict__ out_fm, int B, int F, int D, int C, int* status) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kWarps) + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * kWarps;
+  const int Q = D >> 2;
+  const int S = F * Q;
+  const float qscale = (float)Q * (1.0f / 32.0f);
+  // A lane's float4 slots (lane, lane+32, ...) are the same (field, quarter) pairs for EVERY batch row:
+  // resolve field, table base pointer, vocabulary size and linear weight once, outside the row loop.
+  // NCH chunks of 4 slots per lane cover F*D/4 <= NCH*128 float4 per row (wider rows: fm_linear_fwd_vec_loop).
+  constexpr int kMaxSlots = NCH * kChunk;
+  const float* sbase[kMaxSlots];
+  int sfield[kMaxSlots];
+  int svocab[kMaxSlots];
+  float swl[kMaxSlots];
+#pragma unroll
+  for (int c = 0; c < kMaxSlots; ++c) {
+    const int slot = c * 32 + lane;
+    sfield[c] = -1;
+    svocab[c] = 0;
+    swl[c] = 0.f;
+    sbase[c] = table;
+    if (slot < S) {
+      const int f = slot / Q;
+      const int64_t lo = row_offsets[f];
+      sfield[c] = f;
+      svocab[c] = (int)(row_offsets[f + 1] - lo);
+      sbase[c] = table + lo * D + ((slot - f * Q) << 2);
+      swl[c] = out_lin ? __ldg(w_lin + f) : 0.f;
+    }
+  }
+
+  for (int row0 = warp * kRowsPerPass; row0 < B; row0 += n_warps * kRowsPerPass) {
+    float4 acc[kRowsPerPass];
+    float sq[kRowsPerPass], lin[kRowsPerPass];
+#pragma unroll
+    for (int r = 0; r < kRowsPerPass; ++r) {
+      acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      sq[r] = 0.f;
+      lin[r] = 0.f;
+    }
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      {
+        int id[kRowsPerPass][kChunk];
+#pragma unroll
+        for (int r = 0; r < kRowsPerPass; ++r)
+#pragma unroll
+          for (int c = 0; c < kChunk; ++c) {
+            const int k = cc * kChunk + c;
+            id[r][c] = -1;
+            if (sfield[k] >= 0 && row0 + r < B) id[r][c] = __ldg(idx + (int64_t)(row0 + r) * F + sfield[k]);
+          }
+        float4 e[kRowsPerPass][kChunk];
+#pragma unroll
+        for (int r = 0; r < kRowsPerPass; ++r)
+#pragma unroll
+          for (int c = 0; c < kChunk; ++c) {
+            const int k = cc * kChunk + c;
+            e[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((unsigned)id[r][c] < (unsigned)svocab[k]) {
+              e[r][c] = ldg_stream_f4(sbase[k] + (int64_t)id[r][c] * D);
+            } else if (status && sfield[k] >= 0 && row0 + r < B) {
+              atomicOr(status, 1 << (sfield[k] & 31));
+            }
+          }
+#pragma unroll
+        for (int r = 0; r < kRowsPerPass; ++r)
+#pragma unroll
+          for (int c = 0; c < kChunk; ++c) {
+            const float4 v = e[r][c];
+            acc[r].x += v.x; acc[r].y += v.y; acc[r].z += v.z; acc[r].w += v.w;
+            sq[r] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            lin[r] += swl[cc * kChunk + c] * ((v.x + v.y) + (v.z + v.w));
+          }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerPass; ++r) {
+      const int row = row0 + r;
+      if (row >= B) break;   // warp-uniform
+      if (out_fm) {
+        float4 a = acc[r];
+        for (int o = 16; o >= Q; o >>= 1) {
+          a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+          a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+          a.z += __shfl_xor_sync(0xffffffffu, a.z, o);
+          a.w += __shfl_xor_sync(0xffffffffu, a.w, o);
+        }
+        // every lane of a q-class now holds the class total: scale by Q/32 so the warp sum counts it once
+        const float s2 = (a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w) * qscale;
+        const float v = warp_sum(s2 - sq[r]);
+        if (lane == 0) out_fm[row] = 0.5f * v;
+      }
+      if (out_lin) {
+        float l = lin[r];
+        for (int c = lane; c < C; c += 32) l += __ldg(w_lin + F + c) * __ldg(dense + (int64_t)row * C + c);
+        l = warp_sum(l);
+        if (lane == 0) out_lin[row] = l;
+      }
+    }
+  }
+}
+
+// any-width variant (slots resolved inside the row loop)
+__global__ void __launch_bounds__(kThreads)
+fm_linear_fwd_vec_loop(const int32_t* __restrict__ idx, const float* __restrict__ table,
                   const int64_t* __restrict__ row_offsets, const float* __restrict__ dense,
                   const float* __restrict__ w_lin, float* __restrict__ out_lin,
                   float* __restrict__ out_fm, int B, int F, int D, int C, int* status) {
@@ -321,6 +431,7 @@ static bool vec_ok(int D, const void* table) {
   return D % 4 == 0 && Q <= 32 && (Q & (Q - 1)) == 0 && (reinterpret_cast<uintptr_t>(table) % 16) == 0;
 }
 
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -341,8 +452,16 @@ int dtb_fm_linear_fwd(const int32_t* idx, const float* table, const int64_t* row
     int blocks = ceil_div(warps, kWarps);
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    fm_linear_fwd_vec<<<blocks, kThreads, 0, st>>>(idx, table, row_offsets, dense, w_lin, out_lin, out_fm,
-                                                   B, F, D, C, status);
+    const int S = F * (D / 4);
+    if (S <= 128)
+      fm_linear_fwd_vec<1><<<blocks, kThreads, 0, st>>>(idx, table, row_offsets, dense, w_lin, out_lin, out_fm, B, F,
+                                                        D, C, status);
+    else if (S <= 256)
+      fm_linear_fwd_vec<2><<<blocks, kThreads, 0, st>>>(idx, table, row_offsets, dense, w_lin, out_lin, out_fm, B, F,
+                                                        D, C, status);
+    else
+      fm_linear_fwd_vec_loop<<<blocks, kThreads, 0, st>>>(idx, table, row_offsets, dense, w_lin, out_lin, out_fm, B,
+                                                          F, D, C, status);
   } else {
     fm_linear_fwd_generic<<<ceil_div(B, 128), 128, 0, st>>>(idx, table, row_offsets, dense, w_lin, out_lin,
                                                             out_fm, B, F, D, C, status);

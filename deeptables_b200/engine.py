@@ -430,8 +430,10 @@ class CrossFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dk = torch.zeros_like(kernels)
         db = torch.zeros_like(biases)
+        ws_bytes = N.lib.dtb_cross_bwd_workspace_bytes(b, w, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(N.lib.dtb_cross_bwd(ptr(x), ptr(kernels), ptr(biases), ptr(xw), ptr(dy), ptr(dx), ptr(dk), ptr(db),
-                                  b, w, n, stream_ptr()), 'cross_bwd')
+                                  ptr(ws), ws_bytes, b, w, n, stream_ptr()), 'cross_bwd')
         return dx, dk, db
 
 

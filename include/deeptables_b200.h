@@ -197,9 +197,10 @@ int dtb_tc_selftest(const float* A, const float* Bmat, float* C, void* workspace
  * xw_saved [B, n_layers] keeps the per-layer scalars x_l.w_l for backward. */
 int dtb_cross_fwd(const float* X, const float* kernels, const float* biases, float* Y,
                   float* xw_saved, int B, int W, int n_layers, void* stream);
+size_t dtb_cross_bwd_workspace_bytes(int B, int W, int n_layers);
 int dtb_cross_bwd(const float* X, const float* kernels, const float* biases, const float* xw_saved,
-                  const float* dY, float* dX, float* d_kernels, float* d_biases, int B, int W,
-                  int n_layers, void* stream);
+                  const float* dY, float* dX, float* d_kernels, float* d_biases, void* workspace,
+                  size_t workspace_bytes, int B, int W, int n_layers, void* stream);
 
 /* ---- InnerProduct / OuterProduct (layers.py:473-487, 541-581), gather fused --------------- */
 /* ip[B,P] (NULL: skipped), op[B,P] (NULL: skipped); P = F(F-1)/2 pairs (i<j) row-major.

@@ -420,7 +420,9 @@ def test_cross_fwd_bwd(nat, b, w, n):
     dy = g.normal(size=(b, w)).astype(np.float32)
     dX = torch.empty(b, w, device='cuda')
     dK, dB = torch.zeros(n, w, device='cuda'), torch.zeros(n, w, device='cuda')
-    nat.check(nat.lib.dtb_cross_bwd(P(X), P(K), P(Bv), P(xw), P(dev(dy)), P(dX), P(dK), P(dB), b, w, n, None))
+    wsb = nat.lib.dtb_cross_bwd_workspace_bytes(b, w, n)
+    wsc = torch.empty(wsb, dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_cross_bwd(P(X), P(K), P(Bv), P(xw), P(dev(dy)), P(dX), P(dK), P(dB), P(wsc), wsb, b, w, n, None))
     grads = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64] + k64 + b64)
     sc = max(1.0, float(grads[0].abs().max()))
     np.testing.assert_allclose(dX.cpu().numpy(), grads[0].numpy(), rtol=1e-3, atol=1e-4 * sc)
