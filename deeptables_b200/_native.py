@@ -56,6 +56,8 @@ _SIGNATURES = {
                             c_int, c_int, P, P]),
     'dtb_cin_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, _IP, c_int,
                             c_int, c_int, c_int, P]),
+    'dtb_cin_bwd_phase': (c_int, [P, P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, _IP, c_int,
+                                  c_int, c_int, c_int, c_int, P]),
     'dtb_cin_tc_supported': (c_int, [c_int, c_int, _IP, c_int, c_int]),
     'dtb_cin_tc_set_variant': (c_int, [c_int]),
     'dtb_tc_selftest': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),

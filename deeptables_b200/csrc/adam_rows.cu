@@ -208,13 +208,16 @@ __global__ void grad_rows_pack_kernel(const int32_t* __restrict__ idx, const int
     if (row >= 0 && q == 0) old = atomicMax(claim + row, step);
     old = __shfl_sync(0xffffffffu, old, lane - q);
     if (!live) continue;
+    const bool mine = row >= 0 && old < step;
+    float4* src = reinterpret_cast<float4*>(grad + (mine ? row : 0) * D + (q << 2));
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row >= 0 && old < step) {
-      float4* src = reinterpret_cast<float4*>(grad + row * D + (q << 2));
-      v = *src;
-      *src = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    if (mine) v = *src;
     *reinterpret_cast<float4*>(packed + ref * D + (q << 2)) = v;
+    // Zero the row only AFTER the store above, which cannot issue before the load has returned.  A zero
+    // store issued right behind the load hits the line while its miss is still pending and the LSU
+    // replays it: measured 1.1 ms instead of 0.2 ms for this kernel (tools/pack_probe.cu, V2 vs V6).
+    asm volatile("" ::: "memory");
+    if (mine) *src = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 

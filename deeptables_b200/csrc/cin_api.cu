@@ -62,10 +62,10 @@ int dtb_cin_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
                       act, status, st);
 }
 
-int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets, const float* weights,
-                const float* d_pooled, const void* saved, float* grad_table, float* d_weights, float* d_bias,
-                void* workspace, size_t workspace_bytes, int B, int F, int D, const int* layer_sizes_host,
-                int n_layers, int direct, int act, int precision, void* stream) {
+static int cin_bwd_impl(const int32_t* idx, const float* table, const int64_t* row_offsets, const float* weights,
+                        const float* d_pooled, const void* saved, float* grad_table, float* d_weights, float* d_bias,
+                        void* workspace, size_t workspace_bytes, int B, int F, int D, const int* layer_sizes_host,
+                        int n_layers, int direct, int act, int precision, int phase, void* stream) {
   DTB_CHECK_ARG(idx && table && row_offsets && weights && d_pooled && saved && grad_table && d_weights &&
                     workspace,
                 "NULL argument");
@@ -80,13 +80,31 @@ int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(s, precision))
     return cin_tc_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
-                      workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3, st);
+                      workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3, phase, st);
   if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1) {
     set_error("dtb_cin_bwd: tensor-core path requested but shape unsupported (F=%d D=%d)", F, D);
     return DTB_ERR_UNSUPPORTED;
   }
+  if (phase == 2) return DTB_OK;
   return cin_fp32_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
                       workspace, workspace_bytes, B, act, st);
+}
+
+int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets, const float* weights,
+                const float* d_pooled, const void* saved, float* grad_table, float* d_weights, float* d_bias,
+                void* workspace, size_t workspace_bytes, int B, int F, int D, const int* layer_sizes_host,
+                int n_layers, int direct, int act, int precision, void* stream) {
+  return cin_bwd_impl(idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias, workspace,
+                      workspace_bytes, B, F, D, layer_sizes_host, n_layers, direct, act, precision, 0, stream);
+}
+
+int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row_offsets, const float* weights,
+                      const float* d_pooled, const void* saved, float* grad_table, float* d_weights, float* d_bias,
+                      void* workspace, size_t workspace_bytes, int B, int F, int D, const int* layer_sizes_host,
+                      int n_layers, int direct, int act, int precision, int phase, void* stream) {
+  DTB_CHECK_ARG(phase == 1 || phase == 2, "phase must be 1 (embedding gradient) or 2 (weight gradient)");
+  return cin_bwd_impl(idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias, workspace,
+                      workspace_bytes, B, F, D, layer_sizes_host, n_layers, direct, act, precision, phase, stream);
 }
 
 }  // extern "C"

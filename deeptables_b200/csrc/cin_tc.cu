@@ -1241,10 +1241,14 @@ static bool cin_tc_bwd_supported(const CinShape& s) {
 int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* d_pooled, const void* saved, float* grad_table,
                float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
-               int n_pass, cudaStream_t st) {
-  if (!cin_tc_bwd_supported(s) || g_tc_bwd_fp32)
+               int n_pass, int phase, cudaStream_t st) {
+  // phase 0: everything; 1: the embedding-gradient part (weight pack + dgrad); 2: the weight-gradient part
+  // (wgrad + bias).  Lets the host start the data-parallel exchange of the table gradient under the wgrad.
+  if (!cin_tc_bwd_supported(s) || g_tc_bwd_fp32) {
+    if (phase == 2) return DTB_OK;
     return cin_fp32_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
                         workspace, workspace_bytes, B, act, st);
+  }
   if (workspace_bytes < cin_tc_bwd_workspace_bytes(s, B)) {
     set_error("dtb_cin_bwd: workspace too small for the tensor-core backward");
     return DTB_ERR_INVALID_ARG;
@@ -1269,23 +1273,25 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    cin_tc_pack_t_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k]);
-    DTB_LAUNCH_OK();
+    if (phase != 2) {
+      cin_tc_pack_t_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k]);
+      DTB_LAUNCH_OK();
+    }
     woff += chunk * s.F;
     soff += (size_t)B * s.D * s.L[k];
     if ((int)chunk > bstage) bstage = (int)chunk;
   }
   p.b_stage_bytes = bstage;
   const TcBwdSmemLayout lay = tc_bwd_layout(bstage, s.F);
-  int rc;
-  switch (s.D) {
+  int rc = DTB_OK;
+  if (phase != 2) switch (s.D) {
     case 4: rc = launch_dgrad<4>(p, lay.total, st); break;
     case 8: rc = launch_dgrad<8>(p, lay.total, st); break;
     case 16: rc = launch_dgrad<16>(p, lay.total, st); break;
     case 32: rc = launch_dgrad<32>(p, lay.total, st); break;
     default: set_error("dtb_cin_bwd: embedding dim %d unsupported", s.D); return DTB_ERR_UNSUPPORTED;
   }
-  if (rc != DTB_OK) return rc;
+  if (rc != DTB_OK || phase == 1) return rc;
   // ---- wgrad, one launch per layer ------------------------------------------------------------
   const int R = 128 / s.D;
   const size_t n_super = ((size_t)B + 2 * R - 1) / (2 * R);

@@ -250,6 +250,13 @@ class DeepModel:
             flatten_emb_layer = _LazyFlat(scope, embeddings) if self.n_fields else None
             if capture and 'flatten_embeddings' in capture and flatten_emb_layer is not None:
                 flatten_emb_layer._get()
+            # cin_nets is evaluated before anything else touches the embedding table: autograd runs nodes
+            # in reverse creation order, so its backward comes last and its weight-gradient kernels can hide
+            # the data-parallel exchange of the table gradient (engine._table_grad_done).  It does not use
+            # concat_emb_dense (reference deepnets.py:69-81).
+            results = {}
+            if 'cin_nets' in cfg.nets and self.n_fields:
+                results['cin_nets'] = deepnets.get('cin_nets')(embeddings, flatten_emb_layer, dense_layer, None, cfg, desc)
             # concat_embedding_dense + bn_concat_emb_dense (reference deepmodel.py:348-361)
             if block is not None:
                 x = E.ConcatEmbDenseFn.apply(block.table.anchor, dense_layer, block)
@@ -261,13 +268,13 @@ class DeepModel:
             concat_emb_dense = L.BatchNormalization(name='bn_concat_emb_dense')(x)
             if describe:
                 desc.set_concat_embed_dense(tuple(concat_emb_dense.shape))
-            outs = OrderedDict()
             for net in cfg.nets:
+                if net in results:
+                    continue
                 fn = deepnets.get(net)
-                out = fn(embeddings if self.n_fields else [], flatten_emb_layer, dense_layer, concat_emb_dense,
-                         cfg, desc)
-                if out is not None:
-                    outs[net] = out
+                results[net] = fn(embeddings if self.n_fields else [], flatten_emb_layer, dense_layer,
+                                  concat_emb_dense, cfg, desc)
+            outs = OrderedDict((net, results[net]) for net in cfg.nets if results[net] is not None)
             if len(outs) > 1:
                 logits = []
                 for name, out in outs.items():
@@ -351,6 +358,10 @@ class DeepModel:
             t.ensure_training_state()
             self._select_table_optimizer(self.world_size * cat.shape[0] * t.n_fields)
             self._catch_up(cat, self._step)
+        if t is not None:
+            t.pending_bwd = 0
+            t.on_grad_final = (lambda: self._begin_table_exchange(cat)) if (self._dist and t.lazy_adam) else None
+        self._early_exchange = None
         z = self._forward(cat, cont, training=True)
         prob, dz = E.loss_forward_backward(z, y, self.task, sample_weight, True, self._loss_acc)
         dp.scale_for_mean(dz)
@@ -377,26 +388,43 @@ class DeepModel:
         self._step = step
         return prob
 
-    def _exchange_gradients(self, cat):
-        """Data-parallel exchange (dp.py): dense bucket + table gradient all-reduce, ids all-gather;
-        rows first touched by another rank this step are caught up before the row-wise Adam."""
+    def _row_exchange_fns(self, cat):
         t = self.table
-        pack = unpack = None
-        if t is not None and t.lazy_adam:
-            step = self._step + 1
-            if t.claim is None:
-                t.claim = torch.zeros(t.total_rows, dtype=torch.int32, device=self.device)
+        step = self._step + 1
+        if t.claim is None:
+            t.claim = torch.zeros(t.total_rows, dtype=torch.int32, device=self.device)
 
-            def pack():
-                packed = torch.empty(cat.shape[0], t.n_fields, t.dim, dtype=torch.float32, device=self.device)
-                check(N.lib.dtb_grad_rows_pack(ptr(cat), ptr(t.row_offsets), ptr(t.grad), ptr(t.claim), ptr(packed),
-                                               step, cat.shape[0], t.n_fields, t.dim, stream_ptr()), 'grad_rows_pack')
-                return packed
+        def pack():
+            packed = torch.empty(cat.shape[0], t.n_fields, t.dim, dtype=torch.float32, device=self.device)
+            check(N.lib.dtb_grad_rows_pack(ptr(cat), ptr(t.row_offsets), ptr(t.grad), ptr(t.claim), ptr(packed),
+                                           step, cat.shape[0], t.n_fields, t.dim, stream_ptr()), 'grad_rows_pack')
+            return packed
 
-            def unpack(ids, packed):
-                check(N.lib.dtb_grad_rows_unpack(ptr(ids), ptr(t.row_offsets), ptr(packed), ptr(t.grad), ids.shape[0],
-                                                 t.n_fields, t.dim, stream_ptr()), 'grad_rows_unpack')
-        union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat, pack, unpack)
+        def unpack(ids, packed):
+            check(N.lib.dtb_grad_rows_unpack(ptr(ids), ptr(t.row_offsets), ptr(packed), ptr(t.grad), ids.shape[0],
+                                             t.n_fields, t.dim, stream_ptr()), 'grad_rows_unpack')
+        return pack, unpack
+
+    def _begin_table_exchange(self, cat):
+        """Called from inside backward the moment the table gradient is final (engine._table_grad_done):
+        pack this rank's rows and start the all-gathers so they run under the remaining backward kernels."""
+        pack, unpack = self._row_exchange_fns(cat)
+        self._early_exchange = dp.TableExchange(cat, pack, unpack)
+
+    def _exchange_gradients(self, cat):
+        """Data-parallel exchange (dp.py): dense bucket all-reduce + row-wise table-gradient exchange; rows
+        first touched by another rank this step are caught up before the row-wise Adam."""
+        t = self.table
+        early = getattr(self, '_early_exchange', None)
+        self._early_exchange = None
+        if early is not None:
+            torch.distributed.all_reduce(self._scope.flat_g)
+            union = early.finish()
+        else:
+            pack = unpack = None
+            if t is not None and t.lazy_adam:
+                pack, unpack = self._row_exchange_fns(cat)
+            union = dp.exchange(self._scope.flat_g, t.grad if t is not None else None, cat, pack, unpack)
         if t is not None:
             self._catch_up(union, self._step)     # lazy mode: rows first touched by another rank this step
         return union

@@ -67,6 +67,34 @@ def exchange(flat_grad, table_grad, cat_ids, pack_rows=None, unpack_rows=None):
     return all_ids.reshape(-1, ids.shape[-1])
 
 
+class TableExchange:
+    """The row-wise exchange in two halves so that the all-gathers run under other kernels:
+    ``begin`` (pack + asynchronous all-gathers) as soon as the table gradient is final, ``finish``
+    (wait + rank-ordered unpack) right before the optimiser."""
+
+    def __init__(self, cat_ids, pack_rows, unpack_rows):
+        self.ids = cat_ids.contiguous()
+        self.unpack_rows = unpack_rows
+        world = dist.get_world_size()
+        self.all_ids = torch.empty((world,) + tuple(self.ids.shape), dtype=self.ids.dtype, device=self.ids.device)
+        self.packed = pack_rows()
+        self.all_packed = torch.empty((world,) + tuple(self.packed.shape), dtype=self.packed.dtype,
+                                      device=self.packed.device)
+        if self.ids.is_cuda:
+            self.works = [dist.all_gather_into_tensor(self.all_ids, self.ids, async_op=True),
+                          dist.all_gather_into_tensor(self.all_packed, self.packed, async_op=True)]
+        else:
+            self.works = [dist.all_gather(list(self.all_ids.unbind(0)), self.ids, async_op=True),
+                          dist.all_gather(list(self.all_packed.unbind(0)), self.packed, async_op=True)]
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        for r in range(self.all_ids.shape[0]):          # fixed order => identical bits on every replica
+            self.unpack_rows(self.all_ids[r], self.all_packed[r])
+        return self.all_ids.reshape(-1, self.ids.shape[-1])
+
+
 def broadcast_parameters(tensors, src=0):
     """Identical replicas at start: rank ``src``'s initial weights win."""
     if is_distributed():

@@ -164,6 +164,24 @@ def _grad_target(table):
     return table.grad
 
 
+def _note_consumer(ctx, table):
+    """Forward of a table-consuming op that autograd will differentiate (the anchor input requires grad
+    and grad mode was on at apply time): one more backward will add into table.grad."""
+    if ctx.needs_input_grad[0] and not getattr(table, 'is_tensor_table', False):
+        table.pending_bwd = getattr(table, 'pending_bwd', 0) + 1
+
+
+def _table_grad_done(table):
+    """An op finished its contribution to table.grad.  When it was the last one of the step the table
+    gradient is final and the data-parallel exchange may start -- possibly while weight-gradient kernels
+    of the same op are still to be launched (CINFn)."""
+    if getattr(table, 'is_tensor_table', False):
+        return
+    table.pending_bwd = getattr(table, 'pending_bwd', 1) - 1
+    if table.pending_bwd == 0 and getattr(table, 'on_grad_final', None) is not None:
+        table.on_grad_final()
+
+
 class _TableBackwardMixin:
     @staticmethod
     def finish_tensor_table(table):
@@ -188,6 +206,7 @@ class GatherFn(torch.autograd.Function):
         check(N.lib.dtb_embedding_gather(ptr(idx), ptr(w), ptr(offs), ptr(out), b, t.n_fields, t.dim,
                                          ptr(t.status), stream_ptr()), 'embedding_gather')
         ctx.block = block
+        _note_consumer(ctx, t)
         return out
 
     @staticmethod
@@ -197,6 +216,7 @@ class GatherFn(torch.autograd.Function):
         g = _f32(g)
         check(N.lib.dtb_embedding_scatter_add(ptr(idx), ptr(offs), ptr(g), ptr(gt), idx.shape[0], t.n_fields,
                                               t.dim, stream_ptr()), 'embedding_scatter_add')
+        _table_grad_done(t)
         return _TableBackwardMixin.finish_tensor_table(t), None
 
 
@@ -221,6 +241,8 @@ class FMLinearFn(torch.autograd.Function):
         ctx.block, ctx.dims = block, (b, f, d, c)
         ctx.save_for_backward(dense, w_lin)
         ctx.want = (want_lin, want_fm)
+        if t is not None:
+            _note_consumer(ctx, t)
         outs = tuple(o for o in (out_lin, out_fm) if o is not None)
         return outs if len(outs) > 1 else outs[0]
 
@@ -240,6 +262,8 @@ class FMLinearFn(torch.autograd.Function):
         gw = torch.zeros_like(w_lin) if want_lin else None
         check(N.lib.dtb_fm_linear_bwd(ptr(idx), ptr(w), ptr(offs), ptr(dense), ptr(w_lin), ptr(g_lin),
                                       ptr(g_fm), ptr(gt), ptr(gw), b, f, d, c, stream_ptr()), 'fm_linear_bwd')
+        if t is not None:
+            _table_grad_done(t)
         ga = _TableBackwardMixin.finish_tensor_table(t) if t is not None else None
         return ga, None, gw, None, None, None
 
@@ -256,6 +280,7 @@ class ConcatEmbDenseFn(torch.autograd.Function):
         check(N.lib.dtb_concat_emb_dense_fwd(ptr(idx), ptr(w), ptr(offs), ptr(dense), ptr(x), b, f, d, c,
                                              ptr(t.status), stream_ptr()), 'concat_emb_dense_fwd')
         ctx.block, ctx.dims = block, (b, f, d, c)
+        _note_consumer(ctx, t)
         return x
 
     @staticmethod
@@ -266,6 +291,7 @@ class ConcatEmbDenseFn(torch.autograd.Function):
         g = _f32(g)
         check(N.lib.dtb_concat_emb_dense_bwd(ptr(idx), ptr(offs), ptr(g), ptr(gt), b, f, d, c, stream_ptr()),
               'concat_emb_dense_bwd')
+        _table_grad_done(t)
         return _TableBackwardMixin.finish_tensor_table(t), None, None
 
 
@@ -387,6 +413,7 @@ class CINFn(torch.autograd.Function):
         ctx.block, ctx.cfg = block, (b, f, d, tuple(sizes), int(direct), act, precision)
         ctx.saved_buf, ctx.ws, ctx.has_bias = saved, ws, bias is not None
         ctx.save_for_backward(weights)
+        _note_consumer(ctx, t)
         return pooled
 
     @staticmethod
@@ -399,9 +426,13 @@ class CINFn(torch.autograd.Function):
         gt = _grad_target(t)
         dw = torch.zeros_like(weights)
         db = torch.zeros(sum(sizes), dtype=torch.float32, device=w.device) if ctx.has_bias else None
-        check(N.lib.dtb_cin_bwd(ptr(idx), ptr(w), ptr(offs), ptr(weights), ptr(g), ptr(ctx.saved_buf), ptr(gt),
-                                ptr(dw), ptr(db), ptr(ctx.ws), ctx.ws.numel(), b, f, d, sizes_c, len(sizes),
-                                direct, act, precision, stream_ptr()), 'cin_bwd')
+        args = (ptr(idx), ptr(w), ptr(offs), ptr(weights), ptr(g), ptr(ctx.saved_buf), ptr(gt), ptr(dw), ptr(db),
+                ptr(ctx.ws), ctx.ws.numel(), b, f, d, sizes_c, len(sizes), direct, act, precision)
+        # phase 1: everything that adds into the table gradient; then (data parallel) the exchange of the
+        # table gradient may start and overlap phase 2, the weight-gradient kernels
+        check(N.lib.dtb_cin_bwd_phase(*args, 1, stream_ptr()), 'cin_bwd(dgrad)')
+        _table_grad_done(t)
+        check(N.lib.dtb_cin_bwd_phase(*args, 2, stream_ptr()), 'cin_bwd(wgrad)')
         ctx.saved_buf = ctx.ws = None
         return (_TableBackwardMixin.finish_tensor_table(t), dw, db, None, None, None, None, None, None)
 
@@ -453,6 +484,7 @@ class PNNFn(torch.autograd.Function):
                                 PNNFn.KT[kernel_type], ptr(t.status), stream_ptr()), 'pnn_fwd')
         ctx.block, ctx.cfg = block, (b, f, d, want_ip, want_op, kernel_type)
         ctx.save_for_backward(op_kernel)
+        _note_consumer(ctx, t)
         outs = tuple(o for o in (ip, op) if o is not None)
         return outs if len(outs) > 1 else outs[0]
 
@@ -468,6 +500,7 @@ class PNNFn(torch.autograd.Function):
         dk = torch.zeros_like(op_kernel) if want_op else None
         check(N.lib.dtb_pnn_bwd(ptr(idx), ptr(w), ptr(offs), ptr(op_kernel), ptr(d_ip), ptr(d_op), ptr(gt),
                                 ptr(dk), b, f, d, PNNFn.KT[kernel_type], stream_ptr()), 'pnn_bwd')
+        _table_grad_done(t)
         return _TableBackwardMixin.finish_tensor_table(t), dk, None, None, None, None
 
 

@@ -178,6 +178,14 @@ int dtb_cin_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
                 float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int F,
                 int D, const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
                 void* stream);
+/* The same backward in two launches: phase 1 = everything that contributes to grad_table (after it the
+ * embedding gradient of this op is final), phase 2 = d_weights / d_bias.  The host starts the data-parallel
+ * exchange of the table gradient between the two so that it overlaps the weight-gradient kernels. */
+int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                      const float* weights, const float* d_pooled, const void* saved, float* grad_table,
+                      float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int F,
+                      int D, const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
+                      int phase, void* stream);
 /* precision: 0 = auto (tensor-core bf16x3 split when the shape is supported, else fp32 SIMT),
  *            1 = force fp32 SIMT/cuBLAS formulation, 2 = tensor-core bf16x3, 3 = tensor-core bf16x1. */
 #define DTB_CIN_AUTO 0

@@ -206,3 +206,40 @@ def test_lazy_and_dense_table_optimizer_switch_is_transparent():
     for k in results['lazy']:
         for other in ('dense', 'mixed'):
             torch.testing.assert_close(results['lazy'][k], results[other][k], rtol=1e-5, atol=1e-7, msg=f'{other}:{k}')
+
+
+def test_table_gradient_is_final_before_cin_weight_gradient_kernels():
+    """Data-parallel overlap hook: the table gradient must be declared final exactly once per step, after
+    every embedding-gradient producer ran and BEFORE the CIN weight-gradient launches (so the row exchange
+    can run under them)."""
+    from deeptables_b200 import _native as nat
+    vocab, n_cont, b = [40, 30, 20, 50], 3, 64
+    model, conf = build(['linear', 'fm_nets', 'cin_nets', 'dnn_nets', 'pnn_nets'], vocab, 8, n_cont,
+                        cin_params={'cross_layer_size': (16, 16), 'activation': 'relu', 'use_residual': False,
+                                    'use_bias': False, 'direct': False, 'reduce_D': False})
+    idx, cont, y = batch(vocab, n_cont, b)
+    model.train_on_batch(idx, cont, y)                      # allocate training state
+    t = model.table
+    ti, tc, ty = torch.tensor(idx).cuda(), torch.tensor(cont).cuda(), torch.tensor(y).cuda().view(-1, 1)
+    seen = []
+    t.pending_bwd = 0
+    snapshot = {}
+
+    def hook():
+        seen.append(nat.lib.dtb_launch_count())
+        snapshot['grad'] = t.grad.clone()
+
+    z = model._forward(ti, tc, training=True)
+    t.on_grad_final = hook
+    n_consumers = t.pending_bwd
+    assert n_consumers == 5                                  # concat, linear, fm, cin, pnn
+    from deeptables_b200 import engine as E
+    prob, dz = E.loss_forward_backward(z, ty, 'binary', None, True, None)
+    z.backward(dz)
+    end = nat.lib.dtb_launch_count()
+    t.on_grad_final = None
+    assert len(seen) == 1 and t.pending_bwd == 0
+    assert end - seen[0] >= 2                                # the CIN wgrad launches came after the hook
+    assert torch.equal(snapshot['grad'], t.grad)             # nothing touched the table gradient afterwards
+    t.grad.zero_()
+    model._scope.flat_g.zero_()
