@@ -74,6 +74,15 @@ def _worker(rank, world, port, results):
         union2 = dp.exchange(flat2, table2, ids, pack, unpack)
         assert torch.equal(union2, union) and torch.allclose(table2, table) and torch.allclose(flat2, flat)
         assert order == list(range(world))            # ranks applied in rank order on every replica
+        # the split form DeepModel uses to overlap the all-gathers with the CIN weight-gradient kernels:
+        # begin (pack + async all-gathers) inside backward, finish (wait + rank-ordered unpack) before Adam
+        table2 = table_local.clone()
+        order.clear()
+        early = dp.TableExchange(ids, pack, unpack)
+        assert order == [] and float(table2[int(offs[0] + ids[0, 0])].abs().sum()) == 0.0   # packed out, not yet added back
+        union3 = early.finish()
+        assert torch.equal(union3, union) and torch.allclose(table2, table)
+        assert order == list(range(world))
         w = torch.full((3,), float(rank))
         dp.broadcast_parameters([w, None])
         assert torch.equal(w, torch.zeros(3))
