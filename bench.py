@@ -231,8 +231,9 @@ def time_cin_kernel(model, cat, peaks):
     tpath = os.path.join(ROOT, 'profiles', 'r1_cin_tc_traffic.json')
     if tc and os.path.exists(tpath) and b == 65536:
         with open(tpath) as f:
-            tj = json.load(f)['cin_tc_fwd_kernel']
-        traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
+            tj = json.load(f).get('cin_tc_fwd_kernel_compact')     # ncu capture of the current saved-activation format
+        if tj:
+            traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
     return {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
             'frac': tf / peaks['bf16_tflops'], 'traffic': traffic,
             'kernel': 'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)' if tc
@@ -320,7 +321,7 @@ def main():
             'metric': 'xDeepFM train rows/sec, Criteo-shape synthetic', 'value': rows / secs, 'unit': 'rows/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': secs / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (CIN GEMMs: bf16x3 split on '
-            'tcgen05, fp32 accumulate)' if roof['kernel'].startswith('cin_fwd (tcgen05') else 'f32',
+            'tcgen05, fp32 accumulate)' if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
             'data': 'synthetic',
             'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, '
                                    '13 dense + 26 sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])',

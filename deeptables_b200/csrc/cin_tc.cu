@@ -52,6 +52,7 @@ struct CinTcParams {
   unsigned long long bias_off[kCinMaxLayers];
   int b_stage_bytes;                              // bytes reserved per weight stage in smem
   int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
+  int compact;                                    // training: save relu-mask bits instead of the fp32 T_k rows (see cin_tc_compact)
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
 #pragma unroll
       for (int j = 0; j < kMaxHp; ++j) h[j] = (j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
       if (p.saved) {
-        if (b < p.B) {
+        if (b < p.B && !p.compact) {
           float* dst = p.saved + ((size_t)b * D + d) * F;
           for (int j = 0; j < F; ++j) dst[j] = x0g[((size_t)r * F + j) * D + d];
         }
@@ -238,7 +239,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
         tc::fence_after_thread_sync();
         const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
         const float* bias = p.bias ? p.bias + p.bias_off[k] : nullptr;
-        float* sv = (p.saved && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
+        float* sv = (p.saved && !p.compact && b < p.B) ? p.saved + p.saved_off[k] + ((size_t)b * D + d) * L : nullptr;
+        // compact format: one bit per feature map (output > 0) at the head of the T_k region, ceil(L/32) words per row
+        const int mask_words = (L + 31) >> 5;
+        uint32_t* mrow = (p.saved && p.compact && p.act == DTB_ACT_RELU && b < p.B)
+                             ? reinterpret_cast<uint32_t*>(p.saved + p.saved_off[k]) + ((size_t)b * D + d) * mask_words
+                             : nullptr;
+        uint32_t mw[kMaxL / 32];
+#pragma unroll
+        for (int w = 0; w < kMaxL / 32; ++w) mw[w] = 0u;
         // block-transposed copy of the hidden half for the wgrad kernel ([m / 64][j][68], zeros in padded rows)
         float* hb = nullptr;
         if (p.saved && hid_n > 0) {
@@ -266,6 +275,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(sv + cb * 16 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
+            {
+              uint32_t bits = 0u;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) bits |= (o[j] > 0.f ? 1u : 0u) << j;
+              mw[cb >> 1] |= bits << ((cb & 1) * 16);
             }
             if (hb) {
 #pragma unroll
@@ -312,6 +327,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
               }
             }
           }
+        }
+        if (mrow) {
+#pragma unroll
+          for (int w = 0; w < kMaxL / 32; ++w)
+            if (w < mask_words) mrow[w] = mw[w];
         }
         // zero the padding of the next layer's K chunk
         if (k + 1 < p.n_layers) {
@@ -495,7 +515,17 @@ static int g_tc_variant = 1;
 static int g_tc_dbg = 0;
 static int g_tc_bwd_fp32 = 0;   // test hook: run the exact-fp32 backward after the tensor-core forward   // 1: A operand through TMEM (default), 0: through shared memory
 
+static int g_tc_full_save = 0;  // test hook (bit 17 of set_variant): keep the fp32 T_k rows in the saved activations
+
 static bool d_supported(int D) { return D == 4 || D == 8 || D == 16 || D == 32; }
+static bool cin_tc_bwd_supported(const CinShape& s);
+
+// Saved-activation format of a training forward.  Full: x0t + fp32 T_k rows (what the exact-fp32 backward reads)
+// + the block-transposed operand tiles.  Compact: the tensor-core backward needs only the sign of each output
+// (relu mask, 1 bit) and the hidden halves, which the block-transposed tiles already hold -- so T_k shrinks to
+// ceil(L/32) words per row and x0t is not written: -1.7 GB of writes in forward and of reads in dgrad at
+// B = 65 536.  Both halves of a step evaluate this predicate, so it must not change between them.
+static bool cin_tc_compact(const CinShape& s) { return !g_tc_full_save && !g_tc_bwd_fp32 && cin_tc_bwd_supported(s); }
 
 bool cin_tc_supported(const CinShape& s) {
   if (!d_supported(s.D)) return false;
@@ -600,6 +630,7 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   }
   p.b_stage_bytes = bstage;
   p.dbg = g_tc_dbg;
+  p.compact = cin_tc_compact(s) ? 1 : 0;
   const TcSmemLayout lay = tc_layout(bstage, s.F);
 #define DTB_TC_LAUNCH(DD) \
   case DD:                \
@@ -626,6 +657,7 @@ extern "C" {
 int dtb_cin_tc_set_variant(int a_operand_in_tmem) {
   g_tc_dbg = (a_operand_in_tmem >> 8) & 0xff;     // profiling switches ride in bits 8..15
   g_tc_bwd_fp32 = (a_operand_in_tmem >> 16) & 1;  // bit 16: exact-fp32 backward
+  g_tc_full_save = (a_operand_in_tmem >> 17) & 1; // bit 17: full (fp32 T_k) saved activations
   g_tc_variant = (a_operand_in_tmem & 0xff) ? 1 : 0;
   return DTB_OK;
 }
@@ -679,7 +711,9 @@ struct CinTcBwdParams {
   int L[kCinMaxLayers], H[kCinMaxLayers], Hp[kCinMaxLayers];
   int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
   unsigned long long wpack_off[kCinMaxLayers], saved_off[kCinMaxLayers], dc_off[kCinMaxLayers];
+  unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed h_{k+1} tiles (as in CinTcParams)
   int b_stage_bytes;
+  int compact;                                    // saved activations in the compact format (cin_tc_compact)
 };
 
 // weights -> per chunk i: [hi | lo] image of B[n=j][k=l] = W[(i*H + j), l], canonical K-major no swizzle
@@ -793,6 +827,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
         // ---- dC_k row -> TMEM A operand (hi|lo) + HBM tiles for wgrad ---------------------------
         const float* Trow = p.saved + p.saved_off[k] + m_pad * L;
+        const int mask_words = (L + 31) >> 5;
+        uint32_t mw[kMaxL / 32];
+#pragma unroll
+        for (int w = 0; w < kMaxL / 32; ++w) mw[w] = 0u;
+        if (p.compact && p.act == DTB_ACT_RELU && valid) {
+          const uint32_t* mrow = reinterpret_cast<const uint32_t*>(p.saved + p.saved_off[k]) + m_pad * mask_words;
+#pragma unroll
+          for (int w = 0; w < kMaxL / 32; ++w)
+            if (w < mask_words) mw[w] = __ldg(mrow + w);
+        }
         const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
         uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
 #pragma unroll
@@ -801,7 +845,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
             float tv[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-              const float4 q4 = valid ? *reinterpret_cast<const float4*>(Trow + cb * 16 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4 q4 = (valid && !p.compact) ? *reinterpret_cast<const float4*>(Trow + cb * 16 + j)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
               tv[j] = q4.x; tv[j + 1] = q4.y; tv[j + 2] = q4.z; tv[j + 3] = q4.w;
             }
             float dc[16];
@@ -813,7 +858,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
               if (col < kMaxHp) {
                 if (col < hid_n) gsum += dh[col];
               }
-              if (p.act == DTB_ACT_RELU && !(tv[j] > 0.f)) gsum = 0.f;
+              const bool on = p.compact ? (((mw[cb >> 1] >> ((cb & 1) * 16 + j)) & 1u) != 0u) : (tv[j] > 0.f);
+              if (p.act == DTB_ACT_RELU && !on) gsum = 0.f;
               dc[j] = valid ? gsum : 0.f;
             }
             uint32_t zh[8], zl[8];
@@ -834,12 +880,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         // ---- h_k (this row's slice) and a fresh dh accumulator ------------------------------------
         if (k > 0) {
           const int Hk = p.H[k];
-          const float* prow = p.saved + p.saved_off[k - 1] + m_pad * p.L[k - 1];
+          if (p.compact) {
+            // [m / 64][j][68] tiles written by the forward for wgrad: for a fixed j the 64 rows of a block are contiguous
+            const float* hbp = p.saved + p.hb_off[k - 1] + (m_pad >> 6) * (size_t)(Hk * kWgPad) + (m_pad & 63);
 #pragma unroll
-          for (int j = 0; j < kMaxHp; j += 4) {
-            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid && j < Hk) q4 = *reinterpret_cast<const float4*>(prow + j);   // H_k is a multiple of 4 (L/2, L % 16 == 0)
-            h[j] = q4.x; h[j + 1] = q4.y; h[j + 2] = q4.z; h[j + 3] = q4.w;
+            for (int j = 0; j < kMaxHp; ++j) h[j] = (valid && j < Hk) ? __ldg(hbp + (size_t)j * kWgPad) : 0.f;
+          } else {
+            const float* prow = p.saved + p.saved_off[k - 1] + m_pad * p.L[k - 1];
+#pragma unroll
+            for (int j = 0; j < kMaxHp; j += 4) {
+              float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid && j < Hk) q4 = *reinterpret_cast<const float4*>(prow + j);   // H_k is a multiple of 4 (L/2, L % 16 == 0)
+              h[j] = q4.x; h[j + 1] = q4.y; h[j + 2] = q4.z; h[j + 3] = q4.w;
+            }
           }
         } else {
 #pragma unroll
@@ -1263,12 +1316,16 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   size_t dc_off[kCinMaxLayers];
   dc_bytes(s, B, dc_off);
   size_t woff = 0, soff = (size_t)B * s.D * s.F;
+  p.compact = cin_tc_compact(s) ? 1 : 0;
+  size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float) + (m_pad_rows(s, B) / 64) * s.F * kWgPad;   // as cin_tc_fwd
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
     p.L[k] = s.L[k]; p.H[k] = s.H[k]; p.Hp[k] = round_up(s.H[k], kSubK);
     p.pool_lo[k] = s.pool_lo[k]; p.pool_n[k] = s.pool_n[k]; p.pcol0[k] = s.pcol0[k];
     p.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
     p.wpack_off[k] = woff; p.saved_off[k] = soff; p.dc_off[k] = dc_off[k];
+    p.hb_off[k] = hoff;
+    hoff += (m_pad_rows(s, B) / 64) * p.hid_n[k] * kWgPad;
     const size_t chunk = (size_t)s.L[k] * p.Hp[k] * 4;
     const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
     int blocks = (int)((total + 255) / 256);

@@ -562,22 +562,38 @@ def test_cin_tensor_core_backward(nat, f, d, sizes, direct, use_bias, act, b):
     saved = torch.empty(nat.lib.dtb_cin_saved_bytes(b, f, d, sizes_c, n, int(direct)), dtype=torch.uint8, device='cuda')
     d_idx, d_tab, d_offs, d_w = dev(idx), dev(flat), dev(offs), dev(wcat)
     d_b = dev(np.concatenate(bias)) if use_bias else None
-    nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(pooled), P(saved), P(ws), ws_bytes,
-                                  b, f, d, sizes_c, n, int(direct), act, 2, None, None))
     dp = g.normal(size=(b, pw)).astype(np.float32)
-    gt = torch.zeros(flat.shape, device='cuda')
-    dw = torch.zeros(wcat.shape, device='cuda')
-    dbias = torch.zeros(sum(sizes), device='cuda') if use_bias else None
     d_dp = dev(dp)
-    nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt), P(dw), P(dbias),
-                                  P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None))
-    torch.cuda.synchronize()
+
+    def fwd_bwd():
+        gt_ = torch.zeros(flat.shape, device='cuda')
+        dw_ = torch.zeros(wcat.shape, device='cuda')
+        db_ = torch.zeros(sum(sizes), device='cuda') if use_bias else None
+        nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(pooled), P(saved), P(ws),
+                                      ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None, None))
+        nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt_), P(dw_), P(db_),
+                                      P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None))
+        torch.cuda.synchronize()
+        return gt_, dw_, db_
+
+    # (0) default = compact saved activations (relu-mask bits + the operand tiles); bit 17 keeps the fp32 T_k
+    #     rows.  Same arithmetic on the same values: only the order of the fp32 atomics may differ.
+    gt_c, dw_c, db_c = fwd_bwd()
+    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 17))
+    try:
+        gt, dw, dbias = fwd_bwd()
+    finally:
+        nat.lib.dtb_cin_tc_set_variant(1)
+    for a_, b_, what in ((gt_c, gt, 'embedding grad'), (dw_c, dw, 'filter grad'), (db_c, dbias, 'bias grad')):
+        if a_ is not None:
+            e = float((a_ - b_).abs().max() / b_.abs().max())
+            assert e < 2e-6, f'compact vs full saved activations, {what}: {e:.2e}'
     # (1) same saved activations (=> identical relu masks) through the exact-fp32 backward: the two
     #     backward implementations must agree to bf16x3 precision
     gt2 = torch.zeros(flat.shape, device='cuda')
     dw2 = torch.zeros(wcat.shape, device='cuda')
     db2 = torch.zeros(sum(sizes), device='cuda') if use_bias else None
-    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 16))
+    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 16) | (1 << 17))
     try:
         nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt2), P(dw2), P(db2),
                                       P(ws), ws_bytes, b, f, d, sizes_c, n, int(direct), act, 2, None))

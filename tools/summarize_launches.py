@@ -1,5 +1,7 @@
 """Summarise an ncu launch list (--metrics gpu__time_duration.sum --csv) into per-kernel totals and shares.
-usage: python tools/summarize_launches.py launches.csv [first_kernel_substring]"""
+usage: python tools/summarize_launches.py launches.csv [step_marker]
+With a marker (e.g. 'adam_rows_kernel<0>', the first kernel of a train step) only the launches from its first
+occurrence up to (not including) its second one are summarised: exactly one step."""
 import csv
 import re
 import sys
@@ -14,6 +16,10 @@ def main():
     for r in csv.DictReader(lines):
         if r.get('Metric Name') == 'gpu__time_duration.sum':
             rows.append((r['Kernel Name'], float(r['Metric Value']) / 1e3))
+    if len(sys.argv) > 2:
+        hits = [i for i, (n, _) in enumerate(rows) if sys.argv[2] in n]
+        if len(hits) >= 2:
+            rows = rows[hits[0]:hits[1]]
     agg = OrderedDict()
     for name, us in rows:
         short = re.sub(r'\(.*', '', name)[:100]
