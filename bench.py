@@ -312,6 +312,21 @@ def main():
     secs_e2e = timed(e2e_step, args.steps)
     loss = float(model._loss_acc.item()) / args.batch
 
+    # score-only pass (SURVEY 8d "also report score-only"): forward + task activation, device-resident inputs,
+    # no collective.  Informational: a failure here must never cost the headline line.
+    score = None
+    try:
+        def score_step(s):
+            c, d, _ = devb[s % n_pool]
+            model.predict_step(c, d)
+        for s in range(2):
+            score_step(s)
+        secs_score = timed(score_step, args.steps)
+        score = {'value': args.batch * world * args.steps / secs_score, 'unit': 'rows/s',
+                 'ms_per_step': secs_score / args.steps * 1e3, 'what': 'DeepModel.predict_step, inputs resident in HBM'}
+    except Exception as exc:                                # pragma: no cover
+        score = {'error': f'{type(exc).__name__}: {exc}'[:200]}
+
     if rank == 0:
         peaks = measured_peaks()
         roof = time_cin_kernel(model, devb[0][0], peaks)
@@ -333,6 +348,7 @@ def main():
             'e2e': {'value': rows / secs_e2e, 'unit': 'rows/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                     'ms_per_step': secs_e2e / args.steps * 1e3},
             'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'final_loss': loss,
+            'score_only': score,
         }
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_baseline(args, conf)

@@ -111,3 +111,20 @@ def test_ignore_case_dict():
     assert d['val_auc'] == 3
     with pytest.raises(KeyError):
         d[1]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and
+    prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0', '--cpu-sample-rows', '128'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['unit'] == 'rows/s' and line['value'] > 0
+    for key in ('metric', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['kind'] in ('port', 'reference')
