@@ -128,3 +128,46 @@ def test_bench_reference_arm_prints_the_contract_line():
     for key in ('metric', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'config', 'cpu_baseline', 'e2e'):
         assert key in line, key
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['kind'] in ('port', 'reference')
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype in include/deeptables_b200.h against the ctypes table in _native.py: same arity and the
+    same scalar class per argument (an ABI drift here corrupts arguments silently on the GPU box)."""
+    import ctypes
+    import re
+    from deeptables_b200 import _native as nat
+    with open(nat.HEADER_PATH) as f:
+        text = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    text = re.sub(r'//[^\n]*', '', text)
+    protos = re.findall(r'([A-Za-z_][A-Za-z0-9_ \*]*?)\b(dtb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', text)
+    assert len(protos) >= 30
+
+    def classify_c(decl):
+        decl = decl.strip()
+        if '*' in decl:
+            return 'ptr'
+        base = re.sub(r'\b[A-Za-z_][A-Za-z0-9_]*$', '', decl).strip() or decl     # drop the parameter name
+        base = base.replace('const', '').strip()
+        return {'int': 'i32', 'int32_t': 'i32', 'int64_t': 'i64', 'long long': 'i64', 'size_t': 'u64',
+                'unsigned long long': 'u64', 'uint64_t': 'u64', 'float': 'f32', 'double': 'f64'}[base]
+
+    def classify_ct(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, 'contents') or getattr(t, '_type_', None) is ctypes.c_int and t is not ctypes.c_int:
+            return 'ptr'
+        return {ctypes.c_int: 'i32', ctypes.c_int64: 'i64', ctypes.c_longlong: 'i64', ctypes.c_size_t: 'u64',
+                ctypes.c_ulonglong: 'u64', ctypes.c_float: 'f32', ctypes.c_double: 'f64'}[t]
+
+    seen = set()
+    for ret, name, args in protos:
+        seen.add(name)
+        assert name in nat._SIGNATURES, f'{name} declared in the header but not bound'
+        res, argtypes = nat._SIGNATURES[name]
+        params = [a for a in (x.strip() for x in args.split(',')) if a and a != 'void']
+        assert len(params) == len(argtypes), f'{name}: header has {len(params)} parameters, ctypes table {len(argtypes)}'
+        for k, (c_decl, ct) in enumerate(zip(params, argtypes)):
+            assert classify_c(c_decl) == classify_ct(ct), f'{name} arg {k} ({c_decl!r}) bound as {ct}'
+        ret = ret.replace('extern', '').replace('"C"', '').strip()
+        want = 'ptr' if '*' in ret else classify_c(ret + ' x')
+        got = 'ptr' if res in (ctypes.c_char_p, ctypes.c_void_p) else classify_ct(res)
+        assert want == got, f'{name}: return type {ret!r} bound as {res}'
+    assert seen == set(nat._SIGNATURES), sorted(set(nat._SIGNATURES) ^ seen)
