@@ -171,3 +171,18 @@ def test_ctypes_signatures_match_the_header_prototypes():
         got = 'ptr' if res in (ctypes.c_char_p, ctypes.c_void_p) else classify_ct(res)
         assert want == got, f'{name}: return type {ret!r} bound as {res}'
     assert seen == set(nat._SIGNATURES), sorted(set(nat._SIGNATURES) ^ seen)
+
+
+def test_no_undefined_globals_in_gpu_only_code():
+    """Function bodies of the host modules, bench.py and the GPU tests only execute on a GPU box; catch typos in
+    global names here (the image has no pyflakes): tools/lint_names.py."""
+    import glob
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('lint_names', os.path.join(root, 'tools', 'lint_names.py'))
+    lint = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lint)
+    files = (glob.glob(os.path.join(root, 'deeptables_b200', '*.py')) + glob.glob(os.path.join(root, 'tests', '*.py')) +
+             glob.glob(os.path.join(root, 'tools', '*.py')) + [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')])
+    problems = [p for f in files for p in lint.check(f)]
+    assert not problems, '\n'.join(problems)
