@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument('--cpu-sample-rows', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cin-precision', type=int, default=0)
+    ap.add_argument('--id-dist', default='uniform', choices=['uniform', 'zipf'],
+                    help="categorical id distribution of the synthetic batches (the headline is 'uniform')")
     return ap.parse_args()
 
 
@@ -53,14 +55,23 @@ def make_config(cin_precision=0):
                     'use_bias': False, 'direct': False, 'reduce_D': False, 'precision': cin_precision})
 
 
-def synth_batches(n_batches, batch, vocab, seed):
-    """Synthetic Criteo-shape rows: ids uniform in [0, vocab), dense N(0,1),
+def synth_batches(n_batches, batch, vocab, seed, id_dist='uniform'):
+    """Synthetic Criteo-shape rows: ids uniform in [0, vocab) (or, labelled, the
+    Zipf(1.05) variant of SURVEY 8d: rank r drawn with p ~ r^-1.05, many duplicate rows per batch), dense N(0,1),
     label Bernoulli(0.25).  Returned as pinned HOST tensors."""
     import torch
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n_batches):
-        idx = torch.randint(0, vocab, (batch, F_FIELDS), generator=g, dtype=torch.int32)
+        if id_dist == 'zipf':
+            # inverse-CDF sampling of a truncated Zipf(1.05) over ranks 1..vocab (continuous approximation)
+            a = 1.05
+            u = torch.rand(batch, F_FIELDS, generator=g, dtype=torch.float64)
+            top = float(vocab + 1) ** (1.0 - a)
+            r = (1.0 + u * (top - 1.0)) ** (1.0 / (1.0 - a))
+            idx = (r.floor().clamp_(1, vocab) - 1).to(torch.int32)
+        else:
+            idx = torch.randint(0, vocab, (batch, F_FIELDS), generator=g, dtype=torch.int32)
         dense = torch.randn(batch, N_DENSE, generator=g)
         y = (torch.rand(batch, 1, generator=g) < 0.25).float()
         out.append(tuple(t.pin_memory() if torch.cuda.is_available() else t for t in (idx, dense, y)))
@@ -268,7 +279,7 @@ def main():
     model = DeepModel('binary', 2, conf, cats, conts, seed=1234)
     model._build_model()
     n_pool = 4
-    host = synth_batches(n_pool, args.batch, args.vocab, 1234 + rank)
+    host = synth_batches(n_pool, args.batch, args.vocab, 1234 + rank, args.id_dist)
     devb = [tuple(t.cuda(non_blocking=True) for t in hb) for hb in host]
     torch.cuda.synchronize()
 
@@ -337,7 +348,7 @@ def main():
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': secs / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (CIN GEMMs: bf16x3 split on '
             'tcgen05, fp32 accumulate)' if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
-            'data': 'synthetic',
+            'data': 'synthetic' if args.id_dist == 'uniform' else f'synthetic ({args.id_dist} ids: NOT the headline distribution)',
             'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, '
                                    '13 dense + 26 sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])',
                        'global_batch': args.batch * world, 'per_gpu_batch': args.batch, 'parallelism': f'dp{world}',
