@@ -506,6 +506,11 @@ class DeepModel:
                 validation_steps = 1
         if self.model is None:
             self._build_model()
+        if self._dist:
+            # every rank feeds its own shard; the ranks must agree on the number of collective steps
+            agreed = torch.tensor([steps_per_epoch], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(agreed, op=torch.distributed.ReduceOp.MIN)
+            steps_per_epoch = int(agreed.item())
         cat, cont = self._to_device_inputs(X)
         yd = self._to_device_labels(y)
         vcat, vcont = self._to_device_inputs(X_val)
@@ -562,6 +567,13 @@ class DeepModel:
                 self.table.check_status()
             if (epoch + 1) % validation_freq == 0 and n_val > 0:
                 vlogs = self._evaluate_tensors(vcat, vcont, vy, batch_size, validation_steps, metric_fns)
+                if self._dist and vlogs:
+                    # same validation logs on every rank (mean over the ranks' shards), so callbacks such as
+                    # EarlyStopping(restore_best_weights) take identical decisions and the replicas stay identical
+                    keys = sorted(vlogs)
+                    vt = torch.tensor([float(vlogs[k]) for k in keys], dtype=torch.float64, device=self.device)
+                    torch.distributed.all_reduce(vt)
+                    vlogs = dict(zip(keys, (vt / self.world_size).tolist()))
                 logs.update({f'val_{k}': v for k, v in vlogs.items()})
             history.epoch.append(epoch)
             for k, v in logs.items():
@@ -571,6 +583,11 @@ class DeepModel:
                 print(f'Epoch {epoch + 1}/{epochs} - {steps_per_epoch} steps - {msg}')
             for cb in callbacks:
                 _call(cb, 'on_epoch_end', epoch, logs)
+            if self._dist:
+                # early stopping looks at per-rank validation metrics: stop everywhere as soon as one rank stops
+                flag = torch.tensor([1 if self.stop_training else 0], dtype=torch.int32, device=self.device)
+                torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+                self.stop_training = bool(flag.item())
             if self.stop_training:
                 break
         for cb in callbacks:
