@@ -1,7 +1,7 @@
 """Independent brute-force definitions (numpy float64, explicit loops) of the interaction layers,
 written from the defining formulas of the papers the reference cites rather than from its TF op
 sequence.  They exist to pin oracle/layers_ref.py (which mirrors the op sequence) from a second
-direction, because the reference ships no golden vectors (PARITY UNPINNED, see layers_ref.py).
+direction, because the reference ships no golden vectors (see the parity note in layers_ref.py).
 
 TEST INFRASTRUCTURE ONLY.  Small cases only -- these are O(everything) Python loops.
 """

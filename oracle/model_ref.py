@@ -2,7 +2,10 @@
 net builders (deepnets.py:43-224, 401-427), loss (deepmodel.py:319-346) and Keras Adam, restated
 over a flat state dict keyed by the reference's layer / weight names.
 
-TEST INFRASTRUCTURE ONLY (see oracle/layers_ref.py header).  PARITY UNPINNED (TF/Keras absent).
+TEST INFRASTRUCTURE ONLY (see oracle/layers_ref.py header).  Parity: ``forward`` is pinned against the
+reference's own ``DeepModel.__build_model`` executed over tests/golden/tf_shim.py
+(tests/test_reference_golden.py); losses / Adam / BN moving statistics are restated from the Keras
+documentation and stay UNPINNED (TF/Keras absent).
 
 The state dict maps ``'<layer>/<weight>'`` -> torch CPU tensor, e.g.
 ``emb_categorical_vars_all/embeddings_3``, ``bn_concat_emb_dense/gamma``, ``linear_logit/kernel``,
