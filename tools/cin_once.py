@@ -1,0 +1,45 @@
+"""One training-mode CIN forward + backward at the BASELINE shape: the target of `ncu --set full` captures
+(5 kernels of interest: cin_tc_fwd, cin_tc_dgrad, 3 x cin_tc_wgrad).  FULL=1 selects the full saved-activation
+format (bit 17 of dtb_cin_tc_set_variant) for A/B against the default compact one."""
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deeptables_b200 import _native as nat  # noqa: E402
+
+P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())  # noqa: E731
+B = int(os.environ.get('B', 65536))
+F, D, sizes = 26, 16, (128, 128, 128)
+V = 1000000
+sizes_c = nat.int_array(sizes)
+g = torch.Generator(device='cuda').manual_seed(0)
+table = (torch.rand(F * V, D, device='cuda', generator=g) - 0.5) * 0.1
+grad = torch.zeros_like(table)
+offs = torch.arange(F + 1, dtype=torch.int64, device='cuda') * V
+idx = torch.randint(0, V, (B, F), device='cuda', dtype=torch.int32, generator=g)
+K = [26 * 26, 26 * 64, 26 * 64]
+w = torch.cat([(torch.randn(k * 128, device='cuda', generator=g) / k ** 0.5) for k in K])
+dw = torch.zeros_like(w)
+pooled = torch.empty(B, 256, device='cuda')
+d_pooled = torch.randn(B, 256, device='cuda', generator=g) * 1e-3
+ws_bytes = nat.lib.dtb_cin_workspace_bytes(B, F, D, sizes_c, 3, 0, 1)
+ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+saved = torch.empty(nat.lib.dtb_cin_saved_bytes(B, F, D, sizes_c, 3, 0), dtype=torch.uint8, device='cuda')
+if os.environ.get('FULL'):
+    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 17))
+reps = int(os.environ.get('REPS', 1))
+for rep in range(reps):
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
+                                  sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd')
+    e[1].record()
+    nat.check(nat.lib.dtb_cin_bwd(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None, P(ws),
+                                  ws_bytes, B, F, D, sizes_c, 3, 0, 1, 0, None), 'cin_bwd')
+    e[2].record()
+    torch.cuda.synchronize()
+    print(f'rep {rep}: fwd {e[0].elapsed_time(e[1]):.3f} ms  bwd {e[1].elapsed_time(e[2]):.3f} ms '
+          f'({"full" if os.environ.get("FULL") else "compact"} saved activations)', flush=True)

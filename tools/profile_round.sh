@@ -1,0 +1,22 @@
+#!/bin/bash
+# One gpurun call that refreshes everything profiles/ needs for a round (1 GPU, ~4-5 minutes of box time):
+#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/profile_round.sh r2'
+# then, HERE (ncu reads reports without a GPU):
+#   python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv 'adam_rows_kernel<0>' > profiles/${TAG}_launches_step.txt
+#   python tools/ncu_extract.py gpurun_out/${TAG}_cin.ncu-rep --json profiles/r1_cin_tc_traffic.json > profiles/${TAG}_cin_tc_ncu_summary.txt
+TAG=${1:-rN}
+mkdir -p gpurun_out
+# 1. the headline bench line (never under a profiler)
+timeout -s KILL 240 python bench.py > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
+cut -c1-300 gpurun_out/${TAG}_bench_n1.json
+# 2. launch list of one step: shares only
+timeout -s KILL 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 260 --csv \
+    --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_launch_bench.log 2>&1
+# 3. full-section capture of the five CIN kernels (one training forward + backward), source-correlated
+timeout -s KILL 240 ncu --set full --clock-control none --import-source on -k regex:cin_tc_ -c 5 -f \
+    -o gpurun_out/${TAG}_cin python tools/cin_once.py > gpurun_out/${TAG}_ncu_cin.log 2>&1
+# 4. A/B of the saved-activation formats and the HBM-bound kernels, un-profiled
+REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
+FULL=1 REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
+timeout -s KILL 90 python tools/bench_hbm.py > gpurun_out/${TAG}_hbm_kernels.txt 2>&1
+tail -12 gpurun_out/${TAG}_hbm_kernels.txt
