@@ -750,7 +750,13 @@ __host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int 
   return l;
 }
 
-template <int D>
+// kExp selects experiment builds of the SAME kernel (profiling only, D = 16, chosen by the high nibble of the
+// dbg byte of dtb_cin_tc_set_variant; tools/cin_once.py DGRAD_EXP=n).  0 = product code (every `if constexpr`
+// below compiles away: its SASS is unchanged by the presence of the experiments).
+//   1: no accumulator read-out and no FMAs (synchronisation + MMA skeleton)      2: read-out but no FMAs
+//   3: software-pipelined read-out (next tcgen05.ld issued before the FMAs of the current 16 columns)
+//   4: no MMA issue (producer + read-out + FMAs only)
+template <int D, int kExp = 0>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
   constexpr int R = 128 / D;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -907,19 +913,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           tc::mbar_wait(&acc_full[g * 2 + buf], par);
           tc::fence_after_thread_sync();
           float dx = 0.f;
+          if constexpr (kExp == 3) {
+            uint32_t v0[16], v1[16];
+            const uint32_t acc_addr = t_tile + 128 + buf * 64;
+            tc::tmem_ld16(acc_addr, v0);
+#pragma unroll
+            for (int cb = 0; cb < kMaxHp / 16; ++cb) {
+              if (cb * 16 < Hp) {
+                tc::tmem_wait_ld();
+                const bool more = cb + 1 < kMaxHp / 16 && (cb + 1) * 16 < Hp;
+                if (more) {
+                  if (cb & 1) tc::tmem_ld16(acc_addr + (cb + 1) * 16, v0);
+                  else tc::tmem_ld16(acc_addr + (cb + 1) * 16, v1);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float dz = __uint_as_float((cb & 1) ? v1[j] : v0[j]);
+                  dx = fmaf(dz, h[cb * 16 + j], dx);
+                  dh[cb * 16 + j] = fmaf(dz, xi, dh[cb * 16 + j]);
+                }
+              }
+            }
+          } else if constexpr (kExp == 1) {
+            dx = xi;
+          } else {
 #pragma unroll
           for (int cb = 0; cb < kMaxHp / 16; ++cb) {
             if (cb * 16 < Hp) {
               uint32_t v[16];
               tc::tmem_ld16(t_tile + 128 + buf * 64 + cb * 16, v);
               tc::tmem_wait_ld();
+              if constexpr (kExp == 2) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x ^= v[j];
+                dx += __uint_as_float(x & 1u);
+              } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float dz = __uint_as_float(v[j]);
                 dx = fmaf(dz, h[cb * 16 + j], dx);
                 dh[cb * 16 + j] = fmaf(dz, xi, dh[cb * 16 + j]);
               }
+              }
             }
+          }
           }
           tc::fence_before_thread_sync();
           __syncwarp();
@@ -976,7 +1014,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
                   for (int ks = 0; ks < kMaxL / 16; ++ks) {
                     if (ks * 16 < L) {
                       const uint64_t desc_b = desc_hi | (uint64_t)(((b_img + ks * 2 * lbo_b) >> 4) & 0x3FFF);
-                      tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, (uint32_t)((pass | ks) != 0));
+                      if constexpr (kExp != 4)
+                        tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, (uint32_t)((pass | ks) != 0));
                     }
                   }
                 }
@@ -1266,9 +1305,9 @@ static size_t dc_bytes(const CinShape& s, int B, size_t* off /* per layer */) {
 
 size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B) { return wpack_bytes(s) + 1024 + dc_bytes(s, B, nullptr) + 1024; }
 
-template <int D>
-static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
-  auto kern = cin_tc_dgrad_kernel<D>;
+template <int D, int kExp>
+static int launch_dgrad_exp(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
+  auto kern = cin_tc_dgrad_kernel<D, kExp>;
   DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int R = 128 / D;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
@@ -1277,6 +1316,20 @@ static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st
   kern<<<grid, kTcThreads, smem_bytes, st>>>(p);
   DTB_LAUNCH_OK();
   return DTB_OK;
+}
+
+template <int D>
+static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
+  if constexpr (D == 16) {
+    switch (g_tc_dbg >> 4) {       // experiment builds (profiling only): see cin_tc_dgrad_kernel
+      case 1: return launch_dgrad_exp<16, 1>(p, smem_bytes, st);
+      case 2: return launch_dgrad_exp<16, 2>(p, smem_bytes, st);
+      case 3: return launch_dgrad_exp<16, 3>(p, smem_bytes, st);
+      case 4: return launch_dgrad_exp<16, 4>(p, smem_bytes, st);
+      default: break;
+    }
+  }
+  return launch_dgrad_exp<D, 0>(p, smem_bytes, st);
 }
 
 static bool cin_tc_bwd_supported(const CinShape& s) {

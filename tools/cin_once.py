@@ -1,6 +1,8 @@
 """One training-mode CIN forward + backward at the BASELINE shape: the target of `ncu --set full` captures
 (5 kernels of interest: cin_tc_fwd, cin_tc_dgrad, 3 x cin_tc_wgrad).  FULL=1 selects the full saved-activation
-format (bit 17 of dtb_cin_tc_set_variant) for A/B against the default compact one."""
+format (bit 17 of dtb_cin_tc_set_variant) for A/B against the default compact one; DGRAD_EXP=n (1..4) selects an
+experiment build of the data-gradient kernel (see cin_tc_dgrad_kernel: 1 skeleton, 2 read-out only, 3 pipelined
+read-out, 4 no MMA) -- its gradients are then meaningless, only the time is of interest."""
 import ctypes
 import os
 import sys
@@ -28,18 +30,21 @@ d_pooled = torch.randn(B, 256, device='cuda', generator=g) * 1e-3
 ws_bytes = nat.lib.dtb_cin_workspace_bytes(B, F, D, sizes_c, 3, 0, 1)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
 saved = torch.empty(nat.lib.dtb_cin_saved_bytes(B, F, D, sizes_c, 3, 0), dtype=torch.uint8, device='cuda')
-if os.environ.get('FULL'):
-    nat.lib.dtb_cin_tc_set_variant(1 | (1 << 17))
+exp = int(os.environ.get('DGRAD_EXP', 0))
+nat.lib.dtb_cin_tc_set_variant(1 | ((1 << 17) if os.environ.get('FULL') else 0) | (exp << 12))
 reps = int(os.environ.get('REPS', 1))
 for rep in range(reps):
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
     nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
                                   sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd')
     e[1].record()
-    nat.check(nat.lib.dtb_cin_bwd(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None, P(ws),
-                                  ws_bytes, B, F, D, sizes_c, 3, 0, 1, 0, None), 'cin_bwd')
-    e[2].record()
+    for phase in (1, 2):                       # 1: weight pack + dgrad, 2: 3 x wgrad
+        nat.check(nat.lib.dtb_cin_bwd_phase(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None,
+                                            P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, 0, phase, None), 'cin_bwd_phase')
+        e[1 + phase].record()
     torch.cuda.synchronize()
-    print(f'rep {rep}: fwd {e[0].elapsed_time(e[1]):.3f} ms  bwd {e[1].elapsed_time(e[2]):.3f} ms '
-          f'({"full" if os.environ.get("FULL") else "compact"} saved activations)', flush=True)
+    print(f'rep {rep}: fwd {e[0].elapsed_time(e[1]):.3f} ms  dgrad {e[1].elapsed_time(e[2]):.3f} ms  wgrad '
+          f'{e[2].elapsed_time(e[3]):.3f} ms  ({"full" if os.environ.get("FULL") else "compact"} saved activations, '
+          f'dgrad experiment {exp})', flush=True)
+nat.lib.dtb_cin_tc_set_variant(1)
