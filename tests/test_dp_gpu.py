@@ -42,28 +42,30 @@ def _batch(seed):
     return idx, cont, y
 
 
-def _worker(rank, world, port, out_dir, same_shard):
+def _worker(rank, world, port, out_dir, same_shard, table_mode=None):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         m = _build()
+        m._table_mode_override = table_mode          # None: adaptive (dense sweep at this size); 'lazy': row-wise Adam on the union
         assert m.world_size == world
         for step in range(6):
             idx, cont, y = _batch(step if same_shard else step * world + rank)
             m.train_on_batch(idx, cont, y)
-        sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}      # state_dict() flushes the lazy state
         np.savez(os.path.join(out_dir, f'rank{rank}_{int(same_shard)}.npz'), **sd)
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('table_mode', [None, 'lazy'])
 @pytest.mark.parametrize('same_shard', [True, False])
-def test_two_rank_training(tmp_path, same_shard):
+def test_two_rank_training(tmp_path, same_shard, table_mode):
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), same_shard), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), same_shard, table_mode), nprocs=2, join=True)
     r0 = np.load(tmp_path / f'rank0_{int(same_shard)}.npz')
     r1 = np.load(tmp_path / f'rank1_{int(same_shard)}.npz')
     for k in r0.files:
