@@ -737,14 +737,21 @@ __global__ void cin_tc_pack_t_kernel(const float* __restrict__ w, uint8_t* __res
 }
 
 struct TcBwdSmemLayout {
-  int b_off, x0_off, dx_off, bar_off, total;
+  int b_off, x0_off, dx_off, a_off, bar_off, total;
 };
-__host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int F) {
+// stages / a_hi_bytes differ from the defaults only in experiment 5 of the dgrad kernel (dC_hi operand in shared memory)
+__host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int F, int stages = kStagesB,
+                                                         int a_hi_bytes = 0) {
   TcBwdSmemLayout l;
   l.b_off = 0;
-  l.x0_off = kStagesB * b_stage_bytes;
+  l.x0_off = stages * b_stage_bytes;
   l.dx_off = l.x0_off + 2 * 128 * F * 4;
   l.bar_off = l.dx_off + 2 * 128 * F * 4;
+  l.a_off = l.bar_off;
+  if (a_hi_bytes > 0) {
+    l.a_off = (l.bar_off + 127) / 128 * 128;
+    l.bar_off = l.a_off + a_hi_bytes;
+  }
   l.bar_off = (l.bar_off + 15) / 16 * 16;
   l.total = l.bar_off + 256;
   return l;
@@ -756,14 +763,21 @@ __host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int 
 //   1: no accumulator read-out and no FMAs (synchronisation + MMA skeleton)      2: read-out but no FMAs
 //   3: software-pipelined read-out (next tcgen05.ld issued before the FMAs of the current 16 columns)
 //   4: no MMA issue (producer + read-out + FMAs only)
+//   5: a REAL variant (correct gradients): the dC_hi operand lives in shared memory (UMMA K-major no-swizzle tile,
+//      LBO 2048 / SBO 128 as in tc_selftest_kernel<false>) and passes 0 and 2 use the SS form; only dC_lo stays in
+//      TMEM (pass 1, TS form).  Tests whether A-from-TMEM operand reads limit the N = 64 MMAs / collide with the
+//      accumulator read-out.  Costs 64 KB of shared memory, so it runs with 3 weight stages instead of 4.
 template <int D, int kExp = 0>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
   constexpr int R = 128 / D;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const TcBwdSmemLayout lay = tc_bwd_layout(p.b_stage_bytes, p.F);
+  constexpr int kSB = (kExp == 5) ? 3 : kStagesB;                    // weight stages
+  constexpr int kAHiTile = 128 * kMaxL * 2;                           // bytes of one tile's dC_hi operand (experiment 5)
+  const TcBwdSmemLayout lay = tc_bwd_layout(p.b_stage_bytes, p.F, kSB, kExp == 5 ? 2 * kAHiTile : 0);
   uint8_t* smem_b = smem + lay.b_off;
   float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
   float* dxs = reinterpret_cast<float*>(smem + lay.dx_off);
+  [[maybe_unused]] uint8_t* smem_a = smem + lay.a_off;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_ready = bars;          // [tile]            2
   uint64_t* full_b = bars + 2;       // [stage]           4
@@ -779,7 +793,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
   if (threadIdx.x == 0) {
     tc::mbar_init(&a_ready[0], 4);
     tc::mbar_init(&a_ready[1], 4);
-    for (int s = 0; s < kStagesB; ++s) {
+    for (int s = 0; s < kSB; ++s) {
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty_b[s], 1);
     }
@@ -871,7 +885,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
             uint32_t zh[8], zl[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) tc::split_bf16x2(dc[2 * q], dc[2 * q + 1], zh[q], zl[q]);
-            tc::tmem_st8v(t_tile + cb * 8, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
+            if constexpr (kExp == 5) {
+              uint8_t* arow = smem_a + g * kAHiTile + (t >> 3) * 128 + (t & 7) * 16;     // k-group stride 2048 B
+              *reinterpret_cast<uint4*>(arow + (2 * cb) * 2048) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
+              *reinterpret_cast<uint4*>(arow + (2 * cb + 1) * 2048) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
+            } else {
+              tc::tmem_st8v(t_tile + cb * 8, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
+            }
             tc::tmem_st8v(t_tile + 64 + cb * 8, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
             *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
             *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
@@ -881,6 +901,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           }
         }
         tc::fence_before_thread_sync();
+        if constexpr (kExp == 5) tc::fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMA reads
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&a_ready[g]);
         // ---- h_k (this row's slice) and a fresh dh accumulator ------------------------------------
@@ -991,7 +1012,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         const uint32_t img_b = (uint32_t)L * Hp * 2;
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         for (int i = 0; i < F; ++i, ++chunk) {
-          const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+          const uint32_t sb = chunk % kSB, pb = (chunk / kSB) & 1;
           tc::mbar_wait(&full_b[sb], pb);
           const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
 #pragma unroll
@@ -1014,8 +1035,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
                   for (int ks = 0; ks < kMaxL / 16; ++ks) {
                     if (ks * 16 < L) {
                       const uint64_t desc_b = desc_hi | (uint64_t)(((b_img + ks * 2 * lbo_b) >> 4) & 0x3FFF);
-                      if constexpr (kExp != 4)
+                      if constexpr (kExp == 5) {
+                        if (pass == 1)
+                          tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, (uint32_t)((pass | ks) != 0));
+                        else
+                          tc::mma_ss(d_tmem, tc::make_smem_desc(tc::smem_u32(smem_a) + g * kAHiTile + ks * 4096, 2048, 128),
+                                     desc_b, idesc, (uint32_t)((pass | ks) != 0));
+                      } else if constexpr (kExp != 4) {
                         tc::mma_ts(d_tmem, a_addr + ks * 8, desc_b, idesc, (uint32_t)((pass | ks) != 0));
+                      }
                     }
                   }
                 }
@@ -1038,7 +1066,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           const uint32_t stride = (uint32_t)p.L[k] * p.Hp[k] * 4;
           const uint8_t* src = p.wpack + p.wpack_off[k];
           for (int i = 0; i < F; ++i, ++chunk) {
-            const uint32_t sb = chunk % kStagesB, pb = (chunk / kStagesB) & 1;
+            const uint32_t sb = chunk % kSB, pb = (chunk / kSB) & 1;
             tc::mbar_wait(&empty_b[sb], pb ^ 1);
             tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
             tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[sb]);
@@ -1326,6 +1354,11 @@ static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st
       case 2: return launch_dgrad_exp<16, 2>(p, smem_bytes, st);
       case 3: return launch_dgrad_exp<16, 3>(p, smem_bytes, st);
       case 4: return launch_dgrad_exp<16, 4>(p, smem_bytes, st);
+      case 5: {
+        const int need = tc_bwd_layout(p.b_stage_bytes, p.F, 3, 2 * 128 * kMaxL * 2).total;
+        if (need <= 227 * 1024) return launch_dgrad_exp<16, 5>(p, need, st);
+        break;
+      }
       default: break;
     }
   }

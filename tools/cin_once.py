@@ -2,7 +2,8 @@
 (5 kernels of interest: cin_tc_fwd, cin_tc_dgrad, 3 x cin_tc_wgrad).  FULL=1 selects the full saved-activation
 format (bit 17 of dtb_cin_tc_set_variant) for A/B against the default compact one; DGRAD_EXP=n (1..4) selects an
 experiment build of the data-gradient kernel (see cin_tc_dgrad_kernel: 1 skeleton, 2 read-out only, 3 pipelined
-read-out, 4 no MMA) -- its gradients are then meaningless, only the time is of interest."""
+read-out, 4 no MMA -- their gradients are meaningless, only the time is of interest; 5 keeps dC_hi in shared memory
+and is a real variant: CHECK=1 compares its gradients with the product kernel's)."""
 import ctypes
 import os
 import sys
@@ -48,3 +49,19 @@ for rep in range(reps):
           f'{e[2].elapsed_time(e[3]):.3f} ms  ({"full" if os.environ.get("FULL") else "compact"} saved activations, '
           f'dgrad experiment {exp})', flush=True)
 nat.lib.dtb_cin_tc_set_variant(1)
+if os.environ.get('CHECK') and exp:
+    # gradients of the experiment build against the product kernel on the same saved activations
+    res = []
+    for e_ in (0, exp):
+        nat.lib.dtb_cin_tc_set_variant(1 | ((1 << 17) if os.environ.get('FULL') else 0) | (e_ << 12))
+        grad.zero_()
+        dw.zero_()
+        for phase in (1, 2):
+            nat.check(nat.lib.dtb_cin_bwd_phase(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None,
+                                                P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, 0, phase, None), 'cin_bwd_phase')
+        torch.cuda.synchronize()
+        res.append((grad.clone(), dw.clone()))
+    nat.lib.dtb_cin_tc_set_variant(1)
+    eg = float((res[0][0] - res[1][0]).abs().max() / res[0][0].abs().max())
+    ew = float((res[0][1] - res[1][1]).abs().max() / res[0][1].abs().max())
+    print(f'experiment {exp} vs product: embedding grad rel err {eg:.2e}, filter grad rel err {ew:.2e}', flush=True)

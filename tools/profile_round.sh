@@ -19,5 +19,6 @@ timeout -s KILL 240 ncu --set full --clock-control none --import-source on -k re
 REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
 FULL=1 REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
 for e in 1 2 3 4; do DGRAD_EXP=$e REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -1; done   # dgrad ablations
+DGRAD_EXP=5 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | tail -2                         # dC_hi from shared memory
 timeout -s KILL 90 python tools/bench_hbm.py > gpurun_out/${TAG}_hbm_kernels.txt 2>&1
 tail -12 gpurun_out/${TAG}_hbm_kernels.txt
