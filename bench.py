@@ -271,10 +271,11 @@ def time_cin_kernel(model, cat, peaks):
             traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
     return {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
             'frac': tf / peaks['bf16_tflops'], 'traffic': traffic,
-            'kernel': 'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)' if tc
+            'kernel': ('cin_tc_fwd_kernel (tcgen05, single pass on power-of-two-scaled fp16 operands)' if precision == 4 else
+                       'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)') if tc
             else 'cin_fwd (fp32 cuBLAS formulation)',
             'ms': dt * 1e3, 'algorithmic_flop_per_launch': b * CIN_FLOP_PER_ROW,
-            'executed_tensor_tflops': tf * (3 if tc and precision != 3 else 1),
+            'executed_tensor_tflops': tf * (3 if tc and precision not in (3, 4) else 1),
             'hbm_gbs_informational': b * CIN_BYTES_PER_ROW / dt / 1e9, 'peak_source': peaks['source'],
             'cin_backward': {'ms': dt_b * 1e3, 'algorithmic_tflops': 2 * b * CIN_FLOP_PER_ROW / dt_b / 1e12,
                              'kernels': 'cin_tc_dgrad_kernel + 3 x cin_tc_wgrad_kernel'}}
@@ -370,8 +371,10 @@ def main():
         line = {
             'metric': 'xDeepFM train rows/sec, Criteo-shape synthetic', 'value': rows / secs, 'unit': 'rows/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': secs / args.steps * 1e3,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (CIN GEMMs: bf16x3 split on '
-            'tcgen05, fp32 accumulate)' if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': ('f32 (CIN forward GEMMs: one tcgen05 pass on scaled fp16 operands, backward bf16x3; fp32 accumulate)'
+                      if args.cin_precision == 4 else 'f32 (CIN GEMMs: bf16x3 split on tcgen05, fp32 accumulate)')
+            if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
             'data': 'synthetic' if args.id_dist == 'uniform' else f'synthetic ({args.id_dist} ids: NOT the headline distribution)',
             'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, '
                                    '13 dense + 26 sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])',

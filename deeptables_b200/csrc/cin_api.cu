@@ -42,7 +42,7 @@ int dtb_cin_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
                 int* status, void* stream) {
   DTB_CHECK_ARG(idx && table && row_offsets && weights && pooled && workspace, "NULL argument");
   DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU, "unsupported activation");
-  DTB_CHECK_ARG(precision >= 0 && precision <= 3, "bad precision code");
+  DTB_CHECK_ARG(precision >= 0 && precision <= DTB_CIN_TC_F16X1, "bad precision code");
   CinShape s;
   if (!s.init(F, D, layer_sizes_host, n_layers, direct)) {
     set_error("dtb_cin_fwd: invalid CIN configuration (cross_layer_size must be even except for the last "
@@ -51,10 +51,12 @@ int dtb_cin_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
   }
   if (B <= 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc(s, precision))
+  if (use_tc(s, precision)) {
+    const int single = precision == DTB_CIN_TC_BF16X1 || precision == DTB_CIN_TC_F16X1;
     return cin_tc_fwd(s, idx, table, row_offsets, weights, bias, pooled, saved, workspace, workspace_bytes, B,
-                      act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3, status, st);
-  if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1) {
+                      act, single ? 1 : 3, precision == DTB_CIN_TC_F16X1 ? 1 : 0, status, st);
+  }
+  if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1 || precision == DTB_CIN_TC_F16X1) {
     set_error("dtb_cin_fwd: tensor-core path requested but shape unsupported (F=%d D=%d)", F, D);
     return DTB_ERR_UNSUPPORTED;
   }
@@ -70,7 +72,7 @@ static int cin_bwd_impl(const int32_t* idx, const float* table, const int64_t* r
                     workspace,
                 "NULL argument");
   DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU, "unsupported activation");
-  DTB_CHECK_ARG(precision >= 0 && precision <= 3, "bad precision code");
+  DTB_CHECK_ARG(precision >= 0 && precision <= DTB_CIN_TC_F16X1, "bad precision code");
   CinShape s;
   if (!s.init(F, D, layer_sizes_host, n_layers, direct)) {
     set_error("dtb_cin_bwd: invalid CIN configuration");
@@ -81,7 +83,7 @@ static int cin_bwd_impl(const int32_t* idx, const float* table, const int64_t* r
   if (use_tc(s, precision))
     return cin_tc_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
                       workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3, phase, st);
-  if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1) {
+  if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1 || precision == DTB_CIN_TC_F16X1) {
     set_error("dtb_cin_bwd: tensor-core path requested but shape unsupported (F=%d D=%d)", F, D);
     return DTB_ERR_UNSUPPORTED;
   }

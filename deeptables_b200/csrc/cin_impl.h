@@ -18,10 +18,10 @@ int cin_fp32_bwd(const CinShape& s, const int32_t* idx, const float* table, cons
 bool cin_tc_supported(const CinShape& s);
 size_t cin_tc_saved_bytes(const CinShape& s, int B);
 size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training);
-// n_pass: 3 = bf16x3 split (fp32-grade), 1 = single bf16 pass
+// n_pass: 3 = bf16x3 split (fp32-grade), 1 = single pass; f16: single pass on scaled fp16 operands (n_pass must be 1)
 int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* bias, float* pooled, void* saved, void* workspace,
-               size_t workspace_bytes, int B, int act, int n_pass, int* status, cudaStream_t st);
+               size_t workspace_bytes, int B, int act, int n_pass, int f16, int* status, cudaStream_t st);
 int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* d_pooled, const void* saved, float* grad_table,
                float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,

@@ -24,6 +24,7 @@
 #include "cin_impl.h"
 #include "tcgen05.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace dtb {
 
@@ -53,6 +54,7 @@ struct CinTcParams {
   int b_stage_bytes;                              // bytes reserved per weight stage in smem
   int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
   int compact;                                    // training: save relu-mask bits instead of the fp32 T_k rows (see cin_tc_compact)
+  const int* wmax;                                // fp16 variant only: bit pattern of max|W_k| per layer (cin_tc_wmax_kernel)
 };
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -94,6 +96,37 @@ constexpr int kStagesB = 4;
 constexpr int kACols = kSubK / 2;                 // TMEM columns of one bf16 [128 x 32] operand block
 constexpr int kWgPad = 68;                        // row stride (floats) of the block-transposed tiles the wgrad kernel reads
 
+// ---- fp16 variant: max|W_k| (bit pattern, atomicMax on the int view of non-negative floats) and the scaled pack
+__global__ void cin_tc_wmax_kernel(const float* __restrict__ w, int64_t n, int* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float a = fabsf(w[i]);
+    if (a < __int_as_float(0x7f800000)) m = fmaxf(m, a);      // ignore inf / nan
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_int(m));
+}
+
+// same image layout as cin_tc_pack_kernel, but ONE fp16 image per chunk (the "hi" slot), values scaled by the
+// power of two that brings max|W_k| into [2^9, 2^10)
+__global__ void cin_tc_pack_f16_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
+                                       int L, const int* __restrict__ wmax) {
+  float s, inv;
+  tc::pow2_scale_to_1024(__int_as_float(*wmax), s, inv);
+  const int64_t per_chunk = (int64_t)L * Hp;
+  const int64_t total = per_chunk * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / per_chunk);
+    const int rem = (int)(t - (int64_t)i * per_chunk);
+    const int kk = rem / L, n = rem - kk * L;       // n fastest: coalesced reads
+    const float v = kk < H ? w[((int64_t)i * H + kk) * L + n] * s : 0.f;
+    const int64_t off = ((int64_t)(kk >> 3) * (L >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (kk & 7) * 2;
+    *reinterpret_cast<__half*>(out + (int64_t)i * per_chunk * 4 + off) = __float2half_rn(v);
+  }
+}
+
 struct TcSmemLayout {
   int b_off, x0_off, bar_off, total;
 };
@@ -120,7 +153,12 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
-template <int D>
+// kF16 = true is the single-pass fp16 variant (DTB_CIN_TC_F16X1, not the default): operands in fp16 (11-bit
+// significand; one tensor pass instead of the three of the bf16 split) with exact power-of-two scaling into the fp16
+// range -- per GEMM row for the on-the-fly operand Z (bound max|x0 row| * max|h row|), per layer for the weights --
+// undone on the fp32 accumulator.  tools/cin_precision_study.py: max error 2-6e-4 of the output scale, inside the 1e-3
+// parity bar (bf16 single pass: 1.4-4e-3, outside).  With kF16 = false every `if constexpr` below compiles away.
+template <int D, bool kF16 = false>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_constant__ CinTcParams p) {
   constexpr int R = 128 / D;                 // batch rows per M=128 tile
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -187,6 +225,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
       // ---- h_0 = x0 (zero padded to Hp[0]) ; training: save x0t ------------------------------
 #pragma unroll
       for (int j = 0; j < kMaxHp; ++j) h[j] = (j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
+      [[maybe_unused]] float xmax = 0.f;           // kF16: max|x0[m, :]| of this GEMM row
+      if constexpr (kF16) {
+#pragma unroll
+        for (int j = 0; j < kMaxHp; ++j) xmax = fmaxf(xmax, fabsf(h[j]));
+      }
       if (p.saved) {
         if (b < p.B && !p.compact) {
           float* dst = p.saved + ((size_t)b * D + d) * F;
@@ -200,8 +243,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
       }
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
+        [[maybe_unused]] float srow = 1.f, inv_acc = 1.f;      // kF16: operand scale of this row, and 1/(srow * s_W)
+        if constexpr (kF16) {
+          float hmax = 0.f;
+#pragma unroll
+          for (int j = 0; j < kMaxHp; ++j) hmax = fmaxf(hmax, fabsf(h[j]));
+          float inv_row, sw, inv_w;
+          tc::pow2_scale_to_1024(xmax * hmax, srow, inv_row);
+          tc::pow2_scale_to_1024(__int_as_float(__ldg(p.wmax + k)), sw, inv_w);
+          inv_acc = inv_row * inv_w;
+        }
         for (int i = 0; i < F; ++i) {
-          const float xi = x0g[((size_t)r * F + i) * D + d];
+          const float xi = kF16 ? x0g[((size_t)r * F + i) * D + d] * srow : x0g[((size_t)r * F + i) * D + d];
 #pragma unroll
           for (int half = 0; half < kMaxHp / kSubK; ++half) {
             if (half * kSubK < Hp) {
@@ -212,8 +265,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
               uint32_t zh[kACols], zl[kACols];
               if (!(p.dbg & 1)) {
 #pragma unroll
-                for (int q = 0; q < kACols; ++q)
-                  tc::split_bf16x2(xi * h[half * kSubK + 2 * q], xi * h[half * kSubK + 2 * q + 1], zh[q], zl[q]);
+                for (int q = 0; q < kACols; ++q) {
+                  if constexpr (kF16) {
+                    zh[q] = tc::pack_f16x2(xi * h[half * kSubK + 2 * q], xi * h[half * kSubK + 2 * q + 1]);
+                    zl[q] = 0u;
+                  } else {
+                    tc::split_bf16x2(xi * h[half * kSubK + 2 * q], xi * h[half * kSubK + 2 * q + 1], zh[q], zl[q]);
+                  }
+                }
               }
               tc::mbar_wait(&empty_a[sa], pa ^ 1);
               tc::fence_after_thread_sync();
@@ -264,6 +323,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               float val = __uint_as_float(v[j]);
+              if constexpr (kF16) val *= inv_acc;
               if (bias) val += __ldg(bias + cb * 16 + j);
               if (p.act == DTB_ACT_RELU) val = fmaxf(val, 0.f);
               o[j] = val;
@@ -353,7 +413,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_fwd_kernel(const __grid_
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
-        const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)L);
+        const uint32_t idesc = kF16 ? tc::make_idesc_f16(128, (uint32_t)L) : tc::make_idesc_bf16(128, (uint32_t)L);
         const uint32_t lbo_b = (uint32_t)(L >> 3) * 128;       // K-direction core stride of the W image
         const uint32_t img_b = (uint32_t)L * Hp * 2;           // bytes of one (hi or lo) image
         // static part of the W descriptor: LBO, SBO = 128 B, version 1, no swizzle
@@ -573,9 +633,9 @@ size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training) {
   return need;
 }
 
-template <int D>
+template <int D, bool kF16 = false>
 static int launch_fwd(const CinTcParams& p, int smem_bytes, cudaStream_t st) {
-  auto kern = cin_tc_fwd_kernel<D>;
+  auto kern = cin_tc_fwd_kernel<D, kF16>;
   DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   const int R = 128 / D;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
@@ -588,7 +648,11 @@ static int launch_fwd(const CinTcParams& p, int smem_bytes, cudaStream_t st) {
 
 int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* bias, float* pooled, void* saved, void* workspace,
-               size_t workspace_bytes, int B, int act, int n_pass, int* status, cudaStream_t st) {
+               size_t workspace_bytes, int B, int act, int n_pass, int f16, int* status, cudaStream_t st) {
+  if (f16 && (s.D != 16 || workspace_bytes < wpack_bytes(s) + 64)) {
+    set_error("dtb_cin_fwd: the fp16 single-pass variant is built for embedding dim 16 only (got %d)", s.D);
+    return DTB_ERR_UNSUPPORTED;
+  }
   if (workspace_bytes < wpack_bytes(s)) {
     set_error("dtb_cin_fwd: workspace too small for the packed weights");
     return DTB_ERR_INVALID_ARG;
@@ -621,8 +685,19 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
     const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    cin_tc_pack_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], reinterpret_cast<uint8_t*>(workspace) + woff,
-                                               s.F, s.H[k], p.Hp[k], s.L[k]);
+    if (f16) {
+      // per-layer max|W_k| -> power-of-two scale, then one fp16 image per chunk (the max words live behind the images)
+      int* wmax = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + wpack_bytes(s)) + k;
+      DTB_CUDA_OK(cudaMemsetAsync(wmax, 0, sizeof(int), st));
+      const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
+      cin_tc_wmax_kernel<<<(int)((n_w + 255) / 256 < 64 ? (n_w + 255) / 256 : 64), 256, 0, st>>>(weights + s.w_off[k], n_w, wmax);
+      DTB_LAUNCH_OK();
+      cin_tc_pack_f16_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], reinterpret_cast<uint8_t*>(workspace) + woff,
+                                                     s.F, s.H[k], p.Hp[k], s.L[k], wmax);
+    } else {
+      cin_tc_pack_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], reinterpret_cast<uint8_t*>(workspace) + woff,
+                                                 s.F, s.H[k], p.Hp[k], s.L[k]);
+    }
     DTB_LAUNCH_OK();
     woff += chunk * s.F;
     soff += (size_t)B * s.D * s.L[k];
@@ -631,7 +706,9 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   p.b_stage_bytes = bstage;
   p.dbg = g_tc_dbg;
   p.compact = cin_tc_compact(s) ? 1 : 0;
+  p.wmax = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(workspace) + wpack_bytes(s));
   const TcSmemLayout lay = tc_layout(bstage, s.F);
+  if (f16) return launch_fwd<16, true>(p, lay.total, st);
 #define DTB_TC_LAUNCH(DD) \
   case DD:                \
     return launch_fwd<DD>(p, lay.total, st);

@@ -117,6 +117,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);  // m_dim
 }
 
+// D=f32, A=B=fp16 (format code 0), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // same, B operand MN-major (element (n,k): 8 n contiguous per 16-byte row, 8 k-rows per core matrix;
 // LBO = byte distance between k-groups of 8, SBO = between n-groups of 8)
 __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t N) {
@@ -159,6 +164,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+// pack two fp32 into f16x2 (round to nearest even): low half <- a, high half <- b
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// power-of-two scale 2^(9 - floor(log2 v)) that brings v into [2^9, 2^10) (fp16 overflows at 65504), and its exact
+// inverse; 1 for v == 0 / non-finite.  Exponent arithmetic only, so scaling and unscaling are exact.
+__device__ __forceinline__ void pow2_scale_to_1024(float v, float& s, float& inv) {
+  s = 1.f;
+  inv = 1.f;
+  const int e = ((__float_as_int(v) >> 23) & 0xff) - 127;
+  if (v > 0.f && e < 128) {
+    int sh = 9 - e;
+    sh = sh > 60 ? 60 : (sh < -60 ? -60 : sh);       // two such factors multiply in the epilogue: stay inside fp32
+    s = __int_as_float((127 + sh) << 23);
+    inv = __int_as_float((127 - sh) << 23);
+  }
 }
 // z = hi + lo with hi = bf16(z): returns packed hi pair and packed lo pair for (z0, z1)
 __device__ __forceinline__ void split_bf16x2(float z0, float z1, uint32_t& hi, uint32_t& lo) {

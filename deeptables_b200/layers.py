@@ -236,7 +236,7 @@ class CIN(Layer):
         self.use_bias = params.get('use_bias', False)
         self.direct = params.get('direct', False)
         self.reduce_D = params.get('reduce_D', False)
-        self.precision = params.get('precision', 0)        # engine knob: 0 auto, 1 fp32, 2 bf16x3, 3 bf16x1
+        self.precision = params.get('precision', 0)        # engine knob: 0 auto, 1 fp32, 2 bf16x3, 3 bf16x1, 4 fp16x1 forward (scaled) + bf16x3 backward
         if len(self.cross_layer_size) == 0:
             raise ValueError('cross_layer_size must be a list(tuple) of length greater than 1')
         if self.activation not in E.ACT_CODES:

@@ -192,6 +192,9 @@ int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row
 #define DTB_CIN_FP32 1
 #define DTB_CIN_TC_BF16X3 2
 #define DTB_CIN_TC_BF16X1 3
+/* 4: forward on ONE tensor pass with fp16 operands scaled by exact powers of two (per GEMM row / per layer); the
+ * backward of a model that ran this forward uses the bf16x3 kernels.  Not the default; embedding dim 16 only. */
+#define DTB_CIN_TC_F16X1 4
 int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct);
 /* Test hooks for the tensor-core path.  set_variant: 1 (default) feeds the on-the-fly A operand to
  * tcgen05.mma through TMEM, 0 through shared memory.  selftest: C[128,N] = bf16(A[128,K]) @

@@ -83,3 +83,74 @@ def test_baseline_config_full_shape(case):
     losses = [model.train_on_batch(idx.numpy(), cont.numpy(), y) for _ in range(4)]
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
     model.release()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DTB_CIN_TC_F16X1 (precision code 4): single tensor pass on power-of-two-scaled fp16 operands
+# ---------------------------------------------------------------------------------------------------------------
+F16_CASES = [  # (F, sizes, direct, bias, act, B) -- embedding dim 16 only
+    (26, (128, 128, 128), False, False, 1, 37),
+    (26, (32, 32, 16), False, True, 1, 64),
+    (10, (64, 32), True, True, 1, 50),
+    (3, (32, 16), False, False, 0, 9),
+]
+
+
+@pytest.mark.parametrize('f,sizes,direct,use_bias,act,b', F16_CASES)
+def test_cin_fp16_single_pass_forward_is_inside_the_parity_bar(f, sizes, direct, use_bias, act, b):
+    """tools/cin_precision_study.py predicts max |err| of 2-6e-4 of the output scale for this scheme; the parity
+    bar is rtol 1e-3 (+ atol 1e-4 of the scale).  Also checks that a backward (bf16x3 kernels) runs on the
+    activations this forward saved."""
+    import ctypes
+    from deeptables_b200 import _native as nat
+    from oracle import layers_ref as L
+    d = 16
+    P = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())     # noqa: E731
+    g = np.random.default_rng(61)
+    vocab = [9 + i for i in range(f)]
+    offs = np.concatenate([[0], np.cumsum(vocab)]).astype(np.int64)
+    table = ((g.random((int(offs[-1]), d)) - 0.5) * 0.1).astype(np.float32)
+    idx = np.stack([g.integers(0, v, size=b) for v in vocab], axis=1).astype(np.int32)
+    fns = L.cin_field_nums(f, sizes, direct)
+    filt = [(g.normal(size=(f * fns[k], s)) / np.sqrt(f * fns[k])).astype(np.float32) for k, s in enumerate(sizes)]
+    bias = [g.normal(size=s).astype(np.float32) * 0.1 for s in sizes] if use_bias else None
+    sizes_c, n = nat.int_array(sizes), len(sizes)
+    if not nat.lib.dtb_cin_tc_supported(f, d, sizes_c, n, int(direct)):
+        pytest.skip('shape not supported by the tensor-core kernels')
+    params = dict(cross_layer_size=sizes, direct=direct, use_bias=use_bias, activation='relu' if act else 'linear')
+    pw = L.cin_pooled_width(f, params)
+    dev = lambda a: torch.tensor(a).cuda()                                   # noqa: E731
+    d_idx, d_tab, d_offs = dev(idx), dev(table), dev(offs)
+    d_w = dev(np.concatenate([x.reshape(-1) for x in filt]))
+    d_b = dev(np.concatenate(bias)) if use_bias else None
+    pooled = torch.empty(b, pw, device='cuda')
+    ws_bytes = nat.lib.dtb_cin_workspace_bytes(b, f, d, sizes_c, n, int(direct), 1)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
+    saved = torch.empty(nat.lib.dtb_cin_saved_bytes(b, f, d, sizes_c, n, int(direct)), dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(pooled), P(saved), P(ws), ws_bytes,
+                                  b, f, d, sizes_c, n, int(direct), act, 4, None, None), 'cin_fwd fp16x1')
+    # float64 reference of the pooled feature maps (the oracle's CIN up to the sum over D: identity output kernels)
+    t64 = torch.tensor(table, dtype=torch.float64)
+    x = torch.stack([t64[offs[i] + torch.tensor(idx[:, i].astype(np.int64))] for i in range(f)], dim=1)
+    outs = []
+    for col in range(pw):
+        w = {f'f_{k}': torch.tensor(filt[k], dtype=torch.float64).unsqueeze(0) for k in range(n)}
+        if use_bias:
+            w.update({f'bias{k}': torch.tensor(bias[k], dtype=torch.float64) for k in range(n)})
+        kern = torch.zeros(pw, 1, dtype=torch.float64)
+        kern[col, 0] = 1.0
+        w['exFM_out/kernel'], w['exFM_out/bias'] = kern, torch.zeros(1, dtype=torch.float64)
+        outs.append(L.cin(x, params, w))
+    want = torch.cat(outs, dim=1).numpy()
+    got = pooled.cpu().double().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() / scale < 1e-3
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-4 * scale)
+    gt = torch.zeros(table.shape, device='cuda')
+    dw = torch.zeros_like(d_w)
+    db = torch.zeros(sum(sizes), device='cuda') if use_bias else None
+    d_dp = torch.randn(b, pw, device='cuda')
+    nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt), P(dw), P(db), P(ws),
+                                  ws_bytes, b, f, d, sizes_c, n, int(direct), act, 4, None), 'cin_bwd after fp16x1 forward')
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(gt).all()) and bool(torch.isfinite(dw).all()) and float(dw.abs().max()) > 0

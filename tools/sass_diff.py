@@ -25,7 +25,8 @@ def kernels(path):
 
 
 def norm(name):
-    return name.replace('ELi0EEEvNS', 'EEEvNS')       # a defaulted trailing template argument <.., 0>
+    # a defaulted trailing template argument <.., 0> / <.., false>
+    return name.replace('ELi0EEEvNS', 'EEEvNS').replace('ELb0EEEvNS', 'EEEvNS')
 
 
 def main():
