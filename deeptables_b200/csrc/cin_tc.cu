@@ -791,6 +791,7 @@ struct CinTcBwdParams {
   unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed h_{k+1} tiles (as in CinTcParams)
   int b_stage_bytes;
   int compact;                                    // saved activations in the compact format (cin_tc_compact)
+  const int* wmax;                                // experiment 6 only: bit pattern of max|W_k| per layer
 };
 
 // weights -> per chunk i: [hi | lo] image of B[n=j][k=l] = W[(i*H + j), l], canonical K-major no swizzle
@@ -810,6 +811,24 @@ __global__ void cin_tc_pack_t_kernel(const float* __restrict__ w, uint8_t* __res
     uint8_t* base = out + (int64_t)i * per_chunk * 4;
     *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
     *reinterpret_cast<__nv_bfloat16*>(base + per_chunk * 2 + off) = lo;
+  }
+}
+
+// experiment 6: ONE fp16 image per chunk (the "hi" slot) of B[n=j][k=l] = W[(i*H + j), l] * s_W
+__global__ void cin_tc_pack_t_f16_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
+                                         int L, const int* __restrict__ wmax) {
+  float s, inv;
+  tc::pow2_scale_to_1024(__int_as_float(*wmax), s, inv);
+  const int64_t per_chunk = (int64_t)L * Hp;
+  const int64_t total = per_chunk * F;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t / per_chunk);
+    const int rem = (int)(t - (int64_t)i * per_chunk);
+    const int j = rem / L, l = rem - j * L;       // l fastest: coalesced reads
+    const float v = j < H ? w[((int64_t)i * H + j) * L + l] * s : 0.f;
+    const int64_t off = ((int64_t)(l >> 3) * (Hp >> 3) + (j >> 3)) * 128 + (j & 7) * 16 + (l & 7) * 2;
+    *reinterpret_cast<__half*>(out + (int64_t)i * per_chunk * 4 + off) = __float2half_rn(v);
   }
 }
 
@@ -844,6 +863,10 @@ __host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int 
 //      LBO 2048 / SBO 128 as in tc_selftest_kernel<false>) and passes 0 and 2 use the SS form; only dC_lo stays in
 //      TMEM (pass 1, TS form).  Tests whether A-from-TMEM operand reads limit the N = 64 MMAs / collide with the
 //      accumulator read-out.  Costs 64 KB of shared memory, so it runs with 3 weight stages instead of 4.
+//   6: a REAL variant: ONE tensor pass on fp16 operands (the counterpart of cin_tc_fwd_kernel<16, true>): the dC row is
+//      scaled by an exact power of two chosen from its own max (a second sweep over the row computes it), the weights
+//      by the per-layer scale of cin_tc_pack_t_f16_kernel; both are undone on dx / dh.  The bf16 hi/lo dC tiles for
+//      wgrad are written as before.
 template <int D, int kExp = 0>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
   constexpr int R = 128 / D;
@@ -936,6 +959,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         }
         const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
         uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
+        [[maybe_unused]] float trow = 1.f, inv_acc = 1.f;      // kExp 6: scale of this dC row, and 1/(trow * s_W)
+        if constexpr (kExp == 6) {
+          float dmax = 0.f;
+#pragma unroll
+          for (int cb = 0; cb < kMaxL / 16; ++cb) {
+            if (cb * 16 < L) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = cb * 16 + j;
+                float gsum = 0.f;
+                if (valid && col >= pool_lo && col < pool_lo + pool_n) gsum = __ldg(dprow + (col - pool_lo));
+                if (col < kMaxHp) {
+                  if (col < hid_n) gsum += dh[col];
+                }
+                const bool on = p.compact ? (((mw[cb >> 1] >> ((cb & 1) * 16 + j)) & 1u) != 0u)
+                                          : (valid && Trow[col] > 0.f);
+                if (p.act == DTB_ACT_RELU && !on) gsum = 0.f;
+                dmax = fmaxf(dmax, fabsf(gsum));
+              }
+            }
+          }
+          float inv_t, sw, inv_w;
+          tc::pow2_scale_to_1024(dmax, trow, inv_t);
+          tc::pow2_scale_to_1024(__int_as_float(__ldg(p.wmax + k)), sw, inv_w);
+          inv_acc = inv_t * inv_w;
+        }
 #pragma unroll
         for (int cb = 0; cb < kMaxL / 16; ++cb) {
           if (cb * 16 < L) {
@@ -966,10 +1015,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
               uint8_t* arow = smem_a + g * kAHiTile + (t >> 3) * 128 + (t & 7) * 16;     // k-group stride 2048 B
               *reinterpret_cast<uint4*>(arow + (2 * cb) * 2048) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
               *reinterpret_cast<uint4*>(arow + (2 * cb + 1) * 2048) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
+            } else if constexpr (kExp == 6) {
+              uint32_t zf[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) zf[q] = tc::pack_f16x2(dc[2 * q] * trow, dc[2 * q + 1] * trow);
+              tc::tmem_st8v(t_tile + cb * 8, zf[0], zf[1], zf[2], zf[3], zf[4], zf[5], zf[6], zf[7]);
             } else {
               tc::tmem_st8v(t_tile + cb * 8, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
             }
-            tc::tmem_st8v(t_tile + 64 + cb * 8, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
+            if constexpr (kExp != 6)
+              tc::tmem_st8v(t_tile + 64 + cb * 8, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
             *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
             *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
             *reinterpret_cast<uint4*>(dcblk + 32 * L + (cb * 2) * 256) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
@@ -1007,7 +1062,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         for (int i = 0; i < F; ++i) {
           const uint32_t buf = acc_cnt & 1, par = (acc_cnt >> 1) & 1;
           ++acc_cnt;
-          const float xi = x0g[((size_t)r * F + i) * D + d];
+          const float xi = kExp == 6 ? x0g[((size_t)r * F + i) * D + d] * inv_acc : x0g[((size_t)r * F + i) * D + d];
           tc::mbar_wait(&acc_full[g * 2 + buf], par);
           tc::fence_after_thread_sync();
           float dx = 0.f;
@@ -1060,6 +1115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[g * 2 + buf]);
+          if constexpr (kExp == 6) dx *= inv_acc;
           dxg[i * 128 + t] += dx;
         }
         if (k == 0) {
@@ -1084,7 +1140,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
         const int Hp = p.Hp[k], L = p.L[k];
-        const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)Hp);
+        const uint32_t idesc = kExp == 6 ? tc::make_idesc_f16(128, (uint32_t)Hp) : tc::make_idesc_bf16(128, (uint32_t)Hp);
         const uint32_t lbo_b = (uint32_t)(Hp >> 3) * 128;
         const uint32_t img_b = (uint32_t)L * Hp * 2;
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
@@ -1105,7 +1161,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
               const uint32_t d_tmem = a_base + 128 + buf * 64;
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass) {
-                if (pass < p.n_pass) {
+                if (pass < (kExp == 6 ? 1 : p.n_pass)) {
                   const uint32_t a_addr = a_base + (pass == 1 ? 64 : 0);
                   const uint32_t b_img = b_addr + (pass == 2 ? img_b : 0);
 #pragma unroll
@@ -1139,7 +1195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
       uint32_t chunk = 0;
       for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int k = p.n_layers - 1; k >= 0; --k) {
-          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * (p.n_pass > 1 ? 2 : 1);
+          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * ((kExp != 6 && p.n_pass > 1) ? 2 : 1);
           const uint32_t stride = (uint32_t)p.L[k] * p.Hp[k] * 4;
           const uint8_t* src = p.wpack + p.wpack_off[k];
           for (int i = 0; i < F; ++i, ++chunk) {
@@ -1431,6 +1487,7 @@ static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st
       case 2: return launch_dgrad_exp<16, 2>(p, smem_bytes, st);
       case 3: return launch_dgrad_exp<16, 3>(p, smem_bytes, st);
       case 4: return launch_dgrad_exp<16, 4>(p, smem_bytes, st);
+      case 6: return launch_dgrad_exp<16, 6>(p, smem_bytes, st);
       case 5: {
         const int need = tc_bwd_layout(p.b_stage_bytes, p.F, 3, 2 * 128 * kMaxL * 2).total;
         if (need <= 227 * 1024) return launch_dgrad_exp<16, 5>(p, need, st);
@@ -1494,7 +1551,16 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (phase != 2) {
-      cin_tc_pack_t_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k]);
+      if (s.D == 16 && (g_tc_dbg >> 4) == 6) {       // experiment 6: scaled fp16 weights, max words in the trailing slack
+        int* wmax = reinterpret_cast<int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 64) + k;
+        DTB_CUDA_OK(cudaMemsetAsync(wmax, 0, sizeof(int), st));
+        const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
+        cin_tc_wmax_kernel<<<(int)((n_w + 255) / 256 < 64 ? (n_w + 255) / 256 : 64), 256, 0, st>>>(weights + s.w_off[k], n_w, wmax);
+        DTB_LAUNCH_OK();
+        cin_tc_pack_t_f16_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k], wmax);
+      } else {
+        cin_tc_pack_t_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + woff, s.F, s.H[k], p.Hp[k], s.L[k]);
+      }
       DTB_LAUNCH_OK();
     }
     woff += chunk * s.F;
@@ -1502,6 +1568,7 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     if ((int)chunk > bstage) bstage = (int)chunk;
   }
   p.b_stage_bytes = bstage;
+  p.wmax = reinterpret_cast<const int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 64);
   const TcBwdSmemLayout lay = tc_bwd_layout(bstage, s.F);
   int rc = DTB_OK;
   if (phase != 2) switch (s.D) {
