@@ -100,3 +100,84 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# backward: dgrad  dZ = dC . W^T  (A = dC row, per-row scale)   and   wgrad  dW = Z^T . dC  (reduction over the batch
+# rows: ONE scale per operand and layer)
+# ---------------------------------------------------------------------------------------------------------------
+def gemm_bwd(a, b, scheme, row_scale):
+    """a [M,K] @ b [K,N] with both operands rounded per `scheme`; row_scale: per-row (True) or global scale for a."""
+    if scheme == 'exact':
+        return a @ b
+    fmt = torch.bfloat16 if scheme.startswith('bf16') else torch.float16
+    sa = sb = 1.0
+    if fmt is torch.float16:
+        sa = pow2_scale(a, 1024.0, dim=1) if row_scale else pow2_scale(a, 1024.0)
+        sb = pow2_scale(b, 1024.0)
+    a32, b32 = (a * sa).to(torch.float32).to(torch.float64), (b * sb).to(torch.float32).to(torch.float64)
+    if scheme.endswith('x1'):
+        acc = rnd(a32, fmt) @ rnd(b32, fmt)
+    else:                                                   # bf16x3
+        ah, al = split(a32, fmt, 2)
+        bh, bl = split(b32, fmt, 2)
+        acc = ah @ bh + al @ bh + ah @ bl
+    return (acc / (sa * sb)).to(torch.float32).to(torch.float64)
+
+
+def cin_backward(x0, weights, d_pooled, scheme):
+    b = x0.shape[0]
+    hs, cs = [x0], []
+    h = x0
+    for k, size in enumerate(SIZES):                        # exact forward: isolates the backward arithmetic
+        z = (x0.unsqueeze(2) * h.unsqueeze(1)).permute(0, 3, 1, 2).reshape(b * D, -1)
+        c = torch.relu(z @ weights[k]).reshape(b, D, size)
+        cs.append(c)
+        if k + 1 < len(SIZES):
+            h = c[:, :, :size // 2].permute(0, 2, 1)
+            hs.append(h)
+    dx0 = torch.zeros_like(x0)
+    dws = [None] * len(SIZES)
+    dh_next = None
+    col = sum(s // 2 for s in SIZES[:-1]) + SIZES[-1]
+    for k in range(len(SIZES) - 1, -1, -1):
+        size = SIZES[k]
+        npool = size if k == len(SIZES) - 1 else size // 2
+        col -= npool
+        dc = torch.zeros(b, D, size, dtype=torch.float64)
+        dc[:, :, size - npool:] = d_pooled[:, col:col + npool].unsqueeze(1)
+        if dh_next is not None:
+            dc[:, :, :size // 2] += dh_next.permute(0, 2, 1)
+        dc = (dc * (cs[k] > 0)).reshape(b * D, size)
+        h = hs[k]
+        hk = h.shape[1]
+        z = (x0.unsqueeze(2) * h.unsqueeze(1)).permute(0, 3, 1, 2).reshape(b * D, -1)
+        dws[k] = gemm_bwd(z.t().contiguous(), dc, scheme, row_scale=False)                    # wgrad
+        dz = gemm_bwd(dc, weights[k].t().contiguous(), scheme, row_scale=True).reshape(b, D, F, hk)   # dgrad
+        dx0 += (dz * h.permute(0, 2, 1).unsqueeze(2)).sum(dim=3).permute(0, 2, 1)
+        dh = (dz * x0.permute(0, 2, 1).unsqueeze(3)).sum(dim=2).permute(0, 2, 1)              # [b, hk, D]
+        if k == 0:
+            dx0 += dh
+        dh_next = dh
+    return dx0, dws
+
+
+def main_backward():
+    torch.manual_seed(2)
+    b = max(32, B // 2)
+    x0 = ((torch.rand(b, F, D, dtype=torch.float64) - 0.5) * 0.1).to(torch.float32).to(torch.float64)
+    hs = [F, SIZES[0] // 2, SIZES[1] // 2]
+    weights = [(((torch.rand(F * hs[k], s, dtype=torch.float64) * 2 - 1) * (6.0 / (F * hs[k])) ** 0.5)
+                .to(torch.float32).to(torch.float64)) for k, s in enumerate(SIZES)]
+    d_pooled = torch.randn(b, sum(s // 2 for s in SIZES[:-1]) + SIZES[-1], dtype=torch.float64) * 1e-3
+    ref_dx, ref_dw = cin_backward(x0, weights, d_pooled, 'exact')
+    print(f'backward, {b} rows (forward exact, so only the backward GEMM arithmetic differs):')
+    for scheme in ('bf16x1', 'fp16x1', 'bf16x3'):
+        dx, dw = cin_backward(x0, weights, d_pooled, scheme)
+        ex = float((dx - ref_dx).abs().max() / ref_dx.abs().max())
+        ew = max(float((a - r).abs().max() / r.abs().max()) for a, r in zip(dw, ref_dw))
+        print(f'{scheme:8s} embedding grad max|err|/max {ex:.2e}   filter grad max|err|/max {ew:.2e}')
+
+
+if __name__ == '__main__':
+    main_backward()
