@@ -867,10 +867,13 @@ __host__ __device__ inline TcBwdSmemLayout tc_bwd_layout(int b_stage_bytes, int 
 //      scaled by an exact power of two chosen from its own max (a second sweep over the row computes it), the weights
 //      by the per-layer scale of cin_tc_pack_t_f16_kernel; both are undone on dx / dh.  The bf16 hi/lo dC tiles for
 //      wgrad are written as before.
+//   7: 6 + the dC tiles for wgrad are ONE fp16 image (row m scaled by its own t_m), 1/t_m is stored per row in the
+//      free "lo" slot and max|dC_k| in the statistics words: the input of cin_tc_wgrad_kernel<true>.
 template <int D, int kExp = 0>
 __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
   constexpr int R = 128 / D;
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool kF16A = (kExp == 6 || kExp == 7);                   // single fp16 pass (7: also fp16 dC tiles for wgrad)
   constexpr int kSB = (kExp == 5) ? 3 : kStagesB;                    // weight stages
   constexpr int kAHiTile = 128 * kMaxL * 2;                           // bytes of one tile's dC_hi operand (experiment 5)
   const TcBwdSmemLayout lay = tc_bwd_layout(p.b_stage_bytes, p.F, kSB, kExp == 5 ? 2 * kAHiTile : 0);
@@ -960,7 +963,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
         uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
         [[maybe_unused]] float trow = 1.f, inv_acc = 1.f;      // kExp 6: scale of this dC row, and 1/(trow * s_W)
-        if constexpr (kExp == 6) {
+        if constexpr (kF16A) {
           float dmax = 0.f;
 #pragma unroll
           for (int cb = 0; cb < kMaxL / 16; ++cb) {
@@ -984,6 +987,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           tc::pow2_scale_to_1024(dmax, trow, inv_t);
           tc::pow2_scale_to_1024(__int_as_float(__ldg(p.wmax + k)), sw, inv_w);
           inv_acc = inv_t * inv_w;
+          if constexpr (kExp == 7) {
+            // wgrad (fp16 variant) folds 1/t_m into its on-the-fly operand: one float per row in the unused "lo"
+            // slot of the row's 16-row tile block; the layer's max|dC| goes to the statistics words (slot 8 + k)
+            *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + 32 * L + (t & 15) * 4) = inv_t;
+            float wm = dmax;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+            if (lane == 0 && wm > 0.f) atomicMax(const_cast<int*>(p.wmax) + 8 + k, __float_as_int(wm));
+          }
         }
 #pragma unroll
         for (int cb = 0; cb < kMaxL / 16; ++cb) {
@@ -1015,7 +1027,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
               uint8_t* arow = smem_a + g * kAHiTile + (t >> 3) * 128 + (t & 7) * 16;     // k-group stride 2048 B
               *reinterpret_cast<uint4*>(arow + (2 * cb) * 2048) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
               *reinterpret_cast<uint4*>(arow + (2 * cb + 1) * 2048) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
-            } else if constexpr (kExp == 6) {
+            } else if constexpr (kF16A) {
               uint32_t zf[8];
 #pragma unroll
               for (int q = 0; q < 8; ++q) zf[q] = tc::pack_f16x2(dc[2 * q] * trow, dc[2 * q + 1] * trow);
@@ -1023,12 +1035,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
             } else {
               tc::tmem_st8v(t_tile + cb * 8, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
             }
-            if constexpr (kExp != 6)
+            if constexpr (!kF16A)
               tc::tmem_st8v(t_tile + 64 + cb * 8, zl[0], zl[1], zl[2], zl[3], zl[4], zl[5], zl[6], zl[7]);
+            if constexpr (kExp == 7) {
+              uint32_t zt[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) zt[q] = tc::pack_f16x2(dc[2 * q] * trow, dc[2 * q + 1] * trow);
+              *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zt[0], zt[1], zt[2], zt[3]);
+              *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zt[4], zt[5], zt[6], zt[7]);
+            } else {
             *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zh[0], zh[1], zh[2], zh[3]);
             *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zh[4], zh[5], zh[6], zh[7]);
             *reinterpret_cast<uint4*>(dcblk + 32 * L + (cb * 2) * 256) = make_uint4(zl[0], zl[1], zl[2], zl[3]);
             *reinterpret_cast<uint4*>(dcblk + 32 * L + (cb * 2 + 1) * 256) = make_uint4(zl[4], zl[5], zl[6], zl[7]);
+            }
             tc::tmem_wait_st();
           }
         }
@@ -1062,7 +1082,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
         for (int i = 0; i < F; ++i) {
           const uint32_t buf = acc_cnt & 1, par = (acc_cnt >> 1) & 1;
           ++acc_cnt;
-          const float xi = kExp == 6 ? x0g[((size_t)r * F + i) * D + d] * inv_acc : x0g[((size_t)r * F + i) * D + d];
+          const float xi = kF16A ? x0g[((size_t)r * F + i) * D + d] * inv_acc : x0g[((size_t)r * F + i) * D + d];
           tc::mbar_wait(&acc_full[g * 2 + buf], par);
           tc::fence_after_thread_sync();
           float dx = 0.f;
@@ -1115,7 +1135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
           tc::fence_before_thread_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&acc_empty[g * 2 + buf]);
-          if constexpr (kExp == 6) dx *= inv_acc;
+          if constexpr (kF16A) dx *= inv_acc;
           dxg[i * 128 + t] += dx;
         }
         if (k == 0) {
@@ -1140,7 +1160,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
         const int Hp = p.Hp[k], L = p.L[k];
-        const uint32_t idesc = kExp == 6 ? tc::make_idesc_f16(128, (uint32_t)Hp) : tc::make_idesc_bf16(128, (uint32_t)Hp);
+        const uint32_t idesc = kF16A ? tc::make_idesc_f16(128, (uint32_t)Hp) : tc::make_idesc_bf16(128, (uint32_t)Hp);
         const uint32_t lbo_b = (uint32_t)(Hp >> 3) * 128;
         const uint32_t img_b = (uint32_t)L * Hp * 2;
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
@@ -1161,7 +1181,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
               const uint32_t d_tmem = a_base + 128 + buf * 64;
 #pragma unroll
               for (int pass = 0; pass < 3; ++pass) {
-                if (pass < (kExp == 6 ? 1 : p.n_pass)) {
+                if (pass < (kF16A ? 1 : p.n_pass)) {
                   const uint32_t a_addr = a_base + (pass == 1 ? 64 : 0);
                   const uint32_t b_img = b_addr + (pass == 2 ? img_b : 0);
 #pragma unroll
@@ -1195,7 +1215,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) cin_tc_dgrad_kernel(const __gri
       uint32_t chunk = 0;
       for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int k = p.n_layers - 1; k >= 0; --k) {
-          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * ((kExp != 6 && p.n_pass > 1) ? 2 : 1);
+          const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2 * ((!kF16A && p.n_pass > 1) ? 2 : 1);
           const uint32_t stride = (uint32_t)p.L[k] * p.Hp[k] * 4;
           const uint8_t* src = p.wpack + p.wpack_off[k];
           for (int i = 0; i < F; ++i, ++chunk) {
@@ -1235,6 +1255,8 @@ struct CinTcWgradParams {
   int F, H, Hp, L, n_pass;
   int n_stage_total;         // ceil(M_pad / 64)
   int stages_per_split;
+  const int* stats;          // fp16 variant: [8 + k] max|dC_k|, [16] max|x0 tiles|, [24 + k] max|h_k tiles| (bit patterns)
+  int layer;
 };
 
 struct WgSmemLayout {
@@ -1253,6 +1275,11 @@ __host__ __device__ inline WgSmemLayout wg_layout(int L, int Hp, int F) {
   return l;
 }
 
+// kF16 = true: ONE fp16 pass (input written by cin_tc_dgrad_kernel<16, 7>).  The reduction runs over the batch rows
+// m, so both operands need scales that do not depend on m inside the MMA: the dC tile row m carries its own t_m, which
+// is cancelled on the other operand, A'[(i,j), m] = x0[m,i] h[m,j] (G / t_m), with ONE per-layer G chosen from the
+// recorded maxima so that |A'| < 1024 (rows whose contribution is negligible may underflow, nothing can overflow).
+template <bool kF16 = false>
 __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __grid_constant__ CinTcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const WgSmemLayout lay = wg_layout(p.L, p.Hp, p.F);
@@ -1302,6 +1329,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     const bool live = (i < F) && (j < H);
     const bool h_is_x = (p.hb == p.xb);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    [[maybe_unused]] float gscale = 1.f, inv_g = 1.f;
+    if constexpr (kF16) {
+      const float xm = __int_as_float(__ldg(p.stats + 16)), hm = __int_as_float(__ldg(p.stats + 24 + p.layer));
+      const float dm = __int_as_float(__ldg(p.stats + 8 + p.layer));
+      tc::pow2_scale_to_1024(xm * hm * dm * (1.0f / 512.0f), gscale, inv_g);     // 1/t_m <= max|dC| / 512
+    }
     for (int s = 0; s < n_st; ++s) {
       const uint32_t sh = s % kWgStages, ph = (s / kWgStages) & 1;
       const uint32_t sa = s % kWgStagesA, pa = (s / kWgStagesA) & 1;
@@ -1312,12 +1345,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
       const float4* xrow = reinterpret_cast<const float4*>(xs + (live ? i : 0) * kWgPad);
       const float4* hrow = reinterpret_cast<const float4*>(hs + (live ? j : 0) * kWgPad);
       uint32_t zh[32], zl[32];
+      if constexpr (kF16) {
+        // the stage's dC blocks carry 1/t_m of their 16 rows at the head of the unused "lo" slot
+        tc::mbar_wait(&full_b[sh], ph);
+        const float* tv = reinterpret_cast<const float*>(smem + lay.b_off + sh * lay.b_bytes);
+#pragma unroll
+        for (int q4 = 0; q4 < 16; ++q4) {
+          const float4 xv = xrow[q4], hv = hrow[q4];
+          const float4 cv = *reinterpret_cast<const float4*>(tv + (q4 >> 2) * (16 * L) + 8 * L + (q4 & 3) * 4);
+          const float sc = live ? gscale : 0.f;
+          zh[2 * q4] = tc::pack_f16x2(xv.x * hv.x * (cv.x * sc), xv.y * hv.y * (cv.y * sc));
+          zh[2 * q4 + 1] = tc::pack_f16x2(xv.z * hv.z * (cv.z * sc), xv.w * hv.w * (cv.w * sc));
+          zl[2 * q4] = zl[2 * q4 + 1] = 0u;
+        }
+      } else {
 #pragma unroll
       for (int q4 = 0; q4 < 16; ++q4) {
         const float4 xv = xrow[q4], hv = hrow[q4];
         const float sc = live ? 1.f : 0.f;
         tc::split_bf16x2(xv.x * hv.x * sc, xv.y * hv.y * sc, zh[2 * q4], zl[2 * q4]);
         tc::split_bf16x2(xv.z * hv.z * sc, xv.w * hv.w * sc, zh[2 * q4 + 1], zl[2 * q4 + 1]);
+      }
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&empty_h[sh]);
@@ -1328,8 +1376,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
       for (int ks = 0; ks < 4; ++ks) {
         tc::tmem_st8v(a_col + ks * 16, zh[ks * 8 + 0], zh[ks * 8 + 1], zh[ks * 8 + 2], zh[ks * 8 + 3], zh[ks * 8 + 4],
                       zh[ks * 8 + 5], zh[ks * 8 + 6], zh[ks * 8 + 7]);
-        tc::tmem_st8v(a_col + ks * 16 + 8, zl[ks * 8 + 0], zl[ks * 8 + 1], zl[ks * 8 + 2], zl[ks * 8 + 3], zl[ks * 8 + 4],
-                      zl[ks * 8 + 5], zl[ks * 8 + 6], zl[ks * 8 + 7]);
+        if constexpr (!kF16)
+          tc::tmem_st8v(a_col + ks * 16 + 8, zl[ks * 8 + 0], zl[ks * 8 + 1], zl[ks * 8 + 2], zl[ks * 8 + 3], zl[ks * 8 + 4],
+                        zl[ks * 8 + 5], zl[ks * 8 + 6], zl[ks * 8 + 7]);
       }
       tc::tmem_wait_st();
       tc::fence_before_thread_sync();
@@ -1349,7 +1398,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
           tc::tmem_wait_ld();
           if (live) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) atomicAdd(dst + cb * 16 + q, __uint_as_float(v[q]));
+            for (int q = 0; q < 16; ++q) atomicAdd(dst + cb * 16 + q, kF16 ? __uint_as_float(v[q]) * inv_g : __uint_as_float(v[q]));
           }
         }
       }
@@ -1357,7 +1406,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
     }
   } else if (warp == 8) {
     const bool leader = elect_one_sync();
-    const uint32_t idesc = tc::make_idesc_bf16_bmn(128, (uint32_t)L);
+    const uint32_t idesc = kF16 ? (tc::make_idesc_f16(128, (uint32_t)L) | (1u << 16)) : tc::make_idesc_bf16_bmn(128, (uint32_t)L);
     // dC tile descriptor (MN-major): LBO = 128 B (k-group), SBO = 256 B (n-group)
     const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
     const uint32_t smem_b_u32 = tc::smem_u32(smem + lay.b_off);
@@ -1377,7 +1426,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) cin_tc_wgrad_kernel(const __gri
           for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-              if (pass < p.n_pass) {
+              if (pass < (kF16 ? 1 : p.n_pass)) {
                 // pass 0: Z_hi*dC_hi ; 1: Z_lo*dC_hi ; 2: Z_hi*dC_lo
                 const uint32_t a_addr = a_base + ks * 16 + (pass == 1 ? 8 : 0);
                 const uint32_t blk = b_addr + ks * (64 * L) + (pass == 2 ? 32 * L : 0);
@@ -1488,6 +1537,7 @@ static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st
       case 3: return launch_dgrad_exp<16, 3>(p, smem_bytes, st);
       case 4: return launch_dgrad_exp<16, 4>(p, smem_bytes, st);
       case 6: return launch_dgrad_exp<16, 6>(p, smem_bytes, st);
+      case 7: return launch_dgrad_exp<16, 7>(p, smem_bytes, st);
       case 5: {
         const int need = tc_bwd_layout(p.b_stage_bytes, p.F, 3, 2 * 128 * kMaxL * 2).total;
         if (need <= 227 * 1024) return launch_dgrad_exp<16, 5>(p, need, st);
@@ -1537,6 +1587,12 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   dc_bytes(s, B, dc_off);
   size_t woff = 0, soff = (size_t)B * s.D * s.F;
   p.compact = cin_tc_compact(s) ? 1 : 0;
+  // experiment builds 6 / 7 (single fp16 pass; profiling hook only): 64 statistics words at the end of the workspace:
+  // [k] max|W_k|, [8 + k] max|dC_k|, [16] max|x0 tiles|, [24 + k] max|h_k tiles|  (bit patterns of non-negative floats)
+  const int exp_build = g_tc_dbg >> 4;
+  const bool f16a = s.D == 16 && (exp_build == 6 || exp_build == 7);
+  const bool f16w = s.D == 16 && exp_build == 7 && d_bias == nullptr;
+  int* stats = reinterpret_cast<int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 256);
   size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float) + (m_pad_rows(s, B) / 64) * s.F * kWgPad;   // as cin_tc_fwd
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
@@ -1551,9 +1607,9 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (phase != 2) {
-      if (s.D == 16 && (g_tc_dbg >> 4) == 6) {       // experiment 6: scaled fp16 weights, max words in the trailing slack
-        int* wmax = reinterpret_cast<int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 64) + k;
-        DTB_CUDA_OK(cudaMemsetAsync(wmax, 0, sizeof(int), st));
+      if (f16a) {                                    // experiments 6 / 7: scaled fp16 weights; statistics words in the trailing slack
+        int* wmax = stats + k;
+        if (k == 0) DTB_CUDA_OK(cudaMemsetAsync(stats, 0, 256, st));
         const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
         cin_tc_wmax_kernel<<<(int)((n_w + 255) / 256 < 64 ? (n_w + 255) / 256 : 64), 256, 0, st>>>(weights + s.w_off[k], n_w, wmax);
         DTB_LAUNCH_OK();
@@ -1568,7 +1624,29 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     if ((int)chunk > bstage) bstage = (int)chunk;
   }
   p.b_stage_bytes = bstage;
-  p.wmax = reinterpret_cast<const int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 64);
+  p.wmax = stats;
+  if (s.D == 16 && exp_build == 7 && d_bias != nullptr) {
+    set_error("dtb_cin_bwd: experiment build 7 (fp16 tiles) has no bias-gradient kernel; use a CIN without bias");
+    return DTB_ERR_UNSUPPORTED;
+  }
+  if (f16w && phase != 2) {
+    // maxima of the operand tiles the forward saved (the wgrad scale G needs them); padded entries are zeros
+    const size_t blocks64 = m_pad_rows(s, B) / 64;
+    const float* sv = reinterpret_cast<const float*>(saved);
+    size_t pos = cin_fp32_saved_bytes(s, B) / sizeof(float);
+    for (int k = 0; k < s.n_layers; ++k) {
+      const int64_t n = (int64_t)(blocks64 * (size_t)(k == 0 ? s.F : s.H[k]) * kWgPad);
+      int nb = (int)((n + 255) / 256);
+      if (nb > sm_count() * 8) nb = sm_count() * 8;
+      cin_tc_wmax_kernel<<<nb, 256, 0, st>>>(sv + pos, n, stats + 24 + k);
+      DTB_LAUNCH_OK();
+      if (k == 0) {
+        cin_tc_wmax_kernel<<<nb, 256, 0, st>>>(sv + pos, n, stats + 16);
+        DTB_LAUNCH_OK();
+      }
+      pos += (size_t)n;          // x0 tiles, then h_1, h_2, ... tiles
+    }
+  }
   const TcBwdSmemLayout lay = tc_bwd_layout(bstage, s.F);
   int rc = DTB_OK;
   if (phase != 2) switch (s.D) {
@@ -1606,8 +1684,15 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     w.stages_per_split = (w.n_stage_total + splits - 1) / splits;
     splits = (w.n_stage_total + w.stages_per_split - 1) / w.stages_per_split;
     const WgSmemLayout wl = wg_layout(w.L, w.Hp, w.F);
-    DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
-    cin_tc_wgrad_kernel<<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
+    if (f16w) {
+      w.stats = stats;
+      w.layer = k;
+      DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
+      cin_tc_wgrad_kernel<true><<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
+    } else {
+      DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
+      cin_tc_wgrad_kernel<false><<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
+    }
     DTB_LAUNCH_OK();
     if (d_bias) {
       const int n_blocks16 = (int)(m_pad / 16);

@@ -3,8 +3,8 @@
 format (bit 17 of dtb_cin_tc_set_variant) for A/B against the default compact one; DGRAD_EXP=n (1..4) selects an
 experiment build of the data-gradient kernel (see cin_tc_dgrad_kernel: 1 skeleton, 2 read-out only, 3 pipelined
 read-out, 4 no MMA -- their gradients are meaningless, only the time is of interest; 5 keeps dC_hi in shared memory
-and 6 runs ONE fp16 pass with per-row scaling: both are real variants, CHECK=1 compares their gradients with the
-product kernel's)."""
+6 runs the data-gradient kernel on ONE fp16 pass with per-row scaling, 7 does that for the weight-gradient
+kernels too (fp16 dC tiles): all three are real variants, CHECK=1 compares their gradients with the product kernels')."""
 import ctypes
 import os
 import sys

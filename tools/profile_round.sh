@@ -20,7 +20,8 @@ REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
 FULL=1 REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -3
 for e in 1 2 3 4; do DGRAD_EXP=$e REPS=3 timeout -s KILL 60 python tools/cin_once.py 2>&1 | tail -1; done   # dgrad ablations
 DGRAD_EXP=5 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | tail -2                         # dC_hi from shared memory
-DGRAD_EXP=6 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | tail -2                         # single fp16 pass
+DGRAD_EXP=6 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | tail -2                         # dgrad on a single fp16 pass
+DGRAD_EXP=7 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | tail -2                         # dgrad + wgrad on a single fp16 pass
 # 5. the fp16 single-pass forward (precision code 4): step time + roofline of the forward kernel, and its parity tests
 timeout -s KILL 120 python bench.py --cin-precision 4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n1_f16fwd.json 2> gpurun_out/${TAG}_bench_n1_f16fwd.err
 cut -c1-300 gpurun_out/${TAG}_bench_n1_f16fwd.json
