@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument('--cpu-sample-rows', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cin-precision', type=int, default=0)
+    ap.add_argument('--cin-exp', type=int, default=0,
+                    help='profiling only: experiment build of the CIN backward kernels (cin_tc.cu), 0 = product kernels')
     ap.add_argument('--id-dist', default='uniform', choices=['uniform', 'zipf'],
                     help="categorical id distribution of the synthetic batches (the headline is 'uniform')")
     return ap.parse_args()
@@ -299,6 +301,8 @@ def main():
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
 
     conf = make_config(args.cin_precision)
+    if args.cin_exp:
+        N.check(N.lib.dtb_cin_tc_set_variant(1 | (args.cin_exp << 12)), 'cin_tc_set_variant')
     cats = [CategoricalColumn(f'C{i + 1}', args.vocab, EMB_DIM) for i in range(F_FIELDS)]
     conts = [ContinuousColumn('input_continuous_all', [f'I{i + 1}' for i in range(N_DENSE)])]
     model = DeepModel('binary', 2, conf, cats, conts, seed=1234)
@@ -375,6 +379,7 @@ def main():
             'dtype': ('f32 (CIN forward GEMMs: one tcgen05 pass on scaled fp16 operands, backward bf16x3; fp32 accumulate)'
                       if args.cin_precision == 4 else 'f32 (CIN GEMMs: bf16x3 split on tcgen05, fp32 accumulate)')
             if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
+            'experiment_build': args.cin_exp or None,
             'data': 'synthetic' if args.id_dist == 'uniform' else f'synthetic ({args.id_dist} ids: NOT the headline distribution)',
             'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, '
                                    '13 dense + 26 sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])',

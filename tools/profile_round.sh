@@ -25,6 +25,8 @@ DGRAD_EXP=7 CHECK=1 REPS=3 timeout -s KILL 90 python tools/cin_once.py 2>&1 | ta
 # 5. the fp16 single-pass forward (precision code 4): step time + roofline of the forward kernel, and its parity tests
 timeout -s KILL 120 python bench.py --cin-precision 4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n1_f16fwd.json 2> gpurun_out/${TAG}_bench_n1_f16fwd.err
 cut -c1-300 gpurun_out/${TAG}_bench_n1_f16fwd.json
+timeout -s KILL 120 python bench.py --cin-precision 4 --cin-exp 7 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_n1_f16all.json 2> gpurun_out/${TAG}_bench_n1_f16all.err
+cut -c1-300 gpurun_out/${TAG}_bench_n1_f16all.json
 timeout -s KILL 120 python -m pytest tests/test_zz_baseline_configs_gpu.py -q -k fp16 --runxfail 2>&1 | tail -5
 timeout -s KILL 90 python tools/bench_hbm.py > gpurun_out/${TAG}_hbm_kernels.txt 2>&1
 tail -12 gpurun_out/${TAG}_hbm_kernels.txt
