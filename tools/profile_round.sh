@@ -1,6 +1,7 @@
 #!/bin/bash
-# One gpurun call that refreshes everything profiles/ needs for a round (1 GPU, ~4-5 minutes of box time):
-#   /usr/local/graft/bin/gpurun --timeout 600 -- 'bash tools/profile_round.sh r2'
+# One gpurun call that refreshes everything profiles/ needs for a round and runs every prepared experiment
+# (1 GPU, ~10 minutes of box time; every step has its own timeout):
+#   /usr/local/graft/bin/gpurun --timeout 1200 -- 'bash tools/profile_round.sh r2 > gpurun_out/r2_profile_round.log 2>&1; tail -60 gpurun_out/r2_profile_round.log'
 # then, HERE (ncu reads reports without a GPU):
 #   python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv 'adam_rows_kernel<0>' > profiles/${TAG}_launches_step.txt
 #   python tools/ncu_extract.py gpurun_out/${TAG}_cin.ncu-rep --json profiles/r1_cin_tc_traffic.json > profiles/${TAG}_cin_tc_ncu_summary.txt
