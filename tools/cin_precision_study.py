@@ -98,8 +98,6 @@ def main():
               f'   entries outside rtol 1e-3 / atol 1e-4*scale: {100 * viol:.3f} %')
 
 
-if __name__ == '__main__':
-    main()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -180,4 +178,5 @@ def main_backward():
 
 
 if __name__ == '__main__':
+    main()
     main_backward()
