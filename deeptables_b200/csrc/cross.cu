@@ -3,8 +3,8 @@
 // HBM-bound: one warp owns one batch row; x0 and the running x_l live in shared memory (W floats
 // each), the W-long dot product is a strided register sum + 5 shuffles.  Per row the kernel moves
 // 2*W*4 bytes (read x, write y) for 4*W*n_layers FLOP.
-// Backward recomputes x_1..x_{L-1} from the saved per-layer scalars (x_l . w_l) -- no reductions --
-// and accumulates d_kernels / d_biases per CTA in shared memory before one atomic per element.
+// Backward: see the register-resident variants below (per-row kernel emits dX + two [B, L] scalar tables, the
+// weight gradients are column reductions); the shared-memory kernels serve inputs wider than 1024 columns.
 #include "dtb_common.cuh"
 
 namespace dtb {
@@ -19,8 +19,9 @@ cross_fwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* x0 = smem + (size_t)wib * 2 * W;
   float* xl = x0 + W;
-  const int warp = blockIdx.x * kCrossWarps + wib;
-  const int n_warps = gridDim.x * kCrossWarps;
+  const int wpb = blockDim.x >> 5;
+  const int warp = blockIdx.x * wpb + wib;
+  const int n_warps = gridDim.x * wpb;
   for (int row = warp; row < B; row += n_warps) {
     for (int c = lane; c < W; c += 32) {
       const float v = X[(int64_t)row * W + c];
@@ -43,64 +44,52 @@ cross_fwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
   }
 }
 
-__global__ void __launch_bounds__(kCrossWarps * 32)
-cross_bwd_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
-                 const float* __restrict__ biases, const float* __restrict__ xw_saved,
-                 const float* __restrict__ dY, float* __restrict__ dX, float* __restrict__ d_kernels,
-                 float* __restrict__ d_biases, int B, int W, int n_layers) {
+// Shared-memory twin of cross_bwd_reg_kernel below for inputs wider than the register variants hold: a warp keeps
+// x0 / g / dx0 of its row in shared memory (3 W floats) and emits dX plus the two [B, L] scalar tables; the weight
+// gradients come from the same column reductions (cross_colreduce / gsum / combine).
+__global__ void cross_bwd_smem_kernel(const float* __restrict__ X, const float* __restrict__ kernels,
+                                      const float* __restrict__ xw_saved, const float* __restrict__ dY,
+                                      float* __restrict__ dX, float* __restrict__ coef, float* __restrict__ gx, int B,
+                                      int W, int n_layers) {
   extern __shared__ float smem[];
-  // layout: per warp: dW, db accumulators [2*L*W] (a lane owns columns lane, lane+32, ...: plain
-  // read-modify-write, no atomics) | x_0..x_{L-1} [L*W], g [W], dx0 [W]
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* wbase = smem + (size_t)wib * (3 * n_layers + 2) * W;
-  float* acc_w = wbase;
-  float* acc_b = wbase + (size_t)n_layers * W;
-  float* xs = wbase + (size_t)2 * n_layers * W;
-  float* g = xs + (size_t)n_layers * W;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* x0 = smem + (size_t)wib * 3 * W;
+  float* g = x0 + W;
   float* dx0 = g + W;
-  for (int i = lane; i < 2 * n_layers * W; i += 32) wbase[i] = 0.f;
-  __syncwarp();
-  const int warp = blockIdx.x * kCrossWarps + wib;
-  const int n_warps = gridDim.x * kCrossWarps;
+  const int warp = blockIdx.x * wpb + wib;
+  const int n_warps = gridDim.x * wpb;
   for (int row = warp; row < B; row += n_warps) {
     const float* s = xw_saved + (int64_t)row * n_layers;
     for (int c = lane; c < W; c += 32) {
-      float x0 = X[(int64_t)row * W + c];
-      float xl = x0;
-      xs[c] = x0;
-      for (int l = 0; l + 1 < n_layers; ++l) {
-        xl = x0 * __ldg(s + l) + xl + __ldg(biases + (size_t)l * W + c);
-        xs[(size_t)(l + 1) * W + c] = xl;
-      }
+      x0[c] = X[(int64_t)row * W + c];
       g[c] = dY[(int64_t)row * W + c];
       dx0[c] = 0.f;
     }
     __syncwarp();
+    float a_l = 1.f;                       // A_l = 1 + sum_{l' < l} s_l'
+    for (int l = 0; l + 1 < n_layers; ++l) a_l += __ldg(s + l);
     for (int l = n_layers - 1; l >= 0; --l) {
-      const float* xl = xs + (size_t)l * W;
       float gx0 = 0.f;
-      for (int c = lane; c < W; c += 32) gx0 += g[c] * xs[c];
+      for (int c = lane; c < W; c += 32) gx0 = fmaf(g[c], x0[c], gx0);
       gx0 = warp_sum(gx0);
       const float sl = __ldg(s + l);
+      if (lane == 0) {
+        coef[(int64_t)row * n_layers + l] = a_l * gx0;
+        gx[(int64_t)row * n_layers + l] = gx0;
+      }
+      const float* w = kernels + (size_t)l * W;
       for (int c = lane; c < W; c += 32) {
         const float gc = g[c];
-        acc_b[(size_t)l * W + c] += gc;
-        acc_w[(size_t)l * W + c] += xl[c] * gx0;
-        dx0[c] += gc * sl;
-        g[c] = gc + __ldg(kernels + (size_t)l * W + c) * gx0;
+        dx0[c] = fmaf(gc, sl, dx0[c]);
+        g[c] = fmaf(__ldg(w + c), gx0, gc);
       }
+      if (l > 0) a_l -= __ldg(s + l - 1);
       __syncwarp();
     }
     for (int c = lane; c < W; c += 32) dX[(int64_t)row * W + c] = g[c] + dx0[c];
     __syncwarp();
   }
-  __syncwarp();
-  for (int i = lane; i < n_layers * W; i += 32) {
-    if (acc_w[i] != 0.f) atomicAdd(d_kernels + i, acc_w[i]);
-    if (acc_b[i] != 0.f) atomicAdd(d_biases + i, acc_b[i]);
-  }
 }
-
 
 // ------------------------------------------------------------------------------------------
 // Register-resident variants (W <= 32*PER): a lane keeps its PER columns of x0 / x_l / g in registers,
@@ -212,7 +201,8 @@ __global__ void __launch_bounds__(256) cross_bwd_reg_kernel(const float* __restr
 // m1[c, l] += sum_rows X[row,c] coef[row,l] ; s[c] += sum_rows dY[row,c]      block = 32 columns x 8 row lanes
 __global__ void cross_colreduce_kernel(const float* __restrict__ X, const float* __restrict__ dY,
                                        const float* __restrict__ coef, float* __restrict__ m1, float* __restrict__ s,
-                                       int B, int W, int n_layers, int rows_per_block) {
+                                       int B, int W, int n_layers, int rows_per_block, int ld, int want_s) {
+  // coef / m1 are [*, ld] with this launch's (<= kCrossMaxL) layers starting at the given pointers
   __shared__ float red[8][32][kCrossMaxL + 1];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int r_begin = blockIdx.y * rows_per_block;
@@ -223,10 +213,10 @@ __global__ void cross_colreduce_kernel(const float* __restrict__ X, const float*
   if (c < W) {
     for (int r = r_begin + threadIdx.y; r < r_end; r += 8) {
       const float x = X[(int64_t)r * W + c];
-      acc[kCrossMaxL] += dY[(int64_t)r * W + c];
+      if (want_s) acc[kCrossMaxL] += dY[(int64_t)r * W + c];
 #pragma unroll
       for (int l = 0; l < kCrossMaxL; ++l)
-        if (l < n_layers) acc[l] = fmaf(x, __ldg(coef + (int64_t)r * n_layers + l), acc[l]);
+        if (l < n_layers) acc[l] = fmaf(x, __ldg(coef + (int64_t)r * ld + l), acc[l]);
     }
   }
 #pragma unroll
@@ -236,21 +226,21 @@ __global__ void cross_colreduce_kernel(const float* __restrict__ X, const float*
     for (int l = 0; l <= kCrossMaxL; ++l) {
       float v = 0.f;
       for (int j = 0; j < 8; ++j) v += red[j][threadIdx.x][l];
-      if (l < n_layers) atomicAdd(m1 + (size_t)c * n_layers + l, v);
-      else if (l == kCrossMaxL) atomicAdd(s + c, v);
+      if (l < n_layers) atomicAdd(m1 + (size_t)c * ld + l, v);
+      else if (l == kCrossMaxL && want_s) atomicAdd(s + c, v);
     }
   }
 }
 
 // G[l] = sum_rows gx[row, l]
-__global__ void cross_gsum_kernel(const float* __restrict__ gx, float* __restrict__ G, int B, int n_layers) {
+__global__ void cross_gsum_kernel(const float* __restrict__ gx, float* __restrict__ G, int B, int n_layers, int ld) {
   float acc[kCrossMaxL];
 #pragma unroll
   for (int l = 0; l < kCrossMaxL; ++l) acc[l] = 0.f;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < B; r += gridDim.x * blockDim.x)
 #pragma unroll
     for (int l = 0; l < kCrossMaxL; ++l)
-      if (l < n_layers) acc[l] += gx[(int64_t)r * n_layers + l];
+      if (l < n_layers) acc[l] += gx[(int64_t)r * ld + l];
 #pragma unroll
   for (int l = 0; l < kCrossMaxL; ++l) {
     const float v = warp_sum(acc[l]);
@@ -286,28 +276,32 @@ int dtb_cross_fwd(const float* X, const float* kernels, const float* biases, flo
   DTB_CHECK_ARG(X && kernels && biases && Y, "NULL argument");
   DTB_CHECK_ARG(B >= 0 && W > 0 && n_layers >= 0, "bad shape");
   if (B == 0) return DTB_OK;
-  if (W <= 512 && n_layers <= kCrossMaxL) {
+  if (W <= 1024) {
     int blocks = ceil_div(B, 8);
     const int capr = sm_count() * 8;
     if (blocks > capr) blocks = capr;
     if (W <= 128)
       cross_fwd_reg_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
-    else
+    else if (W <= 512)
       cross_fwd_reg_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
+    else
+      cross_fwd_reg_kernel<32><<<blocks, 256, 0, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
     DTB_LAUNCH_OK();
     return DTB_OK;
   }
-  const size_t smem = (size_t)kCrossWarps * 2 * W * sizeof(float);
-  if (smem > 200 * 1024) {
+  // wider rows: x0 / x_l of a row in shared memory, as many warps per CTA (<= 4) as the budget holds
+  int warps = (int)((200 * 1024) / ((size_t)2 * W * sizeof(float)));
+  if (warps > kCrossWarps) warps = kCrossWarps;
+  if (warps < 1) {
     set_error("dtb_cross_fwd: input width %d too large for the shared-memory row buffers", W);
     return DTB_ERR_UNSUPPORTED;
   }
+  const size_t smem = (size_t)warps * 2 * W * sizeof(float);
   DTB_CUDA_OK(cudaFuncSetAttribute(cross_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int blocks = ceil_div(B, kCrossWarps);
+  int blocks = ceil_div(B, warps);
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  cross_fwd_kernel<<<blocks, kCrossWarps * 32, smem, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B,
-                                                                             W, n_layers);
+  cross_fwd_kernel<<<blocks, warps * 32, smem, (cudaStream_t)stream>>>(X, kernels, biases, Y, xw_saved, B, W, n_layers);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }
@@ -323,50 +317,58 @@ int dtb_cross_bwd(const float* X, const float* kernels, const float* biases, con
   DTB_CHECK_ARG(X && kernels && biases && xw_saved && dY && dX && d_kernels && d_biases, "NULL argument");
   DTB_CHECK_ARG(B >= 0 && W > 0 && n_layers > 0, "bad shape");
   if (B == 0) return DTB_OK;
-  if (W <= 512 && n_layers <= kCrossMaxL && workspace && workspace_bytes >= dtb_cross_bwd_workspace_bytes(B, W, n_layers)) {
-    cudaStream_t st = (cudaStream_t)stream;
-    float* coef = reinterpret_cast<float*>(workspace);
-    float* gx = coef + (size_t)B * n_layers;
-    float* m1 = gx + (size_t)B * n_layers;
-    float* s = m1 + (size_t)W * n_layers;
-    float* G = s + W;
-    DTB_CUDA_OK(cudaMemsetAsync(m1, 0, ((size_t)W * n_layers + W + n_layers) * sizeof(float), st));
+  if (!workspace || workspace_bytes < dtb_cross_bwd_workspace_bytes(B, W, n_layers)) {
+    set_error("dtb_cross_bwd: workspace missing or smaller than dtb_cross_bwd_workspace_bytes()");
+    return DTB_ERR_INVALID_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* coef = reinterpret_cast<float*>(workspace);
+  float* gx = coef + (size_t)B * n_layers;
+  float* m1 = gx + (size_t)B * n_layers;
+  float* s = m1 + (size_t)W * n_layers;
+  float* G = s + W;
+  DTB_CUDA_OK(cudaMemsetAsync(m1, 0, ((size_t)W * n_layers + W + n_layers) * sizeof(float), st));
+  if (W <= 1024 && n_layers <= kCrossMaxL) {
     int blocks = ceil_div(B, 8);
     const int capr = sm_count() * 8;
     if (blocks > capr) blocks = capr;
     if (W <= 128)
       cross_bwd_reg_kernel<4><<<blocks, 256, 0, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
-    else
+    else if (W <= 512)
       cross_bwd_reg_kernel<16><<<blocks, 256, 0, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
-    DTB_LAUNCH_OK();
-    const int col_blocks = ceil_div(W, 32);
-    int row_blocks = ceil_div((int64_t)sm_count() * 8, col_blocks);
-    if (row_blocks > ceil_div(B, 64)) row_blocks = ceil_div(B, 64);
-    if (row_blocks < 1) row_blocks = 1;
-    const int rpb = ceil_div(B, row_blocks);
-    cross_colreduce_kernel<<<dim3(col_blocks, ceil_div(B, rpb)), dim3(32, 8), 0, st>>>(X, dY, coef, m1, s, B, W, n_layers, rpb);
-    DTB_LAUNCH_OK();
-    int gb = ceil_div(B, 256 * 8);
-    if (gb > sm_count()) gb = sm_count();
-    cross_gsum_kernel<<<gb < 1 ? 1 : gb, 256, 0, st>>>(gx, G, B, n_layers);
-    DTB_LAUNCH_OK();
-    cross_combine_kernel<<<ceil_div(W, 128), 128, 0, st>>>(m1, s, G, kernels, biases, d_kernels, d_biases, W, n_layers);
-    DTB_LAUNCH_OK();
-    return DTB_OK;
+    else
+      cross_bwd_reg_kernel<32><<<blocks, 256, 0, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
+  } else {
+    int warps = (int)((200 * 1024) / ((size_t)3 * W * sizeof(float)));
+    if (warps > kCrossWarps) warps = kCrossWarps;
+    if (warps < 1) {
+      set_error("dtb_cross_bwd: input width %d too large for the shared-memory row buffers", W);
+      return DTB_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (size_t)warps * 3 * W * sizeof(float);
+    DTB_CUDA_OK(cudaFuncSetAttribute(cross_bwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = ceil_div(B, warps);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cross_bwd_smem_kernel<<<blocks, warps * 32, smem, st>>>(X, kernels, xw_saved, dY, dX, coef, gx, B, W, n_layers);
   }
-  const size_t smem = (size_t)kCrossWarps * (3 * n_layers + 2) * W * sizeof(float);
-  if (smem > 200 * 1024) {
-    set_error("dtb_cross_bwd: width %d x %d layers exceeds the shared-memory budget", W, n_layers);
-    return DTB_ERR_UNSUPPORTED;
+  DTB_LAUNCH_OK();
+  const int col_blocks = ceil_div(W, 32);
+  int row_blocks = ceil_div((int64_t)sm_count() * 8, col_blocks);
+  if (row_blocks > ceil_div(B, 64)) row_blocks = ceil_div(B, 64);
+  if (row_blocks < 1) row_blocks = 1;
+  const int rpb = ceil_div(B, row_blocks);
+  int gb = ceil_div(B, 256 * 8);
+  if (gb > sm_count()) gb = sm_count();
+  for (int l0 = 0; l0 < n_layers; l0 += kCrossMaxL) {       // the reductions hold <= kCrossMaxL layers in registers
+    const int nl = n_layers - l0 < kCrossMaxL ? n_layers - l0 : kCrossMaxL;
+    cross_colreduce_kernel<<<dim3(col_blocks, ceil_div(B, rpb)), dim3(32, 8), 0, st>>>(X, dY, coef + l0, m1 + l0, s, B, W, nl,
+                                                                                       rpb, n_layers, l0 == 0);
+    DTB_LAUNCH_OK();
+    cross_gsum_kernel<<<gb < 1 ? 1 : gb, 256, 0, st>>>(gx + l0, G + l0, B, nl, n_layers);
+    DTB_LAUNCH_OK();
   }
-  DTB_CUDA_OK(cudaFuncSetAttribute(cross_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int blocks = ceil_div(B, kCrossWarps * 8);
-  const int cap = sm_count() * 2;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  cross_bwd_kernel<<<blocks, kCrossWarps * 32, smem, (cudaStream_t)stream>>>(X, kernels, biases, xw_saved, dY,
-                                                                             dX, d_kernels, d_biases, B, W,
-                                                                             n_layers);
+  cross_combine_kernel<<<ceil_div(W, 128), 128, 0, st>>>(m1, s, G, kernels, biases, d_kernels, d_biases, W, n_layers);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -402,7 +402,10 @@ def test_cin_invalid_config_rejected(nat):
     assert rc == -1 and 'cross_layer_size' in nat.last_error()
 
 
-@pytest.mark.parametrize('b,w,n', [(50, 429, 6), (33, 17, 1), (64, 40, 4)])
+# (70, 845, 6) = BASELINE configs[3] (F*32 + 13), (40, 1079, 4) PNN-width, (21, 1500, 3) shared-memory kernels,
+# (30, 300, 10) more layers than one reduction launch holds
+@pytest.mark.parametrize('b,w,n', [(50, 429, 6), (33, 17, 1), (64, 40, 4), (70, 845, 6), (40, 1079, 4), (21, 1500, 3),
+                                   (30, 300, 10)])
 def test_cross_fwd_bwd(nat, b, w, n):
     g = np.random.default_rng(14)
     x = g.normal(size=(b, w)).astype(np.float32)

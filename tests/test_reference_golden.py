@@ -144,8 +144,6 @@ def test_modelconfig_mirror_matches_reference_defaults():
 # GPU: the CUDA engine against the same reference-code vectors (through DeepModel -> C ABI)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: not yet executed on a B200; '
-                                        'the same path is covered through the oracle in tests/test_model_gpu.py')
 @pytest.mark.parametrize('meta', MODEL_CASES, ids=[m['case'] for m in MODEL_CASES])
 def test_cuda_model_reproduces_reference_build_model(meta):
     """Load the reference model's weights by name into the CUDA DeepModel and compare task_output with the

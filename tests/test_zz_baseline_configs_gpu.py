@@ -2,17 +2,14 @@
 cases: the oracle cannot hold 1.66 GB tables comfortably, so each case checks size-independent properties on the
 whole batch and compares a sample of rows against the CPU oracle run on a compacted copy of the weights
 (only the embedding rows those sample rows reference).
-
-Written after the round-1 GPU budget was spent, hence non-strict xfail until it has run once on a B200 (the file
-name sorts last on purpose)."""
+"""
 import numpy as np
 import pytest
 import torch
 
 from oracle import model_ref as M
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='new: not yet executed on a B200 (round-1 GPU budget spent)')]
+pytestmark = [pytest.mark.gpu]
 
 F, C, V = 26, 13, 1_000_000
 
