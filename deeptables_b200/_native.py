@@ -38,8 +38,9 @@ _SIGNATURES = {
     'dtb_batchnorm_train_fwd': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, c_float, P]),
     'dtb_batchnorm_infer_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_float, P]),
     'dtb_batchnorm_bwd': (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_float, P]),
-    'dtb_dense_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
-    'dtb_dense_bwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_dense_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'dtb_dense_fwd': (c_int, [P, P, P, P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
+    'dtb_dense_bwd': (c_int, [P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, c_int, P]),
     'dtb_dropout': (c_int, [P, P, c_int64, c_float, c_ulonglong, P]),
     'dtb_loss_fwd_bwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_adam_dense': (c_int, [P, P, P, P, c_int64, c_float, c_double, c_double, c_float, c_int, P]),

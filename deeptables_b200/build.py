@@ -61,7 +61,7 @@ def build(force=False, verbose=True):
             raise RuntimeError(f'nvcc failed on {src}:\n{out.decode()}')
         if verbose and out.strip():
             sys.stderr.write(out.decode())
-    cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs + ['-lcublas']
+    cmd = [NVCC, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', OUT] + objs      # no GEMM library: every kernel of the product is hand-written
     subprocess.check_call(cmd)
     with open(stamp, 'w') as f:
         f.write(fp)

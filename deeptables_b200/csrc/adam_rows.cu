@@ -20,12 +20,33 @@ __device__ __forceinline__ void replay_zero_grad(float4& p, float4& m, float4& v
   if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f &&
       v.w == 0.f)
     return;   // never-touched row: zero-gradient steps are the identity
-  for (int s = from; s <= upto; ++s) {
+  int s = from;
+  for (; s <= upto; ++s) {
+    const float4 m0 = m;
     const float a = __ldg(alpha_table + s);
     adam_update(p.x, m.x, v.x, 0.f, a, omb1, omb2, eps);
     adam_update(p.y, m.y, v.y, 0.f, a, omb1, omb2, eps);
     adam_update(p.z, m.z, v.z, 0.f, a, omb1, omb2, eps);
     adam_update(p.w, m.w, v.w, 0.f, a, omb1, omb2, eps);
+    // Long gaps (rare ids of a long-tailed column).  After ~1000 zero-gradient steps m reaches the fixed point of its
+    // decay (zero or the smallest denormals, |m| < 1e-44): from then on |m * alpha / (sqrt(v) + eps)| < 1e-40, which
+    // rounds away against any |p| > 1e-25 -- p and m no longer change and only the decay of v is left.
+    if (m.x == m0.x && m.y == m0.y && m.z == m0.z && m.w == m0.w && fabsf(m.x) < 1e-44f && fabsf(m.y) < 1e-44f &&
+        fabsf(m.z) < 1e-44f && fabsf(m.w) < 1e-44f && fabsf(p.x) > 1e-25f && fabsf(p.y) > 1e-25f &&
+        fabsf(p.z) > 1e-25f && fabsf(p.w) > 1e-25f) {
+      ++s;
+      break;
+    }
+  }
+  // v-only tail: one fma per element per step (adam_update's v line with g = 0), until v reaches its own fixed point
+  // (~90 000 steps): same bits as the dense kernel, bounded work per row.
+  for (; s <= upto; ++s) {
+    const float4 v0 = v;
+    v.x = __fmaf_rn(__fsub_rn(0.f, v.x), omb2, v.x);
+    v.y = __fmaf_rn(__fsub_rn(0.f, v.y), omb2, v.y);
+    v.z = __fmaf_rn(__fsub_rn(0.f, v.z), omb2, v.z);
+    v.w = __fmaf_rn(__fsub_rn(0.f, v.w), omb2, v.w);
+    if (v.x == v0.x && v.y == v0.y && v.z == v0.z && v.w == v0.w) break;
   }
 }
 

@@ -12,7 +12,7 @@
 //   T_k[(b,d), l]         = act(Z_k @ W_k + bias_k)        (layers.py:705-709)
 //   h_{k+1}               = T_k[..., :L/2] (or T_k when direct) ; pooled = sum_d of the rest (712-726)
 #include "dtb_common.cuh"
-#include "dtb_cublas.cuh"
+#include "dense_tc.h"
 #include "cin_shapes.h"
 #include "cin_impl.h"
 
@@ -165,6 +165,21 @@ static int fp32_chunk_rows(int B, int D, int kmax) {
   return (int)rows;
 }
 
+// packed bf16 hi/lo images of one layer's filter for the tensor-core GEMMs (dense_tc.cu), either orientation
+static size_t fp32_pack_bytes(const CinShape& s) {
+  size_t m = 0;
+  for (int k = 0; k < s.n_layers; ++k) {
+    const int K = s.F * s.H[k], L = s.L[k];
+    const size_t a = dense_tc_pack_bytes(K, L), b = dense_tc_pack_bytes(L, K);
+    m = a > m ? a : m;
+    m = b > m ? b : m;
+  }
+  return m;
+}
+static size_t fp32_pack_offset(const CinShape& s, int B, int training) {
+  return cin_fp32_workspace_bytes(s, B, training) - fp32_pack_bytes(s) - 1024;
+}
+
 size_t cin_fp32_saved_bytes(const CinShape& s, int B) {
   return (size_t)B * s.D * (s.F + s.sumL) * sizeof(float);
 }
@@ -181,7 +196,7 @@ size_t cin_fp32_workspace_bytes(const CinShape& s, int B, int training) {
     bytes += 2 * (size_t)bc * s.D * s.Hmax * sizeof(float);             // dh ping-pong
     bytes += (size_t)bc * s.D * s.F * sizeof(float);                    // dx0t
   }
-  return bytes + 1024;
+  return (bytes + 255) / 256 * 256 + fp32_pack_bytes(s) + 1024;
 }
 
 int cin_fp32_fwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
@@ -191,11 +206,8 @@ int cin_fp32_fwd(const CinShape& s, const int32_t* idx, const float* table, cons
     set_error("dtb_cin_fwd: workspace too small");
     return DTB_ERR_INVALID_ARG;
   }
-  cublasHandle_t hnd = cublas_handle(st);
-  if (!hnd) {
-    set_error("dtb_cin_fwd: cuBLAS handle unavailable");
-    return DTB_ERR_CUBLAS;
-  }
+  uint8_t* pack = reinterpret_cast<uint8_t*>(workspace) + fp32_pack_offset(s, B, saved != nullptr);
+  const size_t pack_bytes = fp32_pack_bytes(s);
   const int D = s.D, F = s.F;
   const int bc = fp32_chunk_rows(B, D, s.Kmax);
   float* Z = reinterpret_cast<float*>(workspace);
@@ -223,7 +235,11 @@ int cin_fp32_fwd(const CinShape& s, const int32_t* idx, const float* table, cons
                                                              hk + (size_t)b0 * D * ldh, ldh, Z, rows, F, H);
       DTB_LAUNCH_OK();
       float* T = Tk[k] + (size_t)b0 * D * L;
-      DTB_CUBLAS_OK(gemm_nn(hnd, (int)rows, L, K, Z, K, weights + s.w_off[k], L, T, L, 0.f));
+      {
+        const int rc = dense_tc_rows(Z, K, weights + s.w_off[k], L, 0, nullptr, T, L, (int)rows, K, L, DTB_ACT_NONE, pack,
+                                     pack_bytes, st);
+        if (rc != DTB_OK) return rc;
+      }
       if (bias || act != DTB_ACT_NONE) {
         cin_bias_act_kernel<<<ew_grid(rows * L), 256, 0, st>>>(T, bias ? bias + s.b_off[k] : nullptr, rows * L,
                                                                L, act);
@@ -248,11 +264,8 @@ int cin_fp32_bwd(const CinShape& s, const int32_t* idx, const float* table, cons
     set_error("dtb_cin_bwd: workspace too small");
     return DTB_ERR_INVALID_ARG;
   }
-  cublasHandle_t hnd = cublas_handle(st);
-  if (!hnd) {
-    set_error("dtb_cin_bwd: cuBLAS handle unavailable");
-    return DTB_ERR_CUBLAS;
-  }
+  uint8_t* pack = reinterpret_cast<uint8_t*>(workspace) + fp32_pack_offset(s, B, 1);
+  const size_t pack_bytes = fp32_pack_bytes(s);
   const int D = s.D, F = s.F;
   const int bc = fp32_chunk_rows(B, D, s.Kmax);
   float* Z = reinterpret_cast<float*>(workspace);
@@ -294,8 +307,13 @@ int cin_fp32_bwd(const CinShape& s, const int32_t* idx, const float* table, cons
       cin_build_z_kernel<<<ew_grid(rows * K), 256, 0, st>>>(x0t, hk, ldh, Z, rows, F, H);
       DTB_LAUNCH_OK();
       // dW_k[K, L] += Z^T dC ; dZ[rows, K] = dC W_k^T
-      DTB_CUBLAS_OK(gemm_tn(hnd, K, L, (int)rows, Z, K, dC, L, d_weights + s.w_off[k], L, 1.f));
-      DTB_CUBLAS_OK(gemm_nt(hnd, (int)rows, K, L, dC, L, weights + s.w_off[k], L, dZ, K, 0.f));
+      {
+        int rc = dense_tc_wgrad(Z, K, dC, L, d_weights + s.w_off[k], L, nullptr, (int)rows, K, L, st);
+        if (rc == DTB_OK)
+          rc = dense_tc_rows(dC, L, weights + s.w_off[k], L, 1, nullptr, dZ, K, (int)rows, L, K, DTB_ACT_NONE, pack,
+                             pack_bytes, st);
+        if (rc != DTB_OK) return rc;
+      }
       int blocks = ceil_div(rows, 8);
       const int cap = sm_count() * 8;
       if (blocks > cap) blocks = cap;

@@ -6,7 +6,7 @@
 // The Dense GEMMs are plain fp32 library GEMMs (cuBLAS Sgemm); everything around them (bias,
 // activation, narrow logit layers, reductions) is hand-written.  All of it is HBM-bound streaming.
 #include "dtb_common.cuh"
-#include "dtb_cublas.cuh"
+#include "dense_tc.h"
 
 namespace dtb {
 
@@ -413,8 +413,14 @@ int dtb_batchnorm_bwd(const float* X, const float* dY, float* dX, const float* g
   return DTB_OK;
 }
 
-int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, int rows, int in_dim,
-                  int out_dim, int act, void* stream) {
+size_t dtb_dense_workspace_bytes(int in_dim, int out_dim) {
+  if (in_dim <= 0 || out_dim <= 0 || out_dim <= kNarrow) return 0;     // the narrow (logit) kernels need none
+  const size_t a = dense_tc_pack_bytes(in_dim, out_dim), b = dense_tc_pack_bytes(out_dim, in_dim);
+  return a > b ? a : b;
+}
+
+int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, void* workspace,
+                  size_t workspace_bytes, int rows, int in_dim, int out_dim, int act, void* stream) {
   DTB_CHECK_ARG(X && W && Y, "NULL argument");
   DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
   DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU, "unsupported activation");
@@ -428,22 +434,14 @@ int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, i
     DTB_LAUNCH_OK();
     return DTB_OK;
   }
-  cublasHandle_t h = cublas_handle(st);
-  if (!h) {
-    set_error("dtb_dense_fwd: cuBLAS handle unavailable");
-    return DTB_ERR_CUBLAS;
-  }
-  DTB_CUBLAS_OK(gemm_nn(h, rows, out_dim, in_dim, X, in_dim, W, out_dim, Y, out_dim, 0.f));
-  if (bias || act != DTB_ACT_NONE) {
-    const int64_t total = (int64_t)rows * out_dim;
-    bias_act_kernel<<<ew_grid(total), 256, 0, st>>>(Y, bias, total, out_dim, act);
-    DTB_LAUNCH_OK();
-  }
-  return DTB_OK;
+  // tcgen05 GEMM with the bias / activation epilogue fused (dense_tc.cu)
+  return dense_tc_rows(X, in_dim, W, out_dim, 0, bias, Y, out_dim, rows, in_dim, out_dim, act, workspace,
+                       workspace_bytes, st);
 }
 
 int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, float* dX, float* dW,
-                  float* dbias, int rows, int in_dim, int out_dim, int act, void* stream) {
+                  float* dbias, void* workspace, size_t workspace_bytes, int rows, int in_dim, int out_dim, int act,
+                  void* stream) {
   DTB_CHECK_ARG(X && W && dY && dW, "NULL argument");
   DTB_CHECK_ARG(act == DTB_ACT_NONE || (act == DTB_ACT_RELU && Y), "relu backward needs Y");
   DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
@@ -456,12 +454,12 @@ int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, flo
   }
   dim3 grid, block;
   int rpb;
-  if (dbias) {
-    col_reduce_grid(rows, out_dim, grid, block, rpb);
-    col_sum_float_kernel<<<grid, block, 0, st>>>(dY, dbias, rows, out_dim, rpb);
-    DTB_LAUNCH_OK();
-  }
   if (out_dim <= kNarrow) {
+    if (dbias) {
+      col_reduce_grid(rows, out_dim, grid, block, rpb);
+      col_sum_float_kernel<<<grid, block, 0, st>>>(dY, dbias, rows, out_dim, rpb);
+      DTB_LAUNCH_OK();
+    }
     col_reduce_grid(rows, in_dim, grid, block, rpb);
     grid.z = out_dim;
     dense_narrow_bwd_dw<<<grid, block, 0, st>>>(X, dY, dW, rows, in_dim, out_dim, rpb);
@@ -473,15 +471,13 @@ int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, flo
     }
     return DTB_OK;
   }
-  cublasHandle_t h = cublas_handle(st);
-  if (!h) {
-    set_error("dtb_dense_bwd: cuBLAS handle unavailable");
-    return DTB_ERR_CUBLAS;
-  }
-  // dW[in,out] += X^T dZ ; dX[rows,in] = dZ W^T
-  DTB_CUBLAS_OK(gemm_tn(h, in_dim, out_dim, rows, X, in_dim, dY, out_dim, dW, out_dim, 1.f));
-  if (dX) DTB_CUBLAS_OK(gemm_nt(h, rows, in_dim, out_dim, dY, out_dim, W, out_dim, dX, in_dim, 0.f));
-  return DTB_OK;
+  // dW[in,out] += X^T dZ and dbias += colsum(dZ) in one tcgen05 kernel; dX[rows,in] = dZ W^T in another
+  int rc = dense_tc_wgrad(X, in_dim, dY, out_dim, dW, out_dim, dbias, rows, in_dim, out_dim, st);
+  if (rc != DTB_OK) return rc;
+  if (dX)
+    rc = dense_tc_rows(dY, out_dim, W, out_dim, 1, nullptr, dX, in_dim, rows, out_dim, in_dim, DTB_ACT_NONE, workspace,
+                       workspace_bytes, st);
+  return rc;
 }
 
 int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_weight, float* prob, float* dz,

@@ -1,7 +1,5 @@
-// Library-level entry points of the C ABI: version, error string, device query, cuBLAS context.
+// Library-level entry points of the C ABI: version, error string, device query.
 #include "dtb_common.cuh"
-#include "dtb_cublas.cuh"
-#include <mutex>
 #include <atomic>
 #include <cstring>
 #include <cstdlib>
@@ -32,32 +30,11 @@ int sm_count() {
   return cached[dev];
 }
 
-// One cuBLAS handle per device, created on first use; immutable afterwards (the only mutable
-// global of the library, guarded by a mutex as INTEGRATION.md states).
-static std::mutex g_cublas_mu;
-static cublasHandle_t g_cublas[64] = {nullptr};
-
-cublasHandle_t cublas_handle(cudaStream_t stream) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(g_cublas_mu);
-  if (!g_cublas[dev]) {
-    cublasHandle_t h = nullptr;
-    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return nullptr;
-    // Sgemm stays true fp32 (no TF32).  cuBLAS' BF16x9 fp32 emulation was tried for the Dense tower:
-    // no faster at these shapes (11.32 vs 11.19 ms/step), so the plain mode is kept.
-    cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-    g_cublas[dev] = h;
-  }
-  if (cublasSetStream(g_cublas[dev], stream) != CUBLAS_STATUS_SUCCESS) return nullptr;
-  return g_cublas[dev];
-}
-
 }  // namespace dtb
 
 extern "C" {
 
-int dtb_version(void) { return 100; }
+int dtb_version(void) { return 200; }
 
 long long dtb_launch_count(void) { return dtb::g_launches.load(); }
 

@@ -476,7 +476,8 @@ class DeepModel:
         if self.model is None:
             self._build_model()
         self._loss_acc.zero_()
-        self.train_step(cat, cont, yb, sample_weight)
+        sw = _host_to_device(sample_weight, torch.float32, self.device)
+        self.train_step(cat, cont, yb, sw)
         return float(self._loss_acc.item()) / yb.shape[0]
 
     # ------------------------------------------------------------------------------------------
@@ -486,9 +487,15 @@ class DeepModel:
             validation_data=None, shuffle=True, class_weight=None, sample_weight=None, initial_epoch=0,
             steps_per_epoch=None, validation_steps=None, validation_freq=1, max_queue_size=10, workers=1,
             use_multiprocessing=False):
+        if sample_weight is not None and len(sample_weight) != _length(X):
+            raise ValueError(f'sample_weight has {len(sample_weight)} entries for {_length(X)} rows')
         if validation_data is None:
             from sklearn.model_selection import train_test_split
-            X, X_val, y, y_val = train_test_split(X, y, test_size=validation_split)
+            if sample_weight is not None:          # the weights follow their rows through the shuffle + split
+                X, X_val, y, y_val, sample_weight, _ = train_test_split(X, y, np.asarray(sample_weight),
+                                                                        test_size=validation_split)
+            else:
+                X, X_val, y, y_val = train_test_split(X, y, test_size=validation_split)
         else:
             if len(validation_data) != 2:
                 raise ValueError(f'Unexpected validation_data length, expected 2 but {len(validation_data)}.')
@@ -565,6 +572,7 @@ class DeepModel:
                     logs[name] = fn(tt, pp)
             if self.table is not None:
                 self.table.check_status()
+            self.sync_replica_buffers()          # before validation / callbacks snapshot or score the model
             if (epoch + 1) % validation_freq == 0 and n_val > 0:
                 vlogs = self._evaluate_tensors(vcat, vcont, vy, batch_size, validation_steps, metric_fns)
                 if self._dist and vlogs:
@@ -691,6 +699,20 @@ class DeepModel:
                                             ptr(self._alpha_table(self._step)), self._step, E.ADAM_B1, E.ADAM_B2,
                                             E.ADAM_EPS, t.total_rows, t.dim, stream_ptr()), 'adam_rows_flush')
 
+    def sync_replica_buffers(self):
+        """Data parallel: BatchNormalization moving statistics are updated from each rank's own shard; average them
+        over the replicas (tf.distribute.MirroredStrategy aggregates these variables with MEAN, reference
+        deepmodel.py:88-103) so that inference, validation metrics and checkpoints do not depend on the rank."""
+        if not self._dist or self._scope is None or not self._scope.buffers:
+            return
+        flat = torch.cat([b.reshape(-1) for b in self._scope.buffers.values()])
+        torch.distributed.all_reduce(flat)
+        flat /= self.world_size
+        off = 0
+        for b in self._scope.buffers.values():
+            b.copy_(flat[off:off + b.numel()].view(b.shape))
+            off += b.numel()
+
     def state_dict(self):
         self.flush_optimizer_state()
         sd = OrderedDict()
@@ -719,16 +741,43 @@ class DeepModel:
         """Weights + architecture descriptor as .npz keyed by the reference's weight names (the
         reference writes Keras .h5, deepmodel.py:205-221; h5py is absent here -- SURVEY.md 8f rank 2)."""
         sd = {k: v.detach().cpu().numpy() for k, v in self.state_dict().items()}
+        # optimiser state (the reference's .h5 keeps it too): Adam step, moments of the dense weights and of the
+        # embedding rows (state_dict() flushed the lazy rows, so m/v are current for every row)
+        opt = {'__step__': np.array(self._step)}
+        if self._step > 0:
+            opt['__adam_m__'] = self._scope.flat_m.cpu().numpy()
+            opt['__adam_v__'] = self._scope.flat_v.cpu().numpy()
+            if self.table is not None and self.table.m is not None:
+                opt['__adam_table_m__'] = self.table.m.cpu().numpy()
+                opt['__adam_table_v__'] = self.table.v.cpu().numpy()
         os.makedirs(os.path.dirname(os.path.abspath(filepath)) or '.', exist_ok=True)
         with open(filepath, 'wb') as f:
-            np.savez(f, __step__=np.array(self._step), **sd)
+            np.savez(f, **opt, **sd)
 
     def _load_model(self, filepath):
         self._build_model()
         with np.load(filepath) as data:
-            sd = {k: data[k] for k in data.files if k != '__step__'}
+            sd = {k: data[k] for k in data.files if not k.startswith('__')}
+            opt = {k: data[k] for k in data.files if k.startswith('__')}
         self.load_state_dict(sd)
+        self._restore_optimizer(opt)
         return self.model
+
+    def _restore_optimizer(self, opt):
+        """Resume Adam where the checkpoint left it; a weights-only file restarts the optimiser at step 0."""
+        step = int(opt.get('__step__', 0))
+        if step > 0 and '__adam_m__' in opt:
+            self._scope.flat_m.copy_(torch.as_tensor(opt['__adam_m__']).to(self.device))
+            self._scope.flat_v.copy_(torch.as_tensor(opt['__adam_v__']).to(self.device))
+            if self.table is not None and '__adam_table_m__' in opt:
+                t = self.table
+                t.ensure_training_state()
+                t.m.copy_(torch.as_tensor(opt['__adam_table_m__']).to(self.device))
+                t.v.copy_(torch.as_tensor(opt['__adam_table_v__']).to(self.device))
+                t.last_step.fill_(step)
+            self._step = step
+        else:
+            self._step = 0
 
     def release(self):
         self.model = None

@@ -363,6 +363,5 @@ class DeepTable:
             model = deepmodel.DeepModel(pre.task, len(pre.labels) if pre.labels else None, meta['config'],
                                         pre.categorical_columns, pre.continuous_columns,
                                         model_file=os.path.join(filepath, f"{meta['model_name']}.npz"))
-            model._step = meta.get('step', 0)
-            dt._DeepTable__current_model = model
+            dt._DeepTable__current_model = model      # the .npz carries the Adam step and moments (DeepModel._restore_optimizer)
         return dt

@@ -370,7 +370,9 @@ class DenseFn(torch.autograd.Function):
         in_dim, out_dim = kernel.shape
         rows = x.numel() // in_dim
         y = torch.empty(*x.shape[:-1], out_dim, dtype=torch.float32, device=x.device)
-        check(N.lib.dtb_dense_fwd(ptr(x), ptr(kernel), ptr(bias), ptr(y), rows, in_dim, out_dim, act,
+        ws_bytes = N.lib.dtb_dense_workspace_bytes(in_dim, out_dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        check(N.lib.dtb_dense_fwd(ptr(x), ptr(kernel), ptr(bias), ptr(y), ptr(ws), ws_bytes, rows, in_dim, out_dim, act,
                                   stream_ptr()), 'dense_fwd')
         ctx.save_for_backward(x, kernel, y if act else None)
         ctx.has_bias, ctx.act = bias is not None, act
@@ -385,8 +387,10 @@ class DenseFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.zeros_like(kernel)
         db = torch.zeros(out_dim, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-        check(N.lib.dtb_dense_bwd(ptr(x), ptr(kernel), ptr(y), ptr(dz), ptr(dx), ptr(dw), ptr(db), rows, in_dim,
-                                  out_dim, ctx.act, stream_ptr()), 'dense_bwd')
+        ws_bytes = N.lib.dtb_dense_workspace_bytes(in_dim, out_dim)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
+        check(N.lib.dtb_dense_bwd(ptr(x), ptr(kernel), ptr(y), ptr(dz), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws_bytes,
+                                  rows, in_dim, out_dim, ctx.act, stream_ptr()), 'dense_bwd')
         return dx, dw, db, None
 
 

@@ -9,6 +9,7 @@ Tensors are torch CUDA tensors; ``FieldBlock`` (engine.py) is the lazy (B,F,D) e
 that lets FM / CIN / linear / PNN fuse the categorical gather into their kernels.
 """
 import math
+import os
 import re
 import threading
 
@@ -236,7 +237,8 @@ class CIN(Layer):
         self.use_bias = params.get('use_bias', False)
         self.direct = params.get('direct', False)
         self.reduce_D = params.get('reduce_D', False)
-        self.precision = params.get('precision', 0)        # engine knob: 0 auto, 1 fp32, 2 bf16x3, 3 bf16x1, 4 fp16x1 forward (scaled) + bf16x3 backward
+        # test hook: DTB_CIN_PRECISION overrides the auto choice (0) so the whole GPU suite can be run on another CIN mode
+        self.precision = params.get('precision', 0) or int(os.environ.get('DTB_CIN_PRECISION', 0))   # engine knob: 0 auto, 1 fp32, 2 bf16x3, 3 bf16x1, 4 fp16x1 forward (scaled) + bf16x3 backward
         if len(self.cross_layer_size) == 0:
             raise ValueError('cross_layer_size must be a list(tuple) of length greater than 1')
         if self.activation not in E.ACT_CODES:

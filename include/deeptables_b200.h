@@ -8,7 +8,7 @@
  * bodies.  Conventions:
  *
  *  - every pointer is a DEVICE pointer unless the name ends in `_host`; the caller owns every
- *    buffer; the library never allocates output storage (cuBLAS owns a private workspace);
+ *    buffer (outputs and workspaces alike); the library never allocates device memory and links no GEMM library;
  *  - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued asynchronously on it;
  *  - return value: 0 = OK, negative = error (DTB_ERR_*); `dtb_last_error()` gives the text;
  *    no C++ exception crosses this boundary;
@@ -35,7 +35,6 @@ extern "C" {
 #define DTB_ERR_INVALID_ARG (-1)
 #define DTB_ERR_UNSUPPORTED (-2)
 #define DTB_ERR_CUDA (-3)
-#define DTB_ERR_CUBLAS (-4)
 
 /* activation codes (keras Activation names the hot path uses) */
 #define DTB_ACT_NONE 0
@@ -45,7 +44,7 @@ extern "C" {
 int dtb_version(void);
 const char* dtb_last_error(void);
 int dtb_device_sm_count(int* out_host);
-/* number of hand-written kernels this process has launched so far (cuBLAS GEMMs not counted) */
+/* number of kernels this library has launched so far (every kernel on the path is hand-written) */
 long long dtb_launch_count(void);
 
 /* ---- MultiColumnEmbedding (layers.py:889-904) ------------------------------------------- */
@@ -95,14 +94,21 @@ int dtb_batchnorm_bwd(const float* X, const float* dY, float* dX, const float* g
                       const float* save_mean, const float* save_var, float* dgamma, float* dbeta,
                       double* workspace /* [2*cols] */, int rows, int cols, float eps, void* stream);
 
-/* ---- Dense (keras Dense used by deepnets.dnn 415-424, stacking 292, task_output 455) ---- */
+/* ---- Dense (keras Dense used by deepnets.dnn 415-424, stacking 292, task_output 455; the four
+ * projections of MultiheadAttention, layers.py:106-127) ----------------------------------------- */
+/* Layers wider than 8 outputs run as hand-written tcgen05 GEMMs (csrc/dense_tc.cu: operands split on the fly into
+ * bf16 hi + lo, three tensor passes, fp32 accumulation in TMEM => fp32-grade results; bias / activation fused into the
+ * accumulator read-out); out_dim <= 8 (logit layers) as row-dot kernels.  The GEMM path packs the weights into
+ * `workspace` (dtb_dense_workspace_bytes(in_dim, out_dim), 16-byte aligned; 0 for the narrow kernels). */
+size_t dtb_dense_workspace_bytes(int in_dim, int out_dim);
 /* Y[rows,out] = act(X[rows,in] @ W[in,out] + bias).  bias may be NULL. */
-int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, int rows, int in_dim,
-                  int out_dim, int act, void* stream);
+int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, void* workspace,
+                  size_t workspace_bytes, int rows, int in_dim, int out_dim, int act, void* stream);
 /* dY holds dLoss/dY on entry and is overwritten with dLoss/d(pre-activation).  dX may be NULL.
  * dW[in,out] and dbias[out] accumulate (dbias may be NULL). */
 int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, float* dX, float* dW,
-                  float* dbias, int rows, int in_dim, int out_dim, int act, void* stream);
+                  float* dbias, void* workspace, size_t workspace_bytes, int rows, int in_dim, int out_dim,
+                  int act, void* stream);
 
 /* ---- Dropout (keras Dropout, deepmodel.py:430, deepnets.py:426; SpatialDropout1D on the (B,1,D)
  * field embeddings, layers.py:878-901, is element-wise too) -------------------------------------- */
@@ -187,7 +193,7 @@ int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row
                       int D, const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
                       int phase, void* stream);
 /* precision: 0 = auto (tensor-core bf16x3 split when the shape is supported, else fp32 SIMT),
- *            1 = force fp32 SIMT/cuBLAS formulation, 2 = tensor-core bf16x3, 3 = tensor-core bf16x1. */
+ *            1 = force the any-shape materialising formulation (fp32-grade bf16x3 GEMMs of csrc/dense_tc.cu), 2 = tensor-core bf16x3, 3 = tensor-core bf16x1. */
 #define DTB_CIN_AUTO 0
 #define DTB_CIN_FP32 1
 #define DTB_CIN_TC_BF16X3 2

@@ -195,8 +195,11 @@ def test_concat_and_batchnorm(nat, vocab, d, c, b):
     np.testing.assert_allclose(gt.cpu().numpy(), want_g, rtol=1e-5, atol=1e-6)
 
 
+# wide layers = tcgen05 GEMMs (dense_tc.cu): tower shapes, 1079-wide PNN input, AutoInt projection (32 -> 128), ragged
+# row counts / odd widths, more than one 256-column output tile (dX of the 1079-wide layer), K smaller than one chunk
 @pytest.mark.parametrize('rows,i,o,act', [(300, 429, 128, 1), (300, 128, 64, 1), (77, 64, 1, 0), (50, 1, 1, 0),
-                                           (64, 37, 3, 0), (5, 10, 20, 1)])
+                                           (64, 37, 3, 0), (5, 10, 20, 1), (1000, 1079, 128, 1), (2600, 32, 128, 1),
+                                           (129, 845, 128, 0), (33, 7, 300, 1), (4097, 64, 64, 0)])
 def test_dense_fwd_bwd(nat, rows, i, o, act):
     g = np.random.default_rng(7)
     x = g.normal(size=(rows, i)).astype(np.float32)
@@ -205,7 +208,9 @@ def test_dense_fwd_bwd(nat, rows, i, o, act):
     dy = g.normal(size=(rows, o)).astype(np.float32)
     X, W, Bv = dev(x), dev(w), dev(bias)
     Y = torch.empty(rows, o, device='cuda')
-    nat.check(nat.lib.dtb_dense_fwd(P(X), P(W), P(Bv), P(Y), rows, i, o, act, None))
+    wsb = nat.lib.dtb_dense_workspace_bytes(i, o)
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_dense_fwd(P(X), P(W), P(Bv), P(Y), P(ws), wsb, rows, i, o, act, None))
     x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
     w64 = torch.tensor(w, dtype=torch.float64, requires_grad=True)
     b64 = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
@@ -215,7 +220,7 @@ def test_dense_fwd_bwd(nat, rows, i, o, act):
     dX = torch.empty(rows, i, device='cuda')
     dW = torch.zeros(i, o, device='cuda')
     dB = torch.zeros(o, device='cuda')
-    nat.check(nat.lib.dtb_dense_bwd(P(X), P(W), P(Y), P(dY), P(dX), P(dW), P(dB), rows, i, o, act, None))
+    nat.check(nat.lib.dtb_dense_bwd(P(X), P(W), P(Y), P(dY), P(dX), P(dW), P(dB), P(ws), wsb, rows, i, o, act, None))
     gx, gw, gb = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64, w64, b64])
     np.testing.assert_allclose(dX.cpu().numpy(), gx.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(dW.cpu().numpy(), gw.numpy(), rtol=1e-4, atol=1e-4)
@@ -313,6 +318,31 @@ def test_lazy_adam_matches_dense(nat):
     nat.check(nat.lib.dtb_adam_rows_flush(P(wl), P(ml), P(vl), P(last), P(alpha), steps, 0.9, 0.999, 1e-7, rows, d, None))
     assert torch.equal(wl, wd) and torch.equal(ml, md) and torch.equal(vl, vd)
     assert int(last.min().item()) == steps
+
+
+def test_lazy_adam_long_gap_is_bit_exact_and_bounded(nat):
+    """A row untouched for thousands of steps (rare id of a long-tailed column): the replay leaves the full update
+    once m has reached the fixed point of its decay and finishes with the v-only tail -- still the dense kernel's bits."""
+    from deeptables_b200.engine import adam_alpha
+    rows, d, gap = 64, 16, 6000
+    g = np.random.default_rng(3)
+    w0 = g.uniform(-0.05, 0.05, size=(rows, d)).astype(np.float32)
+    g0 = g.normal(size=(rows, d)).astype(np.float32) * np.logspace(-6, 0, rows, dtype=np.float32)[:, None]
+    alpha = dev(np.array([0.0] + [adam_alpha(s) for s in range(1, gap + 3)], dtype=np.float32))
+    offs = dev(np.array([0, rows], dtype=np.int64))
+    ids = dev(np.arange(rows, dtype=np.int32).reshape(rows, 1))
+    wd, md, vd, gd = dev(w0.copy()), torch.zeros(rows, d, device='cuda'), torch.zeros(rows, d, device='cuda'), dev(g0.copy())
+    wl, ml, vl, gl = dev(w0.copy()), torch.zeros(rows, d, device='cuda'), torch.zeros(rows, d, device='cuda'), dev(g0.copy())
+    last = torch.zeros(rows, dtype=torch.int32, device='cuda')
+    nat.check(nat.lib.dtb_adam_rows_apply(P(ids), P(offs), P(wl), P(ml), P(vl), P(gl), P(last), P(alpha), 1, 0.9, 0.999,
+                                          1e-7, rows, 1, d, None))
+    for step in range(1, gap + 1):          # dense: the gradient step, then gap-1 zero-gradient steps
+        nat.check(nat.lib.dtb_adam_dense(P(wd), P(md), P(vd), P(gd), rows * d, float(alpha[step].item()), 0.9, 0.999,
+                                         1e-7, 1, None))
+    nat.check(nat.lib.dtb_adam_rows_catchup(P(ids), P(offs), P(wl), P(ml), P(vl), P(last), P(alpha), gap, 0.9, 0.999, 1e-7,
+                                            rows, 1, d, None))
+    assert torch.equal(wl, wd) and torch.equal(ml, md) and torch.equal(vl, vd)
+    assert float(md.abs().max()) < 1e-44          # the gap really is past the decay of m
 
 
 CIN_CASES = [  # (F, D, sizes, direct, bias, act)
