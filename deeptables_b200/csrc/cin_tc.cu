@@ -23,41 +23,11 @@
 #include "dtb_common.cuh"
 #include "cin_impl.h"
 #include "tcgen05.cuh"
+#include "cin_tc_common.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 namespace dtb {
-
-constexpr int kMaxL = 128;      // feature maps per layer (UMMA N)
-constexpr int kMaxHp = 64;      // padded hidden fields per layer (K chunk)
-constexpr int kTcThreads = 320;
-constexpr int kAccCols = 128;   // TMEM columns per accumulator tile
-constexpr int kTmemCols = 512;
-
-struct CinTcParams {
-  const int32_t* idx;
-  const float* table;
-  const int64_t* row_offsets;
-  const uint8_t* wpack;
-  const float* bias;
-  float* pooled;
-  float* saved;       // training: x0t [B,D,F] then T_k [B,D,L_k] (same layout as the fp32 path)
-  int* status;
-  int B, F, n_layers, act, n_pass, P;
-  int L[kCinMaxLayers], H[kCinMaxLayers], Hp[kCinMaxLayers];
-  int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
-  unsigned long long wpack_off[kCinMaxLayers];   // byte offset of layer k's chunk images
-  unsigned long long saved_off[kCinMaxLayers];   // float offset of T_k inside saved
-  unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed copy of h_{k+1} = T_k[:, :hid_n]
-  unsigned long long xb_off;                     // float offset of the block-transposed copy of x0
-  unsigned long long bias_off[kCinMaxLayers];
-  int b_stage_bytes;                              // bytes reserved per weight stage in smem
-  int dbg;                                        // profiling switches (tools/bench_cin.py): 1 no produce, 2 no MMA, 4 no epilogue
-  int compact;                                    // training: save relu-mask bits instead of the fp32 T_k rows (see cin_tc_compact)
-  const int* wmax;                                // fp16 variant only: bit pattern of max|W_k| per layer (cin_tc_wmax_kernel)
-};
-
-static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // ------------------------------------------------------------------------------------------
 // weight pack: fp32 [K_k, L_k] -> per chunk i: [hi image | lo image], image = canonical K-major
@@ -90,12 +60,6 @@ __global__ void cin_tc_pack_kernel(const float* __restrict__ w, uint8_t* __restr
 // A operand of a granule in TMEM: 16 columns hi + 16 columns lo per tile; kStagesA granules x 2 tiles
 // in flight = 256 columns, next to the two 128-column accumulators.  The weight chunk of field i (all
 // Hp hidden fields, hi+lo, <= 32 KB) is one bulk copy and serves both tiles and both granules.
-constexpr int kSubK = 32;
-constexpr int kStagesA = 4;
-constexpr int kStagesB = 4;
-constexpr int kACols = kSubK / 2;                 // TMEM columns of one bf16 [128 x 32] operand block
-constexpr int kWgPad = 68;                        // row stride (floats) of the block-transposed tiles the wgrad kernel reads
-
 // ---- fp16 variant: max|W_k| (bit pattern, atomicMax on the int view of non-negative floats) and the scaled pack
 __global__ void cin_tc_wmax_kernel(const float* __restrict__ w, int64_t n, int* __restrict__ out) {
   float m = 0.f;
@@ -139,18 +103,6 @@ __host__ __device__ inline TcSmemLayout tc_layout(int b_stage_bytes, int F) {
   l.bar_off = (l.bar_off + 15) / 16 * 16;
   l.total = l.bar_off + 256;
   return l;
-}
-
-__device__ __forceinline__ bool elect_one_sync() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred != 0;
 }
 
 // kF16 = true is the single-pass fp16 variant (DTB_CIN_TC_F16X1, not the default): operands in fp16 (11-bit
@@ -575,6 +527,7 @@ static int g_tc_variant = 1;
 static int g_tc_dbg = 0;
 static int g_tc_bwd_fp32 = 0;   // test hook: run the exact-fp32 backward after the tensor-core forward   // 1: A operand through TMEM (default), 0: through shared memory
 
+static int g_tc_f16_v1 = 0;     // test hook (bit 18 of set_variant): fp16 single pass on the one-thread-per-row kernels
 static int g_tc_full_save = 0;  // test hook (bit 17 of set_variant): keep the fp32 T_k rows in the saved activations
 
 static bool d_supported(int D) { return D == 4 || D == 8 || D == 16 || D == 32; }
@@ -649,9 +602,9 @@ static int launch_fwd(const CinTcParams& p, int smem_bytes, cudaStream_t st) {
 int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* bias, float* pooled, void* saved, void* workspace,
                size_t workspace_bytes, int B, int act, int n_pass, int f16, int* status, cudaStream_t st) {
-  if (f16 && (s.D != 16 || workspace_bytes < wpack_bytes(s) + 64)) {
-    set_error("dtb_cin_fwd: the fp16 single-pass variant is built for embedding dim 16 only (got %d)", s.D);
-    return DTB_ERR_UNSUPPORTED;
+  if (f16 && workspace_bytes < wpack_bytes(s) + 64) {
+    set_error("dtb_cin_fwd: workspace too small for the fp16 weight images and their scale words");
+    return DTB_ERR_INVALID_ARG;
   }
   if (workspace_bytes < wpack_bytes(s)) {
     set_error("dtb_cin_fwd: workspace too small for the packed weights");
@@ -708,7 +661,16 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
   p.compact = cin_tc_compact(s) ? 1 : 0;
   p.wmax = reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(workspace) + wpack_bytes(s));
   const TcSmemLayout lay = tc_layout(bstage, s.F);
-  if (f16) return launch_fwd<16, true>(p, lay.total, st);
+  if (f16) {
+    // two threads per GEMM row (cin_tc2.cu) where the shape allows; bit 18 of dtb_cin_tc_set_variant forces the
+    // one-thread-per-row kernel for A/B timing
+    if (!g_tc_f16_v1 && cin_tc2_fwd_supported(p, s.D)) return cin_tc2_launch_fwd(p, s.D, st);
+    if (s.D != 16) {
+      set_error("dtb_cin_fwd: fp16 single pass: shape outside cin_tc2 and embedding dim %d != 16", s.D);
+      return DTB_ERR_UNSUPPORTED;
+    }
+    return launch_fwd<16, true>(p, lay.total, st);
+  }
 #define DTB_TC_LAUNCH(DD) \
   case DD:                \
     return launch_fwd<DD>(p, lay.total, st);
@@ -735,6 +697,7 @@ int dtb_cin_tc_set_variant(int a_operand_in_tmem) {
   g_tc_dbg = (a_operand_in_tmem >> 8) & 0xff;     // profiling switches ride in bits 8..15
   g_tc_bwd_fp32 = (a_operand_in_tmem >> 16) & 1;  // bit 16: exact-fp32 backward
   g_tc_full_save = (a_operand_in_tmem >> 17) & 1; // bit 17: full (fp32 T_k) saved activations
+  g_tc_f16_v1 = (a_operand_in_tmem >> 18) & 1;    // bit 18: fp16 single pass without the cin_tc2.cu kernels
   g_tc_variant = (a_operand_in_tmem & 0xff) ? 1 : 0;
   return DTB_OK;
 }
@@ -774,25 +737,6 @@ int dtb_tc_selftest(const float* A, const float* Bmat, float* C, void* workspace
 //   dW_k[(i,j), l] = sum_m x0[m,i] h_k[m,j] dC_k[m,l]        [UMMA: A[(i,j), m] built in TMEM from smem tiles
 //                                                             of x0t / h_k, B = dC tiles (MN-major, bulk copy)]
 namespace dtb {
-
-struct CinTcBwdParams {
-  const int32_t* idx;
-  const float* table;
-  const int64_t* row_offsets;
-  const uint8_t* wpack;       // transposed pack (B[n=j][k=l])
-  const float* d_pooled;
-  const float* saved;
-  float* grad_table;
-  uint8_t* dc_tiles;
-  int B, F, n_layers, act, n_pass, P;
-  int L[kCinMaxLayers], H[kCinMaxLayers], Hp[kCinMaxLayers];
-  int pool_lo[kCinMaxLayers], pool_n[kCinMaxLayers], pcol0[kCinMaxLayers], hid_n[kCinMaxLayers];
-  unsigned long long wpack_off[kCinMaxLayers], saved_off[kCinMaxLayers], dc_off[kCinMaxLayers];
-  unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed h_{k+1} tiles (as in CinTcParams)
-  int b_stage_bytes;
-  int compact;                                    // saved activations in the compact format (cin_tc_compact)
-  const int* wmax;                                // experiment 6 only: bit pattern of max|W_k| per layer
-};
 
 // weights -> per chunk i: [hi | lo] image of B[n=j][k=l] = W[(i*H + j), l], canonical K-major no swizzle
 __global__ void cin_tc_pack_t_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,

@@ -91,8 +91,12 @@ def test_cuda_kernels_reproduce_golden_vectors():
     wq = dev(np.concatenate(list(G['att_w']), axis=1))
     bq = dev(np.concatenate(list(G['att_b'])))
     qkvr = torch.empty(b * f, 4 * d, device='cuda')
-    nat.check(nat.lib.dtb_dense_fwd(P(dev(G['x'].reshape(b * f, d))), P(wq), P(bq), P(qkvr), b * f, d, 4 * d, 1, None))
+    wsb = nat.lib.dtb_dense_workspace_bytes(d, 4 * d)
+    wsd = torch.empty(max(wsb, 16), dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_dense_fwd(P(dev(G['x'].reshape(b * f, d))), P(wq), P(bq), P(qkvr), P(wsd), wsb, b * f, d, 4 * d, 1,
+                                    None))
     ya = torch.empty(b, f, d, device='cuda')
     nat.check(nat.lib.dtb_attention_core_fwd(P(qkvr), P(ya), b, f, d, 2, 1, None))
-    np.testing.assert_allclose(ya.cpu().numpy(), G['att_out'], rtol=1e-4, atol=1e-5)
+    # projections wider than 8 run as bf16x3 tensor-core GEMMs (2^-16 per product): 5e-5 absolute on O(1) values
+    np.testing.assert_allclose(ya.cpu().numpy(), G['att_out'], rtol=1e-4, atol=5e-5)
     torch.cuda.synchronize()

@@ -215,15 +215,19 @@ def test_dense_fwd_bwd(nat, rows, i, o, act):
     w64 = torch.tensor(w, dtype=torch.float64, requires_grad=True)
     b64 = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
     y64 = L.dense(x64, w64, b64, 'relu' if act else None)
-    np.testing.assert_allclose(Y.cpu().numpy(), y64.detach().numpy(), rtol=1e-4, atol=1e-5)
+    # out_dim > 8: tcgen05 GEMM on bf16 hi/lo splits (three passes, the dropped lo*lo term is 2^-16 of a product): a
+    # few 1e-5 absolute on O(1) outputs; the narrow kernels are plain fp32
+    tc = o > 8
+    np.testing.assert_allclose(Y.cpu().numpy(), y64.detach().numpy(), rtol=1e-4, atol=1e-4 if tc else 1e-5)
     dY = dev(dy)
     dX = torch.empty(rows, i, device='cuda')
     dW = torch.zeros(i, o, device='cuda')
     dB = torch.zeros(o, device='cuda')
     nat.check(nat.lib.dtb_dense_bwd(P(X), P(W), P(Y), P(dY), P(dX), P(dW), P(dB), P(ws), wsb, rows, i, o, act, None))
     gx, gw, gb = torch.autograd.grad((y64 * torch.tensor(dy, dtype=torch.float64)).sum(), [x64, w64, b64])
-    np.testing.assert_allclose(dX.cpu().numpy(), gx.numpy(), rtol=1e-4, atol=1e-5)
-    np.testing.assert_allclose(dW.cpu().numpy(), gw.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(dX.cpu().numpy(), gx.numpy(), rtol=1e-4, atol=1e-4 if tc else 1e-5)
+    wsc = max(1.0, float(gw.abs().max()))
+    np.testing.assert_allclose(dW.cpu().numpy(), gw.numpy(), rtol=1e-4, atol=(1e-4 * wsc) if tc else 1e-4)
     np.testing.assert_allclose(dB.cpu().numpy(), gb.numpy(), rtol=1e-4, atol=1e-4)
 
 

@@ -33,23 +33,32 @@ ws_bytes = nat.lib.dtb_cin_workspace_bytes(B, F, D, sizes_c, 3, 0, 1)
 ws = torch.empty(ws_bytes, dtype=torch.uint8, device='cuda')
 saved = torch.empty(nat.lib.dtb_cin_saved_bytes(B, F, D, sizes_c, 3, 0), dtype=torch.uint8, device='cuda')
 exp = int(os.environ.get('DGRAD_EXP', 0))
-nat.lib.dtb_cin_tc_set_variant(1 | ((1 << 17) if os.environ.get('FULL') else 0) | (exp << 12))
+prec = int(os.environ.get('PREC', 0))          # CIN precision code (4 = fp16 single pass)
+v1 = (1 << 18) if os.environ.get('V1') else 0   # fp16: one-thread-per-row kernels instead of cin_tc2.cu
+nat.lib.dtb_cin_tc_set_variant(1 | ((1 << 17) if os.environ.get('FULL') else 0) | (exp << 12) | v1)
 reps = int(os.environ.get('REPS', 1))
 for rep in range(reps):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record()
     nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
-                                  sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd')
+                                  sizes_c, 3, 0, 1, prec, None, None), 'cin_fwd')
     e[1].record()
     for phase in (1, 2):                       # 1: weight pack + dgrad, 2: 3 x wgrad
         nat.check(nat.lib.dtb_cin_bwd_phase(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None,
-                                            P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, 0, phase, None), 'cin_bwd_phase')
+                                            P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, prec, phase, None), 'cin_bwd_phase')
         e[1 + phase].record()
     torch.cuda.synchronize()
     print(f'rep {rep}: fwd {e[0].elapsed_time(e[1]):.3f} ms  dgrad {e[1].elapsed_time(e[2]):.3f} ms  wgrad '
           f'{e[2].elapsed_time(e[3]):.3f} ms  ({"full" if os.environ.get("FULL") else "compact"} saved activations, '
-          f'dgrad experiment {exp})', flush=True)
+          f'dgrad experiment {exp}, precision {prec}{" v1" if v1 else ""})', flush=True)
 nat.lib.dtb_cin_tc_set_variant(1)
+if os.environ.get('CHECKF'):
+    # forward of this precision / kernel against the bf16x3 forward
+    ref = torch.empty_like(pooled)
+    nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(ref), P(saved), P(ws), ws_bytes, B, F, D,
+                                  sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd ref')
+    torch.cuda.synchronize()
+    print(f'forward precision {prec} vs bf16x3: max err / scale {float((ref - pooled).abs().max() / ref.abs().max()):.2e}', flush=True)
 if os.environ.get('CHECK') and exp:
     # gradients of the experiment build against the product kernel on the same saved activations
     res = []
