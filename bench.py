@@ -23,8 +23,36 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-F_FIELDS, N_DENSE, EMB_DIM = 26, 13, 16
+F_FIELDS, N_DENSE = 26, 13
 CIN_SIZES = (128, 128, 128)
+_CIN = {'cross_layer_size': CIN_SIZES, 'activation': 'relu', 'use_residual': False, 'use_bias': False, 'direct': False,
+        'reduce_D': False}
+# BASELINE.json configs[1..4] (configs[0], the bank-data README example, needs hypernets' data set: tests/ cover it)
+CONFIGS = {
+    'xdeepfm': dict(nets=['linear', 'cin_nets', 'dnn_nets'], dim=16, batch=65536, kw={'cin_params': _CIN},
+                    metric='xDeepFM train rows/sec, Criteo-shape synthetic',
+                    workload='xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, 13 dense + 26 '
+                             'sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])'),
+    'deepfm_bs8192': dict(nets=['linear', 'fm_nets', 'dnn_nets'], dim=16, batch=8192, kw={},
+                          metric='DeepFM train rows/sec, Criteo-shape synthetic',
+                          workload='DeepFM (linear+fm_nets+dnn_nets) train step, 13 dense + 26 sparse fields, vocab '
+                                   '1M/field, embed_dim 16, bs 8192 (BASELINE configs[1])'),
+    'dcn6_autoint4x32': dict(nets=['dcn_nets', 'autoint_nets'], dim=32, batch=65536,
+                             kw={'cross_params': {'num_cross_layer': 6},
+                                 'autoint_params': {'num_attention': 3, 'num_heads': 4, 'dropout_rate': 0,
+                                                    'use_residual': True}},
+                             metric='DCN(6)+AutoInt(4 heads, d=32) train rows/sec, Criteo-shape synthetic',
+                             workload='dcn_nets (CrossNet depth 6 + DNN) stacked with autoint_nets (3 layers, 4 heads, '
+                                      'd=32) train step, 13 dense + 26 sparse fields, vocab 1M/field, embed_dim 32 '
+                                      '(BASELINE configs[3])'),
+    'five_nets': dict(nets=['fm_nets', 'cin_nets', 'cross_nets', 'autoint_nets', 'pnn_nets'], dim=16, batch=16384,
+                      kw={'cin_params': _CIN},
+                      metric='five-net mix train rows/sec, Criteo-shape synthetic',
+                      workload="nets=['fm_nets','cin_nets','cross_nets','autoint_nets','pnn_nets'] train step, 13 dense + 26 "
+                               'sparse fields, vocab 1M/field, embed_dim 16, 131072 global rows / 8 GPUs = 16384 per GPU '
+                               '(BASELINE configs[4])'),
+}
+EMB_DIM = 16      # of the headline config (CIN_FLOP_PER_ROW below)
 # algorithmic work per row, SURVEY.md 8(d) / DESIGN.md section 5
 CIN_FLOP_PER_ROW = 2 * EMB_DIM * sum(l * k for l, k in zip(CIN_SIZES, (26 * 26, 26 * 64, 26 * 64)))  # 16 400 384
 CIN_BYTES_PER_ROW = 4 * F_FIELDS + 4 * F_FIELDS * EMB_DIM + 4 * (64 + 64 + 128)                        # ids + rows + pooled
@@ -36,7 +64,9 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=65536, help='rows per GPU per step')
+    ap.add_argument('--config', default='xdeepfm', choices=sorted(CONFIGS),
+                    help='which BASELINE.json config to run (default: configs[2], the headline)')
+    ap.add_argument('--batch', type=int, default=0, help='rows per GPU per step (default: the config\'s)')
     ap.add_argument('--vocab', type=int, default=1_000_000)
     ap.add_argument('--cpu-sample-rows', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -48,16 +78,34 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_config(cin_precision=0):
-    from deeptables_b200 import deeptable, deepnets
-    return deeptable.ModelConfig(
-        nets=deepnets.xDeepFM, embeddings_output_dim=EMB_DIM, embedding_dropout=0, dense_dropout=0,
-        metrics=['AUC'],
-        cin_params={'cross_layer_size': CIN_SIZES, 'activation': 'relu', 'use_residual': False,
-                    'use_bias': False, 'direct': False, 'reduce_D': False, 'precision': cin_precision})
+def config_overrides(name, cin_precision=0):
+    """ModelConfig fields of a bench config as a plain dict (no package import: the reference arm uses it too)."""
+    spec = CONFIGS[name]
+    d = dict(nets=list(spec['nets']), embeddings_output_dim=spec['dim'], embedding_dropout=0, dense_dropout=0,
+             metrics=['AUC'])
+    for k, v in spec['kw'].items():
+        d[k] = dict(v)
+    if 'cin_params' in d and cin_precision:
+        d['cin_params']['precision'] = cin_precision
+    return d
 
 
-def synth_batches(n_batches, batch, vocab, seed, id_dist='uniform'):
+def make_config(name='xdeepfm', cin_precision=0):
+    from deeptables_b200 import deeptable
+    return deeptable.ModelConfig(**config_overrides(name, cin_precision))
+
+
+def reference_config(name):
+    """The same configuration for the CPU arm WITHOUT importing the product package (whose import loads the CUDA
+    library): the reference's own ModelConfig() defaults, as dumped from /root/reference by
+    tests/golden/make_reference_golden.py, overlaid with the bench overrides.  oracle/model_ref.py reads dicts."""
+    with open(os.path.join(ROOT, 'tests', 'golden', 'reference_modelconfig.json')) as f:
+        conf = dict(json.load(f)['defaults'])
+    conf.update(config_overrides(name))
+    return conf
+
+
+def synth_batches(n_batches, batch, vocab, seed, id_dist='uniform', pin=True):
     """Synthetic Criteo-shape rows: ids uniform in [0, vocab) (or, labelled, the
     Zipf(1.05) variant of SURVEY 8d: rank r drawn with p ~ r^-1.05, many duplicate rows per batch), dense N(0,1),
     label Bernoulli(0.25).  Returned as pinned HOST tensors."""
@@ -76,7 +124,7 @@ def synth_batches(n_batches, batch, vocab, seed, id_dist='uniform'):
             idx = torch.randint(0, vocab, (batch, F_FIELDS), generator=g, dtype=torch.int32)
         dense = torch.randn(batch, N_DENSE, generator=g)
         y = (torch.rand(batch, 1, generator=g) < 0.25).float()
-        out.append(tuple(t.pin_memory() if torch.cuda.is_available() else t for t in (idx, dense, y)))
+        out.append(tuple(t.pin_memory() if (pin and torch.cuda.is_available()) else t for t in (idx, dense, y)))
     return out
 
 
@@ -155,33 +203,32 @@ def measured_peaks():
 
 
 def cpu_baseline(args, conf, steps=None):
-    """The reference's CPU path: TF/Keras cannot be installed here, so this is the oracle PORT (torch
-    CPU fp32 restatement of the identical graph) on all host cores, on a bounded sample of the
-    same workload."""
+    """The reference's CPU path: TF/Keras cannot be installed here, so this is the oracle PORT (torch CPU fp32
+    restatement of the identical graph) on the host cores, on a bounded sample of the same workload: one micro-batch
+    of `--cpu-sample-rows` rows of the config's batch (the reference formulation materialises 7 GB per CIN layer at
+    65 536 rows), table rows capped at 100 k per field (per-row work does not depend on the table size)."""
     import torch
     from oracle import model_ref as M
+    spec = CONFIGS[args.config]
+    dim = spec['dim']
     cores = os.cpu_count() or 1
-    rows = args.cpu_sample_rows
-    vocab = min(args.vocab, 100_000)          # table size does not change per-row work; keeps init cheap
-    state = M.init_state(conf, [vocab] * F_FIELDS, [EMB_DIM] * F_FIELDS, N_DENSE, seed=1234)
+    rows = min(args.cpu_sample_rows, spec['batch'])
+    vocab = min(args.vocab, 100_000)
+    state = M.init_state(conf, [vocab] * F_FIELDS, [dim] * F_FIELDS, N_DENSE, seed=1234)
     tr = M.RefTrainer(state, conf, F_FIELDS)
-    (idx, dense, y), = synth_batches(1, rows, vocab, 99)
-    # the reference's Adam is dense over every table row; per-row cost is reported, so exclude the
-    # table-size-dependent optimiser sweep from the sample by timing forward+backward+dense Adam on
-    # the sampled table (stated in `sample`)
-    # the graph is dominated by memory-bound elementwise ops: on many-core hosts "all cores" is far from
-    # the fastest setting, so calibrate the thread count on a small slice and use the best one
+    (idx, dense, y), = synth_batches(1, rows, vocab, 99, pin=False)
+    # the graph is dominated by memory-bound elementwise ops: on many-core hosts "all cores" is often not the fastest
+    # setting, so both are reported: a calibration over thread counts on a small slice picks the one that is timed,
+    # and the all-cores time of the same slice is given next to it
     cal_rows = min(rows, 512)
-    best = None
+    cal = {}
     for nt in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(nt)
         tr.train_step(idx[:cal_rows], dense[:cal_rows], y[:cal_rows, 0])
         t0 = time.perf_counter()
         tr.train_step(idx[:cal_rows], dense[:cal_rows], y[:cal_rows, 0])
-        dt_c = time.perf_counter() - t0
-        if best is None or dt_c < best[1]:
-            best = (nt, dt_c)
-    threads = best[0]
+        cal[nt] = time.perf_counter() - t0
+    threads = min(cal, key=cal.get)
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
     tr.train_step(idx, dense, y[:, 0])                    # warm-up step, also sizes the sample
@@ -193,25 +240,91 @@ def cpu_baseline(args, conf, steps=None):
         tr.train_step(idx, dense, y[:, 0])
     dt = (time.perf_counter() - t0) / n
     return {'value': rows / dt, 'unit': 'rows/s', 'cores': threads, 'kind': 'port',
-            'sample': f'{n} train steps x {rows} rows, {threads} threads (best of a calibration over 8..{cores} on {cores} host cores), xDeepFM CIN{CIN_SIZES}, vocab {vocab}/field, torch-CPU fp32 '
-                      f'oracle port (TensorFlow not installable: no network)', 'sec_per_step': dt}
+            'sample': f'{n} train steps x {rows} rows (one micro-batch of the {spec["batch"]}-row batch), {threads} threads = '
+                      f'fastest of a calibration over {sorted(cal)} on {cores} host cores (all {cores} cores: '
+                      f'{cal[max(cal)] / cal[threads]:.2f}x slower on the calibration slice), {args.config}, vocab '
+                      f'{vocab}/field, torch-CPU fp32 oracle port (TensorFlow not installable: no network)',
+            'sec_per_step': dt}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    conf = make_config()
+    spec = CONFIGS[args.config]
+    conf = reference_config(args.config)              # plain dict: nothing of the product package is imported
     base = cpu_baseline(args, conf, steps=max(1, args.steps))
-    line = {'impl': 'reference', 'metric': 'xDeepFM train rows/sec, Criteo-shape synthetic', 'value': base['value'],
+    assert 'deeptables_b200' not in sys.modules, 'the reference arm must not load the product library'
+    line = {'impl': 'reference', 'metric': spec['metric'], 'value': base['value'],
             'unit': 'rows/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': base['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) CIN 128x128x128, 13 dense + 26 sparse, '
-                                   'embed_dim 16; CPU sample', 'global_batch': args.cpu_sample_rows},
+            'config': {'workload': spec['workload'] + '; CPU sample', 'global_batch': min(args.cpu_sample_rows, spec['batch'])},
             'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': base['value'], 'unit': 'rows/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+def _timed_alone(fn, flush):
+    """Median of 5 launches timed with CUDA events on the launching stream, L2 evicted by reading a 512 MB buffer."""
+    import torch
+    for _ in range(2):
+        fn()
+    times = []
+    for _ in range(5):
+        flush.sum()                                # read > L2 of clean lines: nothing cache-resident, nothing dirty to write back
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    return sorted(times)[len(times) // 2]
+
+
+def time_fm_linear_kernel(model, cat, dense, peaks):
+    """configs[1] (DeepFM): the fused gather + linear + FM forward, HBM-bound: 104 B ids + 1 664 B rows + 52 B dense +
+    8 B out per row."""
+    import torch
+    from deeptables_b200 import _native as N
+    from deeptables_b200._native import ptr
+    t = model.table
+    b = cat.shape[0]
+    w_lin = model._scope.params['linear/kernel'].detach().reshape(-1).contiguous() if 'linear/kernel' in model._scope.params \
+        else torch.zeros(F_FIELDS + N_DENSE, device=cat.device)
+    o1, o2 = torch.empty(b, 1, device=cat.device), torch.empty(b, 1, device=cat.device)
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=cat.device)
+
+    def fwd():
+        N.check(N.lib.dtb_fm_linear_fwd(ptr(cat), ptr(t.weight), ptr(t.row_offsets), ptr(dense), ptr(w_lin), ptr(o1), ptr(o2), b,
+                                        F_FIELDS, t.dim, N_DENSE, None, N.stream_ptr()), 'fm_linear_fwd')
+    dt = _timed_alone(fwd, flush)
+    bytes_row = 4 * F_FIELDS + 4 * F_FIELDS * t.dim + 4 * N_DENSE + 8
+    gbs = b * bytes_row / dt / 1e9
+    return {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+            'traffic': None, 'kernel': 'fm_linear_fwd (gather + linear + FM fused)', 'ms': dt * 1e3,
+            'algorithmic_bytes_per_launch': b * bytes_row, 'peak_source': peaks['source']}
+
+
+def time_attention_kernel(model, cat, peaks, heads):
+    """configs[3]: one MultiheadAttention core launch (softmax(QK^T/sqrt(dh))V + residual, relu) on [B, F, 4D]
+    projections, HBM-bound at ~5 FLOP/B: reads 4*F*D, writes F*D floats per row."""
+    import torch
+    from deeptables_b200 import _native as N
+    from deeptables_b200._native import ptr
+    b, d = cat.shape[0], model.table.dim
+    qkvr = torch.randn(b, F_FIELDS, 4 * d, device=cat.device)
+    y = torch.empty(b, F_FIELDS, d, device=cat.device)
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=cat.device)
+
+    def fwd():
+        N.check(N.lib.dtb_attention_core_fwd(ptr(qkvr), ptr(y), b, F_FIELDS, d, heads, 1, N.stream_ptr()), 'attention_core_fwd')
+    dt = _timed_alone(fwd, flush)
+    bytes_row = 4 * F_FIELDS * d * 5
+    gbs = b * bytes_row / dt / 1e9
+    return {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'],
+            'traffic': None, 'kernel': f'attention_core_fwd ({heads} heads, d={d})', 'ms': dt * 1e3,
+            'algorithmic_bytes_per_launch': b * bytes_row, 'peak_source': peaks['source']}
 
 
 def time_cin_kernel(model, cat, peaks):
@@ -245,22 +358,8 @@ def time_cin_kernel(model, cat, peaks):
                                   ptr(t.grad), ptr(dw), None, ptr(ws), ws_bytes, b, F_FIELDS, EMB_DIM, sizes_c, 3, 0, 1,
                                   precision, N.stream_ptr()), 'cin_bwd')
 
-    def timed(fn):
-        for _ in range(2):
-            fn()
-        times = []
-        for _ in range(5):
-            flush.sum()                                # read > L2 of clean lines: nothing cache-resident, nothing dirty to write back
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1) * 1e-3)
-        return sorted(times)[len(times) // 2]
-
-    dt = timed(fwd)
-    dt_b = timed(bwd)
+    dt = _timed_alone(fwd, flush)
+    dt_b = _timed_alone(bwd, flush)
     t.grad.zero_()                                     # the probe's gradients must not leak into training
     tc = bool(N.lib.dtb_cin_tc_supported(F_FIELDS, EMB_DIM, sizes_c, 3, 0)) and precision != 1
     tf = b * CIN_FLOP_PER_ROW / dt / 1e12
@@ -300,10 +399,14 @@ def main():
     from deeptables_b200.deepmodel import DeepModel
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
 
-    conf = make_config(args.cin_precision)
+    spec = CONFIGS[args.config]
+    if not args.batch:
+        args.batch = spec['batch']
+    emb_dim = spec['dim']
+    conf = make_config(args.config, args.cin_precision)
     if args.cin_exp:
         N.check(N.lib.dtb_cin_tc_set_variant(1 | (args.cin_exp << 12)), 'cin_tc_set_variant')
-    cats = [CategoricalColumn(f'C{i + 1}', args.vocab, EMB_DIM) for i in range(F_FIELDS)]
+    cats = [CategoricalColumn(f'C{i + 1}', args.vocab, emb_dim) for i in range(F_FIELDS)]
     conts = [ContinuousColumn('input_continuous_all', [f'I{i + 1}' for i in range(N_DENSE)])]
     model = DeepModel('binary', 2, conf, cats, conts, seed=1234)
     model._build_model()
@@ -371,20 +474,24 @@ def main():
 
     if rank == 0:
         peaks = measured_peaks()
-        roof = time_cin_kernel(model, devb[0][0], peaks)
+        if 'cin_nets' in spec['nets']:
+            roof = time_cin_kernel(model, devb[0][0], peaks)
+        elif 'autoint_nets' in spec['nets']:
+            roof = time_attention_kernel(model, devb[0][0], peaks, spec['kw']['autoint_params']['num_heads'])
+        else:
+            roof = time_fm_linear_kernel(model, devb[0][0], devb[0][1], peaks)
         rows = args.batch * world * args.steps
         h2d = sum(t.numel() * t.element_size() for t in host[0])
         line = {
-            'metric': 'xDeepFM train rows/sec, Criteo-shape synthetic', 'value': rows / secs, 'unit': 'rows/s',
+            'metric': spec['metric'], 'value': rows / secs, 'unit': 'rows/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': secs / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': ('f32 (CIN forward GEMMs: one tcgen05 pass on scaled fp16 operands, backward bf16x3; fp32 accumulate)'
                       if args.cin_precision == 4 else 'f32 (CIN GEMMs: bf16x3 split on tcgen05, fp32 accumulate)')
-            if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32',
+            if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32 (Dense GEMMs: bf16x3 split on tcgen05, fp32 accumulate)',
             'experiment_build': args.cin_exp or None,
             'data': 'synthetic' if args.id_dist == 'uniform' else f'synthetic ({args.id_dist} ids: NOT the headline distribution)',
-            'config': {'workload': 'xDeepFM (linear+cin_nets+dnn_nets) train step, CIN 128x128x128 direct=False, '
-                                   '13 dense + 26 sparse fields, vocab 1M/field, embed_dim 16 (BASELINE configs[2])',
+            'config': {'workload': spec['workload'], 'name': args.config,
                        'global_batch': args.batch * world, 'per_gpu_batch': args.batch, 'parallelism': f'dp{world}',
                        'optimizer': 'Adam(1e-3): dense weights dense, embedding rows exact-lazy (bit-identical to '
                                     'dense Keras Adam)', 'embedding_dropout': 0,
@@ -397,7 +504,7 @@ def main():
             'score_only': score,
         }
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_baseline(args, conf)
+            base = cpu_baseline(args, reference_config(args.config))
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
         print(json.dumps(line))
     if world > 1:

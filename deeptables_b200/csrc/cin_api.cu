@@ -82,7 +82,8 @@ static int cin_bwd_impl(const int32_t* idx, const float* table, const int64_t* r
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(s, precision))
     return cin_tc_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
-                      workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3, phase, st);
+                      workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3,
+                      precision == DTB_CIN_TC_F16X1 ? 1 : 0, phase, st);
   if (precision == DTB_CIN_TC_BF16X3 || precision == DTB_CIN_TC_BF16X1 || precision == DTB_CIN_TC_F16X1) {
     set_error("dtb_cin_bwd: tensor-core path requested but shape unsupported (F=%d D=%d)", F, D);
     return DTB_ERR_UNSUPPORTED;

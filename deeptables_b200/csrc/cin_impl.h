@@ -25,6 +25,6 @@ int cin_tc_fwd(const CinShape& s, const int32_t* idx, const float* table, const 
 int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* d_pooled, const void* saved, float* grad_table,
                float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
-               int n_pass, int phase, cudaStream_t st);
+               int n_pass, int f16, int phase, cudaStream_t st);
 
 }  // namespace dtb

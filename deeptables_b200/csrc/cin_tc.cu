@@ -1508,7 +1508,7 @@ static bool cin_tc_bwd_supported(const CinShape& s) {
 int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const int64_t* row_offsets,
                const float* weights, const float* d_pooled, const void* saved, float* grad_table,
                float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int act,
-               int n_pass, int phase, cudaStream_t st) {
+               int n_pass, int f16, int phase, cudaStream_t st) {
   // phase 0: everything; 1: the embedding-gradient part (weight pack + dgrad); 2: the weight-gradient part
   // (wgrad + bias).  Lets the host start the data-parallel exchange of the table gradient under the wgrad.
   if (!cin_tc_bwd_supported(s) || g_tc_bwd_fp32) {
@@ -1534,8 +1534,11 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   // experiment builds 6 / 7 (single fp16 pass; profiling hook only): 64 statistics words at the end of the workspace:
   // [k] max|W_k|, [8 + k] max|dC_k|, [16] max|x0 tiles|, [24 + k] max|h_k tiles|  (bit patterns of non-negative floats)
   const int exp_build = g_tc_dbg >> 4;
-  const bool f16a = s.D == 16 && (exp_build == 6 || exp_build == 7);
-  const bool f16w = s.D == 16 && exp_build == 7 && d_bias == nullptr;
+  // fp16 single pass (DTB_CIN_TC_F16X1): the two-threads-per-row data-gradient kernel of cin_tc2.cu + fp16 dC tiles for
+  // cin_tc_wgrad_kernel<true>.  Decided below once the layer table is filled (cin_tc2_bwd_supported).
+  bool f16_v2 = false;
+  const bool f16a = !f16 && s.D == 16 && (exp_build == 6 || exp_build == 7);
+  bool f16w = !f16 && s.D == 16 && exp_build == 7 && d_bias == nullptr;
   int* stats = reinterpret_cast<int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 256);
   size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float) + (m_pad_rows(s, B) / 64) * s.F * kWgPad;   // as cin_tc_fwd
   int bstage = 0;
@@ -1550,7 +1553,7 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
     int blocks = (int)((total + 255) / 256);
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    if (phase != 2) {
+    if (phase != 2 && !f16) {
       if (f16a) {                                    // experiments 6 / 7: scaled fp16 weights; statistics words in the trailing slack
         int* wmax = stats + k;
         if (k == 0) DTB_CUDA_OK(cudaMemsetAsync(stats, 0, 256, st));
@@ -1569,11 +1572,34 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   }
   p.b_stage_bytes = bstage;
   p.wmax = stats;
-  if (s.D == 16 && exp_build == 7 && d_bias != nullptr) {
+  if (f16) {
+    f16_v2 = !g_tc_f16_v1 && cin_tc2_bwd_supported(p, s.D);
+    if (!f16_v2) {
+      set_error("dtb_cin_bwd: fp16 single pass: shape outside cin_tc2 (F=%d D=%d); use precision 0/2", s.F, s.D);
+      return DTB_ERR_UNSUPPORTED;
+    }
+    f16w = true;
+    if (phase != 2) {
+      DTB_CUDA_OK(cudaMemsetAsync(stats, 0, 256, st));
+      for (int k = 0; k < s.n_layers; ++k) {
+        const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
+        cin_tc_wmax_kernel<<<(int)((n_w + 255) / 256 < 64 ? (n_w + 255) / 256 : 64), 256, 0, st>>>(weights + s.w_off[k], n_w, stats + k);
+        DTB_LAUNCH_OK();
+        const int rc2 = cin_tc2_pack_pairs(weights + s.w_off[k], ws + p.wpack_off[k], s.F, s.H[k], p.Hp[k], s.L[k], stats + k, st);
+        if (rc2 != DTB_OK) return rc2;
+      }
+    }
+  }
+  if (!f16 && s.D == 16 && exp_build == 7 && d_bias != nullptr) {
     set_error("dtb_cin_bwd: experiment build 7 (fp16 tiles) has no bias-gradient kernel; use a CIN without bias");
     return DTB_ERR_UNSUPPORTED;
   }
-  if (f16w && phase != 2) {
+  if (f16_v2 && phase != 2) {
+    // operand maxima recorded by cin_tc2_fwd_kernel at the head of the saved buffer -> statistics words of the wgrad
+    const int* sv = reinterpret_cast<const int*>(saved);
+    DTB_CUDA_OK(cudaMemcpyAsync(stats + 16, sv, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    DTB_CUDA_OK(cudaMemcpyAsync(stats + 24, sv, sizeof(int) * s.n_layers, cudaMemcpyDeviceToDevice, st));
+  } else if (f16w && phase != 2) {
     // maxima of the operand tiles the forward saved (the wgrad scale G needs them); padded entries are zeros
     const size_t blocks64 = m_pad_rows(s, B) / 64;
     const float* sv = reinterpret_cast<const float*>(saved);
@@ -1593,7 +1619,9 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   }
   const TcBwdSmemLayout lay = tc_bwd_layout(bstage, s.F);
   int rc = DTB_OK;
-  if (phase != 2) switch (s.D) {
+  if (phase != 2 && f16_v2) {
+    rc = cin_tc2_launch_dgrad(p, s.D, st);
+  } else if (phase != 2) switch (s.D) {
     case 4: rc = launch_dgrad<4>(p, lay.total, st); break;
     case 8: rc = launch_dgrad<8>(p, lay.total, st); break;
     case 16: rc = launch_dgrad<16>(p, lay.total, st); break;
@@ -1638,7 +1666,10 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
       cin_tc_wgrad_kernel<false><<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
     }
     DTB_LAUNCH_OK();
-    if (d_bias) {
+    if (d_bias && f16w) {
+      const int rcb = cin_tc2_dbias(w.dc_tiles, d_bias + s.b_off[k], w.L, (int)(m_pad / 16), st);
+      if (rcb != DTB_OK) return rcb;
+    } else if (d_bias) {
       const int n_blocks16 = (int)(m_pad / 16);
       int blocks = (int)(((int64_t)n_blocks16 * w.L + 255) / 256);
       if (blocks > sm_count() * 8) blocks = sm_count() * 8;

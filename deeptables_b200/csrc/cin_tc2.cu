@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
       float xmax = 0.f;
       for (int i = 0; i < F; ++i) xmax = fmaxf(xmax, fabsf(x0g[((size_t)r * F + i) * D + d]));
       float hmax = xmax;                               // max|h_k row| over BOTH halves
+      if (p.saved && q == 0) {
+        // maxima of the operand tiles for the fp16 weight-gradient kernel (its one per-layer scale G): word 0 = max|x0|,
+        // word k = max|h_k|; they live at the head of the saved buffer, which the compact format leaves unused
+        float wm = xmax;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+        if (lane == 0 && wm > 0.f) atomicMax(reinterpret_cast<int*>(p.saved), __float_as_int(wm));
+      }
       if (p.saved) {
         // block-transposed copy for the wgrad kernel: [m / 64][field][68]; the two halves write alternate fields
         const size_t m_pad = (size_t)(st * 2 + g) * 128 + t;
@@ -266,6 +274,12 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
           mx[q * 128 + t] = own;
           asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
           hmax = fmaxf(mx[t], mx[128 + t]);
+          if (p.saved && q == 0) {
+            float wm = hmax;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+            if (lane == 0 && wm > 0.f) atomicMax(reinterpret_cast<int*>(p.saved) + k + 1, __float_as_int(wm));
+          }
         }
       }
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");   // x0 block free for the next super tile
@@ -337,6 +351,371 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
   }
 }
 
+// ==========================================================================================
+// Backward, data gradient (the counterpart of cin_tc_dgrad_kernel, cin_tc.cu), same two-threads-per-row organisation
+// ==========================================================================================
+// Per 2 x 128-row super tile, layers last -> first:
+//   dC_k = (d_pooled part + dh_{k+1}) * relu'(T_k), scaled per row into fp16 (exact power of two from the row's max, the
+//          two halves exchange their maxima) -> TMEM A operand (written ONCE per layer) + fp16 tiles in HBM for wgrad;
+//   per PAIR of x0 fields (i0, i1):  dZ[m, (il, j)] = sum_l dC[m, l] W[(i_il, j), l]   one N = 2*Hp (128) MMA chain, K = L
+//   read-out: dx0[m, i] += sum_j dZ h_k[m, j] ;  dh_k[m, j] += dZ x0[m, i]              each thread its half of j
+// What changed against the one-thread-per-row kernel, whose tensor pipe was 48 % busy: N = 128 MMAs instead of N = 64
+// (the A-from-TMEM form feeds the same operand bytes per MMA for half the tensor work at N = 64), one accumulator per
+// tile with the two tiles in ping-pong (tile 0's read-out runs under tile 1's MMAs), a read-out split between two
+// threads with 32 + 32 live values each (no spills), one tensor pass (fp16) instead of three.
+constexpr int kT2StagesW = 3;          // W pair images (2*Hp x L fp16 = 32 KB each)
+
+struct T2BwdSmem {
+  int b_off, x0_off, dx_off, mx_off, bar_off, total;
+};
+__host__ __device__ inline T2BwdSmem tc2_bwd_layout(int b_stage_bytes, int F) {
+  T2BwdSmem l;
+  l.b_off = 0;
+  l.x0_off = kT2StagesW * b_stage_bytes;
+  l.dx_off = l.x0_off + 2 * 128 * F * 4;           // x0s[tile][r][i][d]
+  l.mx_off = l.dx_off + 2 * 2 * 128 * F * 4;       // dxs[tile][half][i][t]
+  l.bar_off = l.mx_off + 2 * 2 * 2 * 128 * 4;      // row maxima [tile][parity][half][t]
+  l.bar_off = (l.bar_off + 15) / 16 * 16;
+  l.total = l.bar_off + 256;
+  return l;
+}
+
+// weights -> per field PAIR pi: ONE fp16 image of B[n = il*Hp + j][k = l] = W[((2 pi + il)*H + j), l] * s_W, canonical
+// K-major no swizzle (zero rows for j >= H and for the phantom field of an odd F)
+__global__ void cin_tc2_pack_pairs_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
+                                          int L, const int* __restrict__ wmax) {
+  float s, inv;
+  tc::pow2_scale_to_1024(__int_as_float(*wmax), s, inv);
+  const int N = 2 * Hp;
+  const int n_pairs = (F + 1) / 2;
+  const int64_t per_img = (int64_t)N * L;
+  const int64_t total = per_img * n_pairs;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int pi = (int)(t / per_img);
+    const int rem = (int)(t - (int64_t)pi * per_img);
+    const int n = rem / L, l = rem - n * L;          // l fastest: coalesced reads
+    const int il = n / Hp, j = n - il * Hp, i = 2 * pi + il;
+    const float v = (i < F && j < H) ? w[((int64_t)i * H + j) * L + l] * s : 0.f;
+    const int64_t off = ((int64_t)(l >> 3) * (N >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (l & 7) * 2;
+    *reinterpret_cast<__half*>(out + (int64_t)pi * per_img * 2 + off) = __float2half_rn(v);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
+  constexpr int R = 128 / D;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const T2BwdSmem lay = tc2_bwd_layout(p.b_stage_bytes, p.F);
+  uint8_t* smem_b = smem + lay.b_off;
+  float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
+  float* dxs = reinterpret_cast<float*>(smem + lay.dx_off);
+  float* mxs = reinterpret_cast<float*>(smem + lay.mx_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* a_ready = bars;          // [tile]   8 warps
+  uint64_t* full_b = bars + 2;       // [stage]  bulk copy (tx)
+  uint64_t* empty_b = bars + 5;      // [stage]  commit
+  uint64_t* acc_full = bars + 8;     // [tile]   commit
+  uint64_t* acc_empty = bars + 10;   // [tile]   8 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = p.F;
+  const int n_pairs = (F + 1) / 2;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&a_ready[g], 8);
+      tc::mbar_init(&acc_full[g], 1);
+      tc::mbar_init(&acc_empty[g], 8);
+    }
+    for (int s = 0; s < kT2StagesW; ++s) {
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty_b[s], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == 16) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 16) {
+    const int g = warp >> 3, q = (warp >> 2) & 1;
+    const int t = (warp & 3) * 32 + lane;
+    const int tt = q * 128 + t;
+    const int r = t / D, d = t % D;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_tile = tmem_base + lane_base + g * 256;   // A: columns [0, 64) ; accumulator: [64, 192)
+    float* x0g = x0s + (size_t)g * 128 * F;                     // [r][i][d]
+    float* dxg = dxs + ((size_t)g * 2 + q) * 128 * F;           // [i][t]  this half's partial dx0
+    float* dxo = dxs + ((size_t)g * 2 + (q ^ 1)) * 128 * F;     //         the other half's
+    float* mxg = mxs + (size_t)g * 2 * 2 * 128;                 // [parity][half][t]
+    uint32_t acc_cnt = 0, mx_cnt = 0;
+    float h[32], dh[32];
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      const int row0 = (st * 2 + g) * R;
+      const int b = row0 + r;
+      const bool valid = b < p.B;
+      const size_t m_pad = (size_t)(st * 2 + g) * 128 + t;      // == b*D + d
+      {
+        constexpr int Q = D / 4;
+        for (int e = tt; e < R * F * Q; e += 256) {
+          const int rr = e / (F * Q);
+          const int rem = e - rr * F * Q;
+          const int i = rem / Q, qq = rem - i * Q;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + rr < p.B) {
+            const int64_t rb = table_row(p.row_offsets, i, __ldg(p.idx + (int64_t)(row0 + rr) * F + i), D, nullptr);
+            if (rb >= 0) v = ldg_stream_f4(p.table + rb + (qq << 2));
+          }
+          *reinterpret_cast<float4*>(x0g + ((size_t)rr * F + i) * D + (qq << 2)) = v;
+        }
+        for (int i = 0; i < F; ++i) dxg[i * 128 + t] = 0.f;
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+#pragma unroll
+      for (int jj = 0; jj < 32; ++jj) dh[jj] = 0.f;
+      for (int k = p.n_layers - 1; k >= 0; --k) {
+        const int L = p.L[k], Hp = p.Hp[k];
+        const int nh = Hp >> 1;                                              // this thread's share of j: 16 or 32
+        const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
+        const int nhn = (k + 1 < p.n_layers) ? (p.Hp[k + 1] >> 1) : 0;      // the next layer's share (dh holds its gradient)
+        const int first_pb = (pool_lo >= hid_n) ? (pool_lo >> 4) : (hid_n >> 4);
+        const int last_pb = (pool_lo + pool_n) >> 4;
+        const int n_pb = last_pb > first_pb ? last_pb - first_pb : 0;
+        const int pb_split = (n_pb + 1) >> 1;
+        const uint16_t* mrow = (p.act == DTB_ACT_RELU && valid)
+                                   ? reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint32_t*>(p.saved + p.saved_off[k]) +
+                                                                       m_pad * ((L + 31) >> 5))
+                                   : nullptr;
+        const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
+        // ---- the 16-column blocks of dC_k this thread owns (same rule as the forward's read-out) ------------------
+        // sweep 0: row maximum of the own blocks ; sweep 1: scale, pack to fp16, TMEM operand + HBM tiles for wgrad
+        float trow = 1.f, inv_t = 1.f;
+        float dmax = 0.f;
+#pragma unroll
+        for (int sweep = 0; sweep < 2; ++sweep) {
+          if (sweep == 1) {
+            float* mx = mxg + (size_t)(mx_cnt & 1) * 2 * 128;
+            ++mx_cnt;
+            mx[q * 128 + t] = dmax;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+            dmax = fmaxf(mx[t], mx[128 + t]);
+            tc::pow2_scale_to_1024(dmax, trow, inv_t);
+            if (q == 0) {
+              // wgrad folds 1/t_m into its on-the-fly operand: one float per row in the unused "lo" slot of the row's
+              // 16-row tile block; the layer's max|dC| goes to the statistics words (slot 8 + k)
+              *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + 32 * L + (t & 15) * 4) = inv_t;
+              float wm = dmax;
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+              if (lane == 0 && wm > 0.f) atomicMax(const_cast<int*>(p.wmax) + 8 + k, __float_as_int(wm));
+            }
+          }
+#pragma unroll
+          for (int slot = 0; slot < 6; ++slot) {
+            int cb;
+            bool live;
+            if (slot < 2) {
+              cb = ((q * nhn) >> 4) + slot;
+              live = (slot * 16 < nhn) && (cb * 16 < hid_n);
+            } else {
+              const int s2 = slot - 2;
+              cb = first_pb + q * pb_split + s2;
+              live = s2 < (q == 0 ? pb_split : n_pb - pb_split);
+            }
+            if (live) {                               // warp-uniform
+              const uint32_t bits = mrow ? (uint32_t)__ldg(mrow + cb) : 0u;
+              float dc[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = cb * 16 + j;
+                float gsum = 0.f;
+                if (valid && col >= pool_lo && col < pool_lo + pool_n) gsum = __ldg(dprow + (col - pool_lo));
+                if (slot < 2) gsum += dh[(slot & 1) * 16 + j];
+                if (p.act == DTB_ACT_RELU && !((bits >> j) & 1u)) gsum = 0.f;
+                dc[j] = valid ? gsum : 0.f;
+              }
+              if (sweep == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) dmax = fmaxf(dmax, fabsf(dc[j]));
+              } else {
+                uint32_t zf[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) zf[c] = tc::pack_f16x2(dc[2 * c] * trow, dc[2 * c + 1] * trow);
+                tc::tmem_st8v(t_tile + cb * 8, zf[0], zf[1], zf[2], zf[3], zf[4], zf[5], zf[6], zf[7]);
+                uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
+                *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zf[0], zf[1], zf[2], zf[3]);
+                *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zf[4], zf[5], zf[6], zf[7]);
+                tc::tmem_wait_st();
+              }
+            }
+          }
+        }
+        tc::fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&a_ready[g]);
+        float sw, inv_w;
+        tc::pow2_scale_to_1024(__int_as_float(__ldg(p.wmax + k)), sw, inv_w);
+        const float inv_acc = inv_t * inv_w;
+        // ---- this thread's half of h_k, and a fresh dh accumulator ------------------------------------------------
+        if (k > 0) {
+          const int Hk = p.H[k];
+          const float* hbp = p.saved + p.hb_off[k - 1] + (m_pad >> 6) * (size_t)(Hk * kWgPad) + (m_pad & 63);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = q * nh + jj;
+            h[jj] = (valid && jj < nh && j < Hk) ? __ldg(hbp + (size_t)j * kWgPad) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = q * nh + jj;
+            h[jj] = (jj < nh && j < F) ? x0g[((size_t)r * F + j) * D + d] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) dh[jj] = 0.f;
+        for (int pi = 0; pi < n_pairs; ++pi) {
+          const uint32_t par = acc_cnt & 1;
+          ++acc_cnt;
+          tc::mbar_wait(&acc_full[g], par);
+          tc::fence_after_thread_sync();
+#pragma unroll
+          for (int il = 0; il < 2; ++il) {
+            const int i = 2 * pi + il;
+            if (i < F) {                                   // warp-uniform (the phantom field of an odd F is all zeros)
+              const float xi = x0g[((size_t)r * F + i) * D + d] * inv_acc;
+              float dx = 0.f;
+              // both 16-column loads of this thread's share in flight before the single wait
+              uint32_t v0[16], v1[16];
+              tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh, v0);
+              if (nh == 32) tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh + 16, v1);
+              tc::tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float dz = __uint_as_float(v0[j]);
+                dx = fmaf(dz, h[j], dx);
+                dh[j] = fmaf(dz, xi, dh[j]);
+              }
+              if (nh == 32) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float dz = __uint_as_float(v1[j]);
+                  dx = fmaf(dz, h[16 + j], dx);
+                  dh[16 + j] = fmaf(dz, xi, dh[16 + j]);
+                }
+              }
+              dxg[i * 128 + t] += dx * inv_acc;
+            }
+          }
+          tc::fence_before_thread_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&acc_empty[g]);
+        }
+        if (k == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int j = q * nh + jj;
+            if (jj < nh && j < F) dxg[j * 128 + t] += dh[jj];     // h_0 is x0 itself
+          }
+        }
+      }
+      // ---- scatter dx0 of this tile into the embedding gradient: both halves' partial sums, alternate fields ----------
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      if (valid) {
+        for (int i = q; i < F; i += 2) {
+          const int64_t rb = table_row(p.row_offsets, i, __ldg(p.idx + (int64_t)b * F + i), D, nullptr);
+          if (rb >= 0) atomicAdd(p.grad_table + rb + d, dxg[i * 128 + t] + dxo[i * 128 + t]);
+        }
+      }
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    }
+  } else if (warp == 16) {
+    const bool leader = elect_one_sync();
+    const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
+    uint32_t chunk = 0, cnt[2] = {0, 0}, layer_cnt = 0;
+    for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+      for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
+        const int Hp = p.Hp[k], L = p.L[k];
+        const uint32_t N = 2 * (uint32_t)Hp;
+        const uint32_t idesc = tc::make_idesc_f16(128, N);
+        const uint32_t lbo_b = (N >> 3) * 128;
+        const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
+        for (int pi = 0; pi < n_pairs; ++pi, ++chunk) {
+          const uint32_t sb = chunk % kT2StagesW, pb = (chunk / kT2StagesW) & 1;
+          tc::mbar_wait(&full_b[sb], pb);
+          const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (pi == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
+            const uint32_t c = cnt[g];
+            ++cnt[g];
+            tc::mbar_wait(&acc_empty[g], (c & 1) ^ 1);
+            tc::fence_after_thread_sync();
+            if (leader) {
+              const uint32_t a_base = tmem_base + g * 256;
+              const uint32_t d_tmem = a_base + 64;
+#pragma unroll
+              for (int ks = 0; ks < kMaxL / 16; ++ks) {
+                if (ks * 16 < L) {
+                  const uint64_t desc_b = desc_hi | (uint64_t)(((b_addr + ks * 2 * lbo_b) >> 4) & 0x3FFF);
+                  tc::mma_ts(d_tmem, a_base + ks * 8, desc_b, idesc, (uint32_t)(ks != 0));
+                }
+              }
+              tc::mma_commit(&acc_full[g]);
+            }
+            __syncwarp();
+          }
+          if (leader) tc::mma_commit(&empty_b[sb]);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      uint32_t chunk = 0;
+      for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
+        for (int k = p.n_layers - 1; k >= 0; --k) {
+          const uint32_t bytes = 2u * (uint32_t)p.Hp[k] * (uint32_t)p.L[k] * 2u;
+          const uint8_t* src = p.wpack + p.wpack_off[k];
+          for (int pi = 0; pi < n_pairs; ++pi, ++chunk) {
+            const uint32_t sb = chunk % kT2StagesW, pb = (chunk / kT2StagesW) & 1;
+            tc::mbar_wait(&empty_b[sb], pb ^ 1);
+            tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
+            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)pi * bytes, bytes, &full_b[sb]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 16) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// d_bias[l] += sum over rows of dC, from the fp16 tiles (row m scaled by t_m, 1/t_m stored behind the image)
+__global__ void cin_tc2_dbias_kernel(const uint8_t* __restrict__ dc_tiles, float* __restrict__ d_bias, int L, int n_blocks16) {
+  const int64_t total = (int64_t)n_blocks16 * L;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t blk = t / L;
+    const int l = (int)(t - blk * L);
+    const uint8_t* base = dc_tiles + blk * (int64_t)(64 * L);
+    const uint8_t* col = base + (l >> 3) * 256 + (l & 7) * 2;
+    const float* inv_t = reinterpret_cast<const float*>(base + 32 * L);
+    float s = 0.f;
+    for (int m = 0; m < 16; ++m)
+      s += __half2float(*reinterpret_cast<const __half*>(col + (m >> 3) * 128 + (m & 7) * 16)) * __ldg(inv_t + m);
+    if (s != 0.f) atomicAdd(d_bias + l, s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -369,11 +748,74 @@ static int tc2_launch(const CinTcParams& p_in, cudaStream_t st) {
   const T2Smem lay = tc2_layout(p.b_stage_bytes, p.F);
   auto kern = cin_tc2_fwd_kernel<D>;
   DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  if (p.saved) DTB_CUDA_OK(cudaMemsetAsync(p.saved, 0, 64, st));          // operand maxima words (see the kernel)
   const int R = 128 / D;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
   int grid = sm_count();
   if (grid > n_super) grid = n_super;
   kern<<<grid, kT2Threads, lay.total, st>>>(p);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+static int tc2_bwd_b_stage(const CinTcBwdParams& p) {
+  int b = 0;
+  for (int k = 0; k < p.n_layers; ++k) {
+    const int bytes = 2 * p.Hp[k] * p.L[k] * 2;
+    if (bytes > b) b = bytes;
+  }
+  return b;
+}
+
+bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D) {
+  if (D != 16 && D != 32) return false;
+  if (!p.compact) return false;
+  for (int k = 0; k < p.n_layers; ++k) {
+    if (p.Hp[k] != 32 && p.Hp[k] != 64) return false;
+    if (p.L[k] % 16 || p.L[k] > kMaxL) return false;
+    if (p.hid_n[k] % 16 || p.pool_lo[k] % 16 || p.pool_n[k] % 16) return false;
+    if (p.hid_n[k] > 0 && p.pool_lo[k] != 0 && p.pool_lo[k] != p.hid_n[k]) return false;
+  }
+  return tc2_bwd_layout(tc2_bwd_b_stage(p), p.F).total <= 227 * 1024;
+}
+
+// packs layer k's pair images at wpack + wpack_off[k] (scale word: wmax[k], already reduced)
+int cin_tc2_pack_pairs(const float* w_k, uint8_t* dst, int F, int H, int Hp, int L, const int* wmax_k, cudaStream_t st) {
+  const int64_t total = (int64_t)((F + 1) / 2) * 2 * Hp * L;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  cin_tc2_pack_pairs_kernel<<<blocks, 256, 0, st>>>(w_k, dst, F, H, Hp, L, wmax_k);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+template <int D>
+static int tc2_launch_dgrad(const CinTcBwdParams& p_in, cudaStream_t st) {
+  CinTcBwdParams p = p_in;
+  p.b_stage_bytes = tc2_bwd_b_stage(p);
+  const T2BwdSmem lay = tc2_bwd_layout(p.b_stage_bytes, p.F);
+  auto kern = cin_tc2_dgrad_kernel<D>;
+  DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
+  const int R = 128 / D;
+  const int n_super = (p.B + 2 * R - 1) / (2 * R);
+  int grid = sm_count();
+  if (grid > n_super) grid = n_super;
+  kern<<<grid, kT2Threads, lay.total, st>>>(p);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int cin_tc2_launch_dgrad(const CinTcBwdParams& p, int D, cudaStream_t st) {
+  if (D == 16) return tc2_launch_dgrad<16>(p, st);
+  if (D == 32) return tc2_launch_dgrad<32>(p, st);
+  set_error("cin_tc2: embedding dim %d unsupported", D);
+  return DTB_ERR_UNSUPPORTED;
+}
+
+int cin_tc2_dbias(const uint8_t* dc_tiles, float* d_bias, int L, int n_blocks16, cudaStream_t st) {
+  int blocks = (int)(((int64_t)n_blocks16 * L + 255) / 256);
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  cin_tc2_dbias_kernel<<<blocks, 256, 0, st>>>(dc_tiles, d_bias, L, n_blocks16);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

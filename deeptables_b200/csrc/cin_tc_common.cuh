@@ -79,5 +79,9 @@ struct CinTcBwdParams {
 // ---- cin_tc2.cu: single-pass fp16 kernels with two threads per GEMM row (see the file header) -------------------------
 bool cin_tc2_fwd_supported(const CinTcParams& p, int D);
 int cin_tc2_launch_fwd(const CinTcParams& p, int D, cudaStream_t st);
+bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D);
+int cin_tc2_pack_pairs(const float* w_k, uint8_t* dst, int F, int H, int Hp, int L, const int* wmax_k, cudaStream_t st);
+int cin_tc2_launch_dgrad(const CinTcBwdParams& p, int D, cudaStream_t st);
+int cin_tc2_dbias(const uint8_t* dc_tiles, float* d_bias, int L, int n_blocks16, cudaStream_t st);
 
 }  // namespace dtb

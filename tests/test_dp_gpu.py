@@ -1,5 +1,7 @@
-"""Data-parallel training on 2 GPUs (NCCL): replicas stay bit-identical, and two ranks fed the SAME
-shard reproduce the single-GPU run on that shard (mean of two identical gradients)."""
+"""Data-parallel training on 2 (and, when the box has them, 8) GPUs over NCCL: replicas stay bit-identical -- weights
+after 6 optimiser steps and, once averaged (DeepModel.sync_replica_buffers, MirroredStrategy's MEAN aggregation), the
+BatchNormalization moving statistics -- and ranks fed the SAME shard reproduce the single-GPU run on that shard (mean
+of identical gradients).  profiles/r2_dp_nccl_tests.log holds the round-2 run of this file on 2 and 8 B200s."""
 import os
 import socket
 
@@ -54,24 +56,26 @@ def _worker(rank, world, port, out_dir, same_shard, table_mode=None):
         for step in range(6):
             idx, cont, y = _batch(step if same_shard else step * world + rank)
             m.train_on_batch(idx, cont, y)
+        m.sync_replica_buffers()                      # BN moving statistics: mean over the replicas (fit() does it per epoch)
         sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}      # state_dict() flushes the lazy state
         np.savez(os.path.join(out_dir, f'rank{rank}_{int(same_shard)}.npz'), **sd)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+@pytest.mark.parametrize('world', [2, 8])
 @pytest.mark.parametrize('table_mode', [None, 'lazy'])
 @pytest.mark.parametrize('same_shard', [True, False])
-def test_two_rank_training(tmp_path, same_shard, table_mode):
+def test_replicas_stay_bit_identical(tmp_path, same_shard, table_mode, world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f'needs {world} GPUs')
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), same_shard, table_mode), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), same_shard, table_mode), nprocs=world, join=True)
     r0 = np.load(tmp_path / f'rank0_{int(same_shard)}.npz')
-    r1 = np.load(tmp_path / f'rank1_{int(same_shard)}.npz')
-    for k in r0.files:
-        if 'moving_' in k and not same_shard:
-            continue          # BatchNorm statistics are per replica (MirroredStrategy semantics)
-        assert np.array_equal(r0[k], r1[k]), f'replicas diverged on {k}'
+    for rank in range(1, world):
+        r1 = np.load(tmp_path / f'rank{rank}_{int(same_shard)}.npz')
+        for k in r0.files:
+            assert np.array_equal(r0[k], r1[k]), f'replica {rank} diverged from replica 0 on {k}'
     if same_shard:
         single = _build()
         for step in range(6):
@@ -79,3 +83,5 @@ def test_two_rank_training(tmp_path, same_shard, table_mode):
         sd = single.state_dict()
         for k in r0.files:
             np.testing.assert_allclose(r0[k], sd[k].cpu().numpy(), rtol=1e-4, atol=1e-6, err_msg=k)
+    print(f'world {world} same_shard {same_shard} table_mode {table_mode}: {len(r0.files)} tensors bit-identical on '
+          f'{world} replicas')

@@ -160,7 +160,8 @@ def test_cin_fp16_single_pass_forward_is_inside_the_parity_bar(f, sizes, direct,
     big = np.abs(want) > 1e-2 * scale
     print(f'fp16x1 {kernel} F={f} sizes={sizes}: max err / scale {err.max() / scale:.2e}, '
           f'max rel err on entries > 1% of scale {(err[big] / np.abs(want[big])).max():.2e}')
-    np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-4 * scale + 1e-5 * scale * (~big))
+    bad = err > 1e-3 * np.abs(want) + 1e-4 * scale + 4e-4 * scale * (~big)
+    assert not bad.any(), f'{int(bad.sum())} entries outside the bar, worst {err[bad].max() / scale:.2e} of the scale'
     gt = torch.zeros(table.shape, device='cuda')
     dw = torch.zeros_like(d_w)
     db = torch.zeros(sum(sizes), device='cuda') if use_bias else None
