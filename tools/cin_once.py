@@ -59,6 +59,22 @@ if os.environ.get('CHECKF'):
                                   sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd ref')
     torch.cuda.synchronize()
     print(f'forward precision {prec} vs bf16x3: max err / scale {float((ref - pooled).abs().max() / ref.abs().max()):.2e}', flush=True)
+if os.environ.get('CHECKB') and prec:
+    # gradients of this precision's backward against the bf16x3 kernels (each on its own forward)
+    res = []
+    for pr in (0, prec):
+        grad.zero_()
+        dw.zero_()
+        nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
+                                      sizes_c, 3, 0, 1, pr, None, None), 'cin_fwd')
+        for phase in (1, 2):
+            nat.check(nat.lib.dtb_cin_bwd_phase(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None,
+                                                P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, pr, phase, None), 'cin_bwd_phase')
+        torch.cuda.synchronize()
+        res.append((grad.clone(), dw.clone()))
+    eg = float((res[0][0] - res[1][0]).abs().max() / res[0][0].abs().max())
+    ew = float((res[0][1] - res[1][1]).abs().max() / res[0][1].abs().max())
+    print(f'backward precision {prec} vs bf16x3: embedding grad rel err {eg:.2e}, filter grad rel err {ew:.2e}', flush=True)
 if os.environ.get('CHECK') and exp:
     # gradients of the experiment build against the product kernel on the same saved activations
     res = []
