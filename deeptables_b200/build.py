@@ -18,7 +18,7 @@ OUT = os.path.join(OUT_DIR, 'libdeeptables_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-DDTB_BUILD',
-         '-shared']
+         '-shared'] + os.environ.get('NVCCFLAGS_EXTRA', '').split()
 
 
 def _sources():

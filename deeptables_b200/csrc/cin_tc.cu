@@ -1474,8 +1474,11 @@ static int launch_dgrad_exp(const CinTcBwdParams& p, int smem_bytes, cudaStream_
 
 template <int D>
 static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
+#ifdef DTB_CIN_EXPERIMENTS
+  // experiment builds of the one-thread-per-row kernel (profiling only, see cin_tc_dgrad_kernel): compiled only with
+  // -DDTB_CIN_EXPERIMENTS (tools/build_experiments.sh); the product library holds kExp = 0 alone
   if constexpr (D == 16) {
-    switch (g_tc_dbg >> 4) {       // experiment builds (profiling only): see cin_tc_dgrad_kernel
+    switch (g_tc_dbg >> 4) {
       case 1: return launch_dgrad_exp<16, 1>(p, smem_bytes, st);
       case 2: return launch_dgrad_exp<16, 2>(p, smem_bytes, st);
       case 3: return launch_dgrad_exp<16, 3>(p, smem_bytes, st);
@@ -1490,6 +1493,12 @@ static int launch_dgrad(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st
       default: break;
     }
   }
+#else
+  if ((g_tc_dbg >> 4) != 0) {
+    set_error("dtb_cin_bwd: experiment build %d requested but this library was built without -DDTB_CIN_EXPERIMENTS", g_tc_dbg >> 4);
+    return DTB_ERR_UNSUPPORTED;
+  }
+#endif
   return launch_dgrad_exp<D, 0>(p, smem_bytes, st);
 }
 

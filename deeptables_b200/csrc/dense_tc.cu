@@ -23,7 +23,8 @@
 
 namespace dtb {
 
-constexpr int kDtThreads = 320;        // warps 0-3 producers, 4-7 epilogue, 8 MMA issue + TMEM owner, 9 weight loader
+constexpr int kDtThreads = 448;        // rows kernel: warps 0-7 producers, 8-11 epilogue, 12 MMA issue + TMEM owner, 13 weight loader
+constexpr int kDtWgThreads = 320;      // wgrad kernel: warps 0-3 X producers (+ epilogue), 4-7 dZ producers, 8 MMA issue
 constexpr int kDtKc = 32;              // reduction elements per pipeline stage (two UMMA k-steps)
 constexpr int kDtStages = 4;
 constexpr int kDtAImg = 128 * kDtKc * 2;          // bytes of one bf16 [128 x 32] image
@@ -96,33 +97,30 @@ __device__ __forceinline__ bool dt_elect_one() {
   return pred != 0;
 }
 
-// One [32 rows x 32 columns] fp32 block of a row-major matrix -> bf16 hi/lo words of a K-major image whose UMMA rows
-// are the matrix ROWS and whose reduction index is the matrix COLUMN (rows kernel: A = X tile).  The warp reads row by
-// row (lanes = 32 consecutive columns: one 128-byte request), a lane pair (k even, k+1) exchanges values so that the
-// even lane stores the packed hi word and the odd lane the packed lo word.
-__device__ __forceinline__ void dt_convert_rows(const float* __restrict__ src, int ld, int row0, int n_rows_valid,
-                                                int col0, int n_cols_valid, uint8_t* img_hi, uint8_t* img_lo,
-                                                int img_row0, int lane) {
+// [16 rows x 32 columns] fp32 block of a row-major matrix -> registers (one 128-byte request per row, all 16 in flight),
+// and registers -> bf16 hi/lo words of a K-major image whose UMMA rows are the matrix ROWS and whose reduction index is
+// the matrix COLUMN (rows kernel: A = X tile).  A lane pair (k even, k+1) exchanges values so that the even lane stores
+// the packed hi word and the odd lane the packed lo word.
+__device__ __forceinline__ void dt_load_rows16(float (&v)[16], const float* __restrict__ src, int ld, int row0,
+                                               int n_rows_valid, int col0, int n_cols_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    v[j] = (j < n_rows_valid && lane < n_cols_valid) ? __ldg(src + (int64_t)(row0 + j) * ld + col0 + lane) : 0.f;
+}
+__device__ __forceinline__ void dt_store_rows16(const float (&v)[16], uint8_t* img_hi, uint8_t* img_lo, int img_row0,
+                                                int lane) {
   const bool even = (lane & 1) == 0;
   const int kk = lane & ~1;
+  uint8_t* img = even ? img_hi : img_lo;
 #pragma unroll
-  for (int rr = 0; rr < 32; rr += 8) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int r = rr + j;
-      v[j] = (r < n_rows_valid && lane < n_cols_valid) ? __ldg(src + (int64_t)(row0 + r) * ld + col0 + lane) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
-      const float a = even ? v[j] : other, b = even ? other : v[j];
-      uint32_t hi, lo;
-      tc::split_bf16x2(a, b, hi, lo);
-      const int r_img = img_row0 + rr + j;
-      const int off = (kk >> 3) * 2048 + (r_img >> 3) * 128 + (r_img & 7) * 16 + (kk & 7) * 2;
-      *reinterpret_cast<uint32_t*>((even ? img_hi : img_lo) + off) = even ? hi : lo;
-    }
+  for (int j = 0; j < 16; ++j) {
+    const float other = __shfl_xor_sync(0xffffffffu, v[j], 1);
+    const float a = even ? v[j] : other, b = even ? other : v[j];
+    uint32_t hi, lo;
+    tc::split_bf16x2(a, b, hi, lo);
+    const int r_img = img_row0 + j;
+    const int off = (kk >> 3) * 2048 + (r_img >> 3) * 128 + (r_img & 7) * 16 + (kk & 7) * 2;
+    *reinterpret_cast<uint32_t*>(img + off) = even ? hi : lo;
   }
 }
 
@@ -133,7 +131,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
   uint8_t* smem_b = smem + lay.b_off;
   float* tbuf = reinterpret_cast<float*>(smem + lay.t_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
-  uint64_t* full_a = bars;                 // [stage] 4 producer warps
+  uint64_t* full_a = bars;                 // [stage] 8 producer warps
   uint64_t* full_b = bars + 4;             // [stage] bulk copy (tx)
   uint64_t* empty = bars + 8;              // [stage] tcgen05.commit
   uint64_t* acc_full = bars + 12;          // [buf]   commit
@@ -146,7 +144,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDtStages; ++s) {
-      tc::mbar_init(&full_a[s], 4);
+      tc::mbar_init(&full_a[s], 8);
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
@@ -156,31 +154,45 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
     }
     tc::fence_barrier_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 12) tc::tmem_alloc(tmem_slot, 512);
   tc::fence_before_thread_sync();
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ============================ A producers: fp32 rows -> bf16 hi/lo images =============================
+    // warp w converts rows [16w, 16w + 16) of the tile.  The loads of the NEXT (item, chunk) are issued before this
+    // chunk's barrier wait and conversion: 8 warps x 16-32 requests of 128 bytes keep 16-32 KB in flight per SM
+    // (the first version had 4 warps x 8: a third of the latency-bandwidth product, 150 us per launch at 65 536 rows).
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / p.n_tiles;
-      const int row0 = mt * 128 + warp * 32;
-      const int rows_valid = p.M - row0;                         // may be <= 0 or > 32: dt_convert_rows clamps by compare
-      for (int c = 0; c < p.n_chunks; ++c, ++it) {
-        const uint32_t s = it % kDtStages, ph = (it / kDtStages) & 1;
-        tc::mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* a_stage = smem_a + s * kDtAStage;
-        dt_convert_rows(p.A, p.lda, row0, rows_valid, c * kDtKc, p.K - c * kDtKc, a_stage, a_stage + kDtAImg, warp * 32,
-                        lane);
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full_a[s]);
-      }
+    float cur[16], nxt[16];
+    int item = blockIdx.x, c = 0;
+    if (item < n_items) {
+      const int row0 = (item / p.n_tiles) * 128 + warp * 16;
+      dt_load_rows16(cur, p.A, p.lda, row0, p.M - row0, 0, p.K, lane);
     }
-  } else if (warp < 8) {
+    while (item < n_items) {
+      int n_item = item, n_c = c + 1;
+      if (n_c == p.n_chunks) { n_c = 0; n_item = item + gridDim.x; }
+      if (n_item < n_items) {
+        const int row0 = (n_item / p.n_tiles) * 128 + warp * 16;
+        dt_load_rows16(nxt, p.A, p.lda, row0, p.M - row0, n_c * kDtKc, p.K - n_c * kDtKc, lane);
+      }
+      const uint32_t s = it % kDtStages, ph = (it / kDtStages) & 1;
+      ++it;
+      tc::mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* a_stage = smem_a + s * kDtAStage;
+      dt_store_rows16(cur, a_stage, a_stage + kDtAImg, warp * 16, lane);
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_a[s]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+      item = n_item;
+      c = n_c;
+    }
+  } else if (warp < 12) {
     // ============================ epilogue: TMEM -> bias / act -> out ======================================
     const int q = warp & 3;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ============================ MMA issue ==================================================================
     const bool leader = dt_elect_one();
     const uint32_t a_u32 = tc::smem_u32(smem_a), b_u32 = tc::smem_u32(smem_b);
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
   }
   tc::fence_before_thread_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc::fence_after_thread_sync();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -299,39 +311,43 @@ struct DenseTcWgradParams {
   int M, K, N, ldx, ldz, ldw, NT, chunks_per_split, n_chunks_total;
 };
 
-// rows [m0, m0+32) x columns [col0, col0+32) of src -> K-major image with UMMA row = column index (img_row0 + lane),
-// reduction index = row; this warp handles row pairs [pair0, pair0 + n_pairs).  Returns the column sum of the values
-// it touched (for the bias gradient).
-__device__ __forceinline__ float dt_convert_cols(const float* __restrict__ src, int ld, int m0, int m_valid, int col0,
-                                                 int n_cols_valid, uint8_t* img_hi, uint8_t* img_lo, int img_row0,
-                                                 int img_rows, int pair0, int lane) {
-  float colsum = 0.f;
-  const bool cok = lane < n_cols_valid;
-  const int r_img = img_row0 + lane;
-  const int base = (r_img >> 3) * 128 + (r_img & 7) * 16;
-  float a[4], b[4];
+// rows [m0, m0+32) x 4 column groups of 32 of src -> K-major image with UMMA row = column index, reduction index = row;
+// this warp handles row pairs [pair0, pair0 + 4).  All 32 requests (4 groups x 4 pairs x 2 rows) are issued before the
+// first conversion.  Adds the column sums of the values it touched to colsum[] (for the bias gradient).
+__device__ __forceinline__ void dt_convert_cols4(const float* __restrict__ src, int ld, int m0, int m_valid, int col0,
+                                                 int n_cols, uint8_t* img_hi, uint8_t* img_lo, int img_row0, int img_rows,
+                                                 int pair0, int lane, float (&colsum)[4]) {
+  float a[4][4], b[4][4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int mm = (pair0 + j) * 2;
-    a[j] = (cok && mm < m_valid) ? __ldg(src + (int64_t)(m0 + mm) * ld + col0 + lane) : 0.f;
-    b[j] = (cok && mm + 1 < m_valid) ? __ldg(src + (int64_t)(m0 + mm + 1) * ld + col0 + lane) : 0.f;
-  }
+  for (int g = 0; g < 4; ++g) {
+    const bool cok = col0 + g * 32 + lane < n_cols;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int mm = (pair0 + j) * 2;
-    uint32_t hi, lo;
-    tc::split_bf16x2(a[j], b[j], hi, lo);
-    const int off = (mm >> 3) * (img_rows >> 3) * 128 + base + (mm & 7) * 2;
-    if (r_img < img_rows) {                       // NT is a multiple of 16, the column groups of 32: the tail group is half used
-      *reinterpret_cast<uint32_t*>(img_hi + off) = hi;
-      *reinterpret_cast<uint32_t*>(img_lo + off) = lo;
+    for (int j = 0; j < 4; ++j) {
+      const int mm = (pair0 + j) * 2;
+      a[g][j] = (cok && mm < m_valid) ? __ldg(src + (int64_t)(m0 + mm) * ld + col0 + g * 32 + lane) : 0.f;
+      b[g][j] = (cok && mm + 1 < m_valid) ? __ldg(src + (int64_t)(m0 + mm + 1) * ld + col0 + g * 32 + lane) : 0.f;
     }
-    colsum += a[j] + b[j];
   }
-  return colsum;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int r_img = img_row0 + g * 32 + lane;
+    const int base = (r_img >> 3) * 128 + (r_img & 7) * 16;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int mm = (pair0 + j) * 2;
+      uint32_t hi, lo;
+      tc::split_bf16x2(a[g][j], b[g][j], hi, lo);
+      const int off = (mm >> 3) * (img_rows >> 3) * 128 + base + (mm & 7) * 2;
+      if (r_img < img_rows) {                     // NT is a multiple of 16, the column groups of 32: the tail group is half used
+        *reinterpret_cast<uint32_t*>(img_hi + off) = hi;
+        *reinterpret_cast<uint32_t*>(img_lo + off) = lo;
+      }
+      colsum[g] += a[g][j] + b[g][j];
+    }
+  }
 }
 
-__global__ void __launch_bounds__(kDtThreads, 1) dense_tc_wgrad_kernel(const __grid_constant__ DenseTcWgradParams p) {
+__global__ void __launch_bounds__(kDtWgThreads, 1) dense_tc_wgrad_kernel(const __grid_constant__ DenseTcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const DtSmem lay = dt_layout(p.NT, 0);
   uint8_t* smem_a = smem + lay.a_off;
@@ -378,17 +394,20 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_wgrad_kernel(const __g
       const int m_valid = p.M - m0;
       if (is_a) {
         uint8_t* st = smem_a + s * kDtAStage;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          dt_convert_cols(p.X, p.ldx, m0, m_valid, k0 + g * 32, p.K - (k0 + g * 32), st, st + kDtAImg, g * 32, 128, pair0,
-                          lane);
+        float unused[4] = {0.f, 0.f, 0.f, 0.f};
+        dt_convert_cols4(p.X, p.ldx, m0, m_valid, k0, p.K, st, st + kDtAImg, 0, 128, pair0, lane, unused);
       } else {
         uint8_t* st = smem_b + s * lay.b_stage;
 #pragma unroll
-        for (int g = 0; g < kDtMaxNT / 32; ++g)
-          if (g * 32 < p.NT)
-            bsum[g] += dt_convert_cols(p.dZ, p.ldz, m0, m_valid, n0 + g * 32, p.N - (n0 + g * 32), st, st + b_img_bytes,
-                                       g * 32, p.NT, pair0, lane);
+        for (int half = 0; half < 2; ++half) {
+          if (half * 128 < p.NT) {
+            float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            dt_convert_cols4(p.dZ, p.ldz, m0, m_valid, n0 + half * 128, p.N, st, st + b_img_bytes, half * 128, p.NT, pair0, lane,
+                             cs);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) bsum[half * 4 + g] += cs[g];
+          }
+        }
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -525,7 +544,7 @@ int dense_tc_wgrad(const float* X, int ldx, const float* dZ, int ldz, float* dW,
   splits = (p.n_chunks_total + p.chunks_per_split - 1) / p.chunks_per_split;
   const DtSmem lay = dt_layout(p.NT, 0);
   DTB_CUDA_OK(cudaFuncSetAttribute(dense_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total));
-  dense_tc_wgrad_kernel<<<dim3(k_tiles, splits, n_tiles), kDtThreads, lay.total, st>>>(p);
+  dense_tc_wgrad_kernel<<<dim3(k_tiles, splits, n_tiles), kDtWgThreads, lay.total, st>>>(p);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -162,19 +162,18 @@ def test_cin_fp16_single_pass_forward_is_inside_the_parity_bar(f, sizes, direct,
           f'max rel err on entries > 1% of scale {(err[big] / np.abs(want[big])).max():.2e}')
     bad = err > 1e-3 * np.abs(want) + 1e-4 * scale + 4e-4 * scale * (~big)
     assert not bad.any(), f'{int(bad.sum())} entries outside the bar, worst {err[bad].max() / scale:.2e} of the scale'
-    # backward: the fp16 single-pass kernels (cin_tc2 dgrad + fp16 wgrad; 'v1': bf16x3 backward on the activations the fp16
-    # forward saved) against the bf16x3 kernels run on their own forward -- same inputs, same upstream gradient
+    # backward: the fp16 single-pass kernels (cin_tc2 dgrad + fp16 wgrad) against the bf16x3 kernels ON THE SAME saved
+    # activations (the fp16 forward's: a different forward flips relu-mask bits of near-zero outputs, which moves single
+    # gradient rows by percents and says nothing about the backward arithmetic)
     d_dp = torch.randn(b, pw, device='cuda', generator=torch.Generator(device='cuda').manual_seed(5))
+    flags = (1 << 18) if kernel == 'v1' else 0
 
-    def backward(prec_f, prec_b, flags):
+    def backward(prec_b):
         nat.lib.dtb_cin_tc_set_variant(1 | flags)
         try:
             gt = torch.zeros(table.shape, device='cuda')
             dw = torch.zeros_like(d_w)
             db = torch.zeros(sum(sizes), device='cuda') if use_bias else None
-            out = torch.empty(b, pw, device='cuda')
-            nat.check(nat.lib.dtb_cin_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_b), P(out), P(saved), P(ws), ws_bytes,
-                                          b, f, d, sizes_c, n, int(direct), act, prec_f, None, None), 'cin_fwd')
             nat.check(nat.lib.dtb_cin_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_w), P(d_dp), P(saved), P(gt), P(dw), P(db), P(ws),
                                           ws_bytes, b, f, d, sizes_c, n, int(direct), act, prec_b, None), 'cin_bwd')
             torch.cuda.synchronize()
@@ -182,12 +181,14 @@ def test_cin_fp16_single_pass_forward_is_inside_the_parity_bar(f, sizes, direct,
         finally:
             nat.lib.dtb_cin_tc_set_variant(1)
 
-    ref = backward(0, 0, 0)
-    got_g = backward(4, 4, 0) if kernel == 'v2' else backward(4, 0, 1 << 18)
-    for name, r_, g_ in zip(('embedding', 'filter', 'bias'), ref, got_g):
-        if r_ is None:
-            continue
-        assert bool(torch.isfinite(g_).all())
-        rel = float((r_ - g_).abs().max() / r_.abs().max())
-        print(f'fp16x1 {kernel} backward, {name} gradient: max err / max {rel:.2e}')
-        assert rel < 2e-3, f'{name} gradient off by {rel:.2e} of its maximum'
+    ref = backward(0)
+    assert all(bool(torch.isfinite(t_).all()) for t_ in ref if t_ is not None) and float(ref[1].abs().max()) > 0
+    if kernel == 'v2':
+        got_g = backward(4)
+        for name, r_, g_ in zip(('embedding', 'filter', 'bias'), ref, got_g):
+            if r_ is None:
+                continue
+            assert bool(torch.isfinite(g_).all())
+            rel = float((r_ - g_).abs().max() / r_.abs().max())
+            print(f'fp16x1 backward, {name} gradient vs bf16x3 on the same activations: max err / max {rel:.2e}')
+            assert rel < 2e-3, f'{name} gradient off by {rel:.2e} of its maximum'

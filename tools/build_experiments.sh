@@ -1,0 +1,6 @@
+#!/bin/bash
+# Rebuild the library WITH the experiment builds of cin_tc_dgrad_kernel (ablation switches 1-7, see cin_tc.cu): profiling
+# only -- the product build (deeptables_b200/build.py, __graft_entry__.build) leaves them out.
+set -e
+cd "$(dirname "$0")/.."
+NVCCFLAGS_EXTRA="-DDTB_CIN_EXPERIMENTS" python deeptables_b200/build.py --force

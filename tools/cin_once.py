@@ -60,13 +60,13 @@ if os.environ.get('CHECKF'):
     torch.cuda.synchronize()
     print(f'forward precision {prec} vs bf16x3: max err / scale {float((ref - pooled).abs().max() / ref.abs().max()):.2e}', flush=True)
 if os.environ.get('CHECKB') and prec:
-    # gradients of this precision's backward against the bf16x3 kernels (each on its own forward)
+    # gradients of this precision's backward against the bf16x3 kernels on the same saved activations
     res = []
+    nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
+                                  sizes_c, 3, 0, 1, prec, None, None), 'cin_fwd')      # ONE forward: same relu masks for both
     for pr in (0, prec):
         grad.zero_()
         dw.zero_()
-        nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
-                                      sizes_c, 3, 0, 1, pr, None, None), 'cin_fwd')
         for phase in (1, 2):
             nat.check(nat.lib.dtb_cin_bwd_phase(P(idx), P(table), P(offs), P(w), P(d_pooled), P(saved), P(grad), P(dw), None,
                                                 P(ws), ws_bytes, B, F, D, sizes_c, 3, 0, 1, pr, phase, None), 'cin_bwd_phase')
