@@ -1457,7 +1457,12 @@ static size_t dc_bytes(const CinShape& s, int B, size_t* off /* per layer */) {
   return total;
 }
 
-size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B) { return wpack_bytes(s) + 1024 + dc_bytes(s, B, nullptr) + 1024; }
+// [packed weights | dC tiles | 1024 B slack whose last 256 B are the statistics words | cin_tc2: max|d_pooled| per
+// (batch row, layer) + 64 B of shape tables]
+static size_t bwd_stats_end(const CinShape& s, int B) { return wpack_bytes(s) + 1024 + dc_bytes(s, B, nullptr) + 1024; }
+size_t cin_tc_bwd_workspace_bytes(const CinShape& s, int B) {
+  return bwd_stats_end(s, B) + (size_t)B * kCinMaxLayers * sizeof(float) + 256;
+}
 
 template <int D, int kExp>
 static int launch_dgrad_exp(const CinTcBwdParams& p, int smem_bytes, cudaStream_t st) {
@@ -1548,7 +1553,8 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
   bool f16_v2 = false;
   const bool f16a = !f16 && s.D == 16 && (exp_build == 6 || exp_build == 7);
   bool f16w = !f16 && s.D == 16 && exp_build == 7 && d_bias == nullptr;
-  int* stats = reinterpret_cast<int*>(ws + cin_tc_bwd_workspace_bytes(s, B) - 256);
+  int* stats = reinterpret_cast<int*>(ws + bwd_stats_end(s, B) - 256);
+  float* dpmax = reinterpret_cast<float*>(ws + bwd_stats_end(s, B));
   size_t hoff = cin_fp32_saved_bytes(s, B) / sizeof(float) + (m_pad_rows(s, B) / 64) * s.F * kWgPad;   // as cin_tc_fwd
   int bstage = 0;
   for (int k = 0; k < s.n_layers; ++k) {
@@ -1588,7 +1594,10 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
       return DTB_ERR_UNSUPPORTED;
     }
     f16w = true;
+    p.dpmax = dpmax;
     if (phase != 2) {
+      const int rcd = cin_tc2_dpmax(d_pooled, dpmax, s.pcol0, s.pool_n, B, s.P, s.n_layers, st);
+      if (rcd != DTB_OK) return rcd;
       DTB_CUDA_OK(cudaMemsetAsync(stats, 0, 256, st));
       for (int k = 0; k < s.n_layers; ++k) {
         const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
@@ -1665,7 +1674,10 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
     w.stages_per_split = (w.n_stage_total + splits - 1) / splits;
     splits = (w.n_stage_total + w.stages_per_split - 1) / w.stages_per_split;
     const WgSmemLayout wl = wg_layout(w.L, w.Hp, w.F);
-    if (f16w) {
+    if (f16_v2) {
+      const int rcw = cin_tc2_launch_wgrad(w.xb, w.hb, w.dc_tiles, w.d_w, w.F, w.H, w.Hp, w.L, w.n_stage_total, stats, k, st);
+      if (rcw != DTB_OK) return rcw;
+    } else if (f16w) {
       w.stats = stats;
       w.layer = k;
       DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
@@ -1674,7 +1686,7 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
       DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
       cin_tc_wgrad_kernel<false><<<dim3(n_pairs, splits), kWgThreads, wl.total, st>>>(w);
     }
-    DTB_LAUNCH_OK();
+    if (!f16_v2) DTB_LAUNCH_OK();
     if (d_bias && f16w) {
       const int rcb = cin_tc2_dbias(w.dc_tiles, d_bias + s.b_off[k], w.L, (int)(m_pad / 16), st);
       if (rcb != DTB_OK) return rcb;

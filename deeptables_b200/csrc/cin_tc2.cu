@@ -24,7 +24,7 @@
 
 namespace dtb {
 
-constexpr int kT2Threads = 576;        // warps 0-15 producer + epilogue, 16 MMA issue + TMEM owner, 17 weight loader
+constexpr int kT2Threads = 608;        // warps 0-15 producer + epilogue, 16 / 17 MMA issue for tile 0 / 1 (16 owns TMEM), 18 weight loader
 constexpr int kT2StagesA = 4;
 constexpr int kT2StagesB = 6;
 constexpr int kT2ACols = 32;           // TMEM columns of one (stage, tile) operand block: fp16 [128 x 64]
@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
   if (threadIdx.x == 0) {
     for (int s = 0; s < kT2StagesA; ++s) {
       tc::mbar_init(&full_a[s], 16);
-      tc::mbar_init(&empty_a[s], 1);
+      tc::mbar_init(&empty_a[s], 2);          // one tcgen05.commit per issuing warp
     }
     for (int s = 0; s < kT2StagesB; ++s) {
       tc::mbar_init(&full_b[s], 1);
-      tc::mbar_init(&empty_b[s], 1);
+      tc::mbar_init(&empty_b[s], 2);
     }
-    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_full, 2);
     tc::fence_barrier_init();
   }
   if (warp == 16) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -284,36 +284,37 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
       }
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");   // x0 block free for the next super tile
     }
-  } else if (warp == 16) {
-    // ================================ MMA issuer ===============================================
+  } else if (warp < 18) {
+    // ================================ MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1 =====================
+    // One issuing thread could not keep the tensor pipe fed once the work per granule fell to 8 x 64 cycles: its loop
+    // (two barrier waits, ~10 uniform-datapath instructions per UTCHMMA, commits) measured ~720 cycles per granule
+    // (ncu source view, profiles/r2_cin_tc2_ncu.txt).  Two warps on different SM sub-partitions each issue one tile.
+    const int g = warp - 16;
     const bool leader = elect_one_sync();
     const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
+    const uint32_t d_tmem = tmem_base + g * kAccCols;
     uint32_t gran = 0, chunk = 0;
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
         const uint32_t idesc = tc::make_idesc_f16(128, (uint32_t)L);
         const uint32_t lbo_b = (uint32_t)(L >> 3) * 128;       // K-direction core stride of the W image
+        const uint32_t kstep = (2 * lbo_b) >> 4;               // descriptor address units per UMMA k-step
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
         for (int i = 0; i < F; ++i, ++chunk, ++gran) {
           const uint32_t sb = chunk % kT2StagesB, pb = (chunk / kT2StagesB) & 1;
           const uint32_t sa = gran % kT2StagesA, pa = (gran / kT2StagesA) & 1;
+          const uint32_t a_base = tmem_base + 2 * kAccCols + (sa * 2 + g) * kT2ACols;
+          const uint64_t desc0 = desc_hi | (uint64_t)(((smem_b_u32 + sb * (uint32_t)p.b_stage_bytes) >> 4) & 0x3FFF);
           tc::mbar_wait(&full_b[sb], pb);
           tc::mbar_wait(&full_a[sa], pa);
           tc::fence_after_thread_sync();
           if (leader) {
-            const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              const uint32_t d_tmem = tmem_base + g * kAccCols;
-              const uint32_t a_base = tmem_base + 2 * kAccCols + (sa * 2 + g) * kT2ACols;
-#pragma unroll
-              for (int ks = 0; ks < kMaxHp / 16; ++ks) {
-                if (ks * 16 < Hp) {
-                  const uint64_t desc_b = desc_hi | (uint64_t)(((b_addr + ks * 2 * lbo_b) >> 4) & 0x3FFF);
-                  tc::mma_ts(d_tmem, a_base + ks * 8, desc_b, idesc, (uint32_t)((i | ks) != 0));
-                }
-              }
+            tc::mma_ts(d_tmem, a_base, desc0, idesc, (uint32_t)(i != 0));
+            tc::mma_ts(d_tmem, a_base + 8, desc0 + kstep, idesc, 1u);
+            if (Hp == 64) {
+              tc::mma_ts(d_tmem, a_base + 16, desc0 + 2 * kstep, idesc, 1u);
+              tc::mma_ts(d_tmem, a_base + 24, desc0 + 3 * kstep, idesc, 1u);
             }
             tc::mma_commit(&empty_a[sa]);
             tc::mma_commit(&empty_b[sb]);
@@ -364,6 +365,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
 // tile with the two tiles in ping-pong (tile 0's read-out runs under tile 1's MMAs), a read-out split between two
 // threads with 32 + 32 live values each (no spills), one tensor pass (fp16) instead of three.
 constexpr int kT2StagesW = 3;          // W pair images (2*Hp x L fp16 = 32 KB each)
+// dC tiles handed from the data-gradient to the weight-gradient kernel: blocks of 16 GEMM rows,
+// [fp16 image, MN-major: (l / 8) groups of 256 B = 2 k-groups x 8 rows x 16 B | 16 floats 1 / t_m]
+__host__ __device__ inline size_t tc2_dc_blk(int L) { return (size_t)32 * L + 64; }
 
 struct T2BwdSmem {
   int b_off, x0_off, dx_off, mx_off, bar_off, total;
@@ -401,6 +405,29 @@ __global__ void cin_tc2_pack_pairs_kernel(const float* __restrict__ w, uint8_t* 
   }
 }
 
+// max |d_pooled[b, pooled columns of layer k]| per batch row and layer: the data-gradient kernel scales each dC row
+// into fp16 by a power of two taken from an UPPER BOUND of the row's maximum (this + max|dh|), so that it needs one
+// sweep over the row instead of two.  One warp per batch row.
+struct DpmaxTab {
+  int pcol0[kCinMaxLayers], pool_n[kCinMaxLayers];
+};
+__global__ void cin_tc2_dpmax_kernel(const float* __restrict__ d_pooled, float* __restrict__ out, int B, int P, int n_layers,
+                                     const DpmaxTab tab) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < B; b += n_warps) {
+    const float* row = d_pooled + (size_t)b * P;
+    for (int k = 0; k < n_layers; ++k) {
+      float m = 0.f;
+      for (int c = lane; c < tab.pool_n[k]; c += 32) m = fmaxf(m, fabsf(__ldg(row + tab.pcol0[k] + c)));
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      if (lane == 0) out[(size_t)b * n_layers + k] = m;
+    }
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __grid_constant__ CinTcBwdParams p) {
   constexpr int R = 128 / D;
@@ -413,7 +440,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
   uint64_t* a_ready = bars;          // [tile]   8 warps
   uint64_t* full_b = bars + 2;       // [stage]  bulk copy (tx)
-  uint64_t* empty_b = bars + 5;      // [stage]  commit
+  uint64_t* empty_b = bars + 5;      // [stage]  one commit per issuing warp
   uint64_t* acc_full = bars + 8;     // [tile]   commit
   uint64_t* acc_empty = bars + 10;   // [tile]   8 warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
@@ -431,7 +458,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
     }
     for (int s = 0; s < kT2StagesW; ++s) {
       tc::mbar_init(&full_b[s], 1);
-      tc::mbar_init(&empty_b[s], 1);
+      tc::mbar_init(&empty_b[s], 2);
     }
     tc::fence_barrier_init();
   }
@@ -477,6 +504,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) dh[jj] = 0.f;
+      float dhmax = 0.f;                                         // max |dh row| over both halves (gradient wrt h_{k+1})
       for (int k = p.n_layers - 1; k >= 0; --k) {
         const int L = p.L[k], Hp = p.Hp[k];
         const int nh = Hp >> 1;                                              // this thread's share of j: 16 or 32
@@ -491,67 +519,64 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
                                                                        m_pad * ((L + 31) >> 5))
                                    : nullptr;
         const float* dprow = p.d_pooled + (size_t)b * p.P + p.pcol0[k];
-        // ---- the 16-column blocks of dC_k this thread owns (same rule as the forward's read-out) ------------------
-        // sweep 0: row maximum of the own blocks ; sweep 1: scale, pack to fp16, TMEM operand + HBM tiles for wgrad
-        float trow = 1.f, inv_t = 1.f;
-        float dmax = 0.f;
+        // ---- row scale from an upper bound of max|dC_k row|: max|d_pooled part| (precomputed per batch row) + max|dh| ------
+        float trow, inv_t;
+        const float bound = (valid ? __ldg(p.dpmax + (size_t)b * p.n_layers + k) : 0.f) + dhmax;
+        tc::pow2_scale_to_1024(bound, trow, inv_t);
+        if (q == 0) {
+          // wgrad folds 1/t_m into its on-the-fly operand: one float per row in the unused "lo" slot of the row's
+          // 16-row tile block; the layer's max|dC| bound goes to the statistics words (slot 8 + k)
+          *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * tc2_dc_blk(L) + 32 * L + (t & 15) * 4) = inv_t;
+          float wm = bound;
 #pragma unroll
-        for (int sweep = 0; sweep < 2; ++sweep) {
-          if (sweep == 1) {
-            float* mx = mxg + (size_t)(mx_cnt & 1) * 2 * 128;
-            ++mx_cnt;
-            mx[q * 128 + t] = dmax;
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-            dmax = fmaxf(mx[t], mx[128 + t]);
-            tc::pow2_scale_to_1024(dmax, trow, inv_t);
-            if (q == 0) {
-              // wgrad folds 1/t_m into its on-the-fly operand: one float per row in the unused "lo" slot of the row's
-              // 16-row tile block; the layer's max|dC| goes to the statistics words (slot 8 + k)
-              *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + 32 * L + (t & 15) * 4) = inv_t;
-              float wm = dmax;
+          for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
+          if (lane == 0 && wm > 0.f) atomicMax(const_cast<int*>(p.wmax) + 8 + k, __float_as_int(wm));
+        }
+        // ---- the 16-column blocks of dC_k this thread owns (same rule as the forward's read-out): one sweep ---------------
+        uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * tc2_dc_blk(L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
 #pragma unroll
-              for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
-              if (lane == 0 && wm > 0.f) atomicMax(const_cast<int*>(p.wmax) + 8 + k, __float_as_int(wm));
-            }
+        for (int slot = 0; slot < 6; ++slot) {
+          int cb;
+          bool live;
+          if (slot < 2) {
+            cb = ((q * nhn) >> 4) + slot;
+            live = (slot * 16 < nhn) && (cb * 16 < hid_n);
+          } else {
+            const int s2 = slot - 2;
+            cb = first_pb + q * pb_split + s2;
+            live = s2 < (q == 0 ? pb_split : n_pb - pb_split);
           }
+          if (live) {                               // warp-uniform
+            float dc[16];
+            const int pc = cb * 16 - pool_lo;       // first pooled column of the block (blocks never straddle the range)
+            if (valid && pc >= 0 && pc < pool_n) {
 #pragma unroll
-          for (int slot = 0; slot < 6; ++slot) {
-            int cb;
-            bool live;
-            if (slot < 2) {
-              cb = ((q * nhn) >> 4) + slot;
-              live = (slot * 16 < nhn) && (cb * 16 < hid_n);
+              for (int j = 0; j < 16; j += 4) {
+                const float4 q4 = __ldg(reinterpret_cast<const float4*>(dprow + pc + j));
+                dc[j] = q4.x; dc[j + 1] = q4.y; dc[j + 2] = q4.z; dc[j + 3] = q4.w;
+              }
             } else {
-              const int s2 = slot - 2;
-              cb = first_pb + q * pb_split + s2;
-              live = s2 < (q == 0 ? pb_split : n_pb - pb_split);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) dc[j] = 0.f;
             }
-            if (live) {                               // warp-uniform
-              const uint32_t bits = mrow ? (uint32_t)__ldg(mrow + cb) : 0u;
-              float dc[16];
+            if (slot < 2) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int col = cb * 16 + j;
-                float gsum = 0.f;
-                if (valid && col >= pool_lo && col < pool_lo + pool_n) gsum = __ldg(dprow + (col - pool_lo));
-                if (slot < 2) gsum += dh[(slot & 1) * 16 + j];
-                if (p.act == DTB_ACT_RELU && !((bits >> j) & 1u)) gsum = 0.f;
-                dc[j] = valid ? gsum : 0.f;
-              }
-              if (sweep == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) dmax = fmaxf(dmax, fabsf(dc[j]));
-              } else {
-                uint32_t zf[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) zf[c] = tc::pack_f16x2(dc[2 * c] * trow, dc[2 * c + 1] * trow);
-                tc::tmem_st8v(t_tile + cb * 8, zf[0], zf[1], zf[2], zf[3], zf[4], zf[5], zf[6], zf[7]);
-                uint8_t* dcblk = p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * (size_t)(64 * L) + ((t & 15) >> 3) * 128 + (t & 7) * 16;
-                *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zf[0], zf[1], zf[2], zf[3]);
-                *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zf[4], zf[5], zf[6], zf[7]);
-                tc::tmem_wait_st();
-              }
+              for (int j = 0; j < 16; ++j) dc[j] += dh[(slot & 1) * 16 + j];
             }
+            uint32_t keep = valid ? 0xffffu : 0u;
+            if (mrow) keep = (uint32_t)__ldg(mrow + cb);
+            else if (p.act == DTB_ACT_RELU) keep = 0u;                  // padded row
+            uint32_t zf[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float lo = ((keep >> (2 * c)) & 1u) ? dc[2 * c] * trow : 0.f;
+              const float hi = ((keep >> (2 * c + 1)) & 1u) ? dc[2 * c + 1] * trow : 0.f;
+              zf[c] = tc::pack_f16x2(lo, hi);
+            }
+            tc::tmem_st8v(t_tile + cb * 8, zf[0], zf[1], zf[2], zf[3], zf[4], zf[5], zf[6], zf[7]);
+            *reinterpret_cast<uint4*>(dcblk + (cb * 2) * 256) = make_uint4(zf[0], zf[1], zf[2], zf[3]);
+            *reinterpret_cast<uint4*>(dcblk + (cb * 2 + 1) * 256) = make_uint4(zf[4], zf[5], zf[6], zf[7]);
+            tc::tmem_wait_st();                                         // zf is reused by the next block
           }
         }
         tc::fence_before_thread_sync();
@@ -589,23 +614,18 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
             if (i < F) {                                   // warp-uniform (the phantom field of an odd F is all zeros)
               const float xi = x0g[((size_t)r * F + i) * D + d] * inv_acc;
               float dx = 0.f;
-              // both 16-column loads of this thread's share in flight before the single wait
-              uint32_t v0[16], v1[16];
-              tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh, v0);
-              if (nh == 32) tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh + 16, v1);
-              tc::tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float dz = __uint_as_float(v0[j]);
-                dx = fmaf(dz, h[j], dx);
-                dh[j] = fmaf(dz, xi, dh[j]);
-              }
-              if (nh == 32) {
+              for (int blk = 0; blk < 2; ++blk) {
+                if (blk * 16 < nh) {
+                  uint32_t v[16];
+                  tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh + blk * 16, v);
+                  tc::tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float dz = __uint_as_float(v1[j]);
-                  dx = fmaf(dz, h[16 + j], dx);
-                  dh[16 + j] = fmaf(dz, xi, dh[16 + j]);
+                  for (int j = 0; j < 16; ++j) {
+                    const float dz = __uint_as_float(v[j]);
+                    dx = fmaf(dz, h[blk * 16 + j], dx);
+                    dh[blk * 16 + j] = fmaf(dz, xi, dh[blk * 16 + j]);
+                  }
                 }
               }
               dxg[i * 128 + t] += dx * inv_acc;
@@ -621,6 +641,16 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
             const int j = q * nh + jj;
             if (jj < nh && j < F) dxg[j * 128 + t] += dh[jj];     // h_0 is x0 itself
           }
+        } else {
+          // max |dh_k row| over both halves: the bound of the next (lower) layer's dC
+          float own = 0.f;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) own = fmaxf(own, fabsf(dh[jj]));
+          float* mx = mxg + (size_t)(mx_cnt & 1) * 2 * 128;
+          ++mx_cnt;
+          mx[q * 128 + t] = own;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+          dhmax = fmaxf(mx[t], mx[128 + t]);
         }
       }
       // ---- scatter dx0 of this tile into the embedding gradient: both halves' partial sums, alternate fields ----------
@@ -633,43 +663,36 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
       }
       asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
     }
-  } else if (warp == 16) {
+  } else if (warp < 18) {
+    // ---- MMA issuers: warp 16 -> tile 0, warp 17 -> tile 1 (independent ping-pong partners) ----------------------------
+    const int g = warp - 16;
     const bool leader = elect_one_sync();
     const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
-    uint32_t chunk = 0, cnt[2] = {0, 0}, layer_cnt = 0;
+    const uint32_t a_base = tmem_base + g * 256;
+    const uint32_t d_tmem = a_base + 64;
+    uint32_t chunk = 0, cnt = 0, layer_cnt = 0;
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
         const int Hp = p.Hp[k], L = p.L[k];
         const uint32_t N = 2 * (uint32_t)Hp;
         const uint32_t idesc = tc::make_idesc_f16(128, N);
         const uint32_t lbo_b = (N >> 3) * 128;
+        const uint32_t kstep = (2 * lbo_b) >> 4;
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-        for (int pi = 0; pi < n_pairs; ++pi, ++chunk) {
+        for (int pi = 0; pi < n_pairs; ++pi, ++chunk, ++cnt) {
           const uint32_t sb = chunk % kT2StagesW, pb = (chunk / kT2StagesW) & 1;
+          const uint64_t desc0 = desc_hi | (uint64_t)(((smem_b_u32 + sb * (uint32_t)p.b_stage_bytes) >> 4) & 0x3FFF);
           tc::mbar_wait(&full_b[sb], pb);
-          const uint32_t b_addr = smem_b_u32 + sb * (uint32_t)p.b_stage_bytes;
+          if (pi == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
+          tc::mbar_wait(&acc_empty[g], (cnt & 1) ^ 1);
+          tc::fence_after_thread_sync();
+          if (leader) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            if (pi == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
-            const uint32_t c = cnt[g];
-            ++cnt[g];
-            tc::mbar_wait(&acc_empty[g], (c & 1) ^ 1);
-            tc::fence_after_thread_sync();
-            if (leader) {
-              const uint32_t a_base = tmem_base + g * 256;
-              const uint32_t d_tmem = a_base + 64;
-#pragma unroll
-              for (int ks = 0; ks < kMaxL / 16; ++ks) {
-                if (ks * 16 < L) {
-                  const uint64_t desc_b = desc_hi | (uint64_t)(((b_addr + ks * 2 * lbo_b) >> 4) & 0x3FFF);
-                  tc::mma_ts(d_tmem, a_base + ks * 8, desc_b, idesc, (uint32_t)(ks != 0));
-                }
-              }
-              tc::mma_commit(&acc_full[g]);
-            }
-            __syncwarp();
+            for (int ks = 0; ks < kMaxL / 16; ++ks)
+              if (ks * 16 < L) tc::mma_ts(d_tmem, a_base + ks * 8, desc0 + ks * kstep, idesc, (uint32_t)(ks != 0));
+            tc::mma_commit(&acc_full[g]);
+            tc::mma_commit(&empty_b[sb]);
           }
-          if (leader) tc::mma_commit(&empty_b[sb]);
           __syncwarp();
         }
       }
@@ -706,13 +729,252 @@ __global__ void cin_tc2_dbias_kernel(const uint8_t* __restrict__ dc_tiles, float
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t blk = t / L;
     const int l = (int)(t - blk * L);
-    const uint8_t* base = dc_tiles + blk * (int64_t)(64 * L);
+    const uint8_t* base = dc_tiles + blk * (int64_t)tc2_dc_blk(L);
     const uint8_t* col = base + (l >> 3) * 256 + (l & 7) * 2;
     const float* inv_t = reinterpret_cast<const float*>(base + 32 * L);
     float s = 0.f;
     for (int m = 0; m < 16; ++m)
       s += __half2float(*reinterpret_cast<const __half*>(col + (m >> 3) * 128 + (m & 7) * 16)) * __ldg(inv_t + m);
     if (s != 0.f) atomicAdd(d_bias + l, s);
+  }
+}
+
+// ==========================================================================================
+// Backward, weight gradient on ONE fp16 pass (the counterpart of cin_tc_wgrad_kernel<true>, cin_tc.cu)
+// ==========================================================================================
+//   dW_k[(i,j), l] = sum_m x0[m,i] h_k[m,j] dC_k[m,l]     UMMA M = (i,j) pairs, K = batch x dim rows m, N = L
+// The reduction runs over m, so per-row scales must cancel inside the MMA: the dC tile row m carries t_m, the
+// on-the-fly operand A'[(i,j), m] = x0[m,i] h[m,j] (G / t_m) its inverse and ONE per-layer G (from the recorded maxima)
+// keeps |A'| < 1024.  What changed against cin_tc_wgrad_kernel<true> (1.94 ms for the three layers, tensor pipe 32 %,
+// producers issue-bound: 3 multiplies + operand fetches per element in 256 threads):
+//   * a SCALER warp multiplies the x0 tile of a stage by G / t_m once (F x 64 products) -- the 256 producer threads then
+//     do ONE multiply per element (x' h) instead of three;
+//   * one MMA-issuing warp per tile; 4 operand stages (an fp16 operand block is 32 TMEM columns, not 64);
+//   * dC blocks without the unused "lo" half: 16.6 KB per 64-row stage instead of 32 KB from L2.
+constexpr int kW2Threads = 416;       // warps 0-7 producers (+ epilogue), 8/9 MMA issue tile 0/1, 10 dC loader, 11 x0/h loader, 12 scaler
+constexpr int kW2Stages = 3;          // x0 / h / dC stages of 64 rows
+constexpr int kW2StagesA = 4;         // operand blocks in TMEM per tile
+
+struct CinTc2WgradParams {
+  const float* xb;           // block-transposed x0:  [M_pad/64][F][68]
+  const float* hb;           // block-transposed h_k: [M_pad/64][H][68]  (== xb for layer 0)
+  const uint8_t* dc_tiles;   // layer k blocks of 16 rows (tc2_dc_blk)
+  float* d_w;                // [F*H, L] accumulate
+  int F, H, Hp, L;
+  int n_stage_total;         // ceil(M_pad / 64)
+  int stages_per_split;
+  const int* stats;          // [8 + k] max|dC_k| bound, [16] max|x0|, [24 + k] max|h_k| (bit patterns)
+  int layer;
+};
+
+struct W2Smem {
+  int b_off, h_off, x_off, xs_off, bar_off, total, b_bytes, h_bytes, x_bytes;
+};
+__host__ __device__ inline W2Smem w2_layout(int L, int Hp, int F) {
+  W2Smem l;
+  l.b_bytes = 4 * (int)tc2_dc_blk(L);
+  l.h_bytes = Hp * kWgPad * 4;
+  l.x_bytes = F * kWgPad * 4;
+  l.b_off = 0;
+  l.h_off = kW2Stages * l.b_bytes;
+  l.x_off = l.h_off + kW2Stages * l.h_bytes;
+  l.xs_off = l.x_off + kW2Stages * l.x_bytes;
+  l.bar_off = l.xs_off + kW2Stages * l.x_bytes;
+  l.bar_off = (l.bar_off + 15) / 16 * 16;
+  l.total = l.bar_off + 320;                      // 32 mbarriers + the TMEM address slot
+  return l;
+}
+
+__global__ void __launch_bounds__(kW2Threads, 1) cin_tc2_wgrad_kernel(const __grid_constant__ CinTc2WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const W2Smem lay = w2_layout(p.L, p.Hp, p.F);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* full_b = bars;            // [stage] 3   dC blocks landed (tx)
+  uint64_t* empty_b = bars + 3;       // [stage] 3   both issuers done with them (+ the scaler read 1/t_m)
+  uint64_t* full_h = bars + 6;        // [stage] 3   x0 / h tiles landed (tx)
+  uint64_t* scaled = bars + 9;        // [stage] 3   scaler wrote x0 * G / t_m
+  uint64_t* empty_h = bars + 12;      // [stage] 3   8 producer warps done reading the tiles
+  uint64_t* full_a = bars + 15;       // [tile][stageA] 8
+  uint64_t* empty_a = bars + 23;      // [tile][stageA] 8
+  uint64_t* acc_done = bars + 31;     // 1 (count 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + lay.bar_off + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int F = p.F, H = p.H, Hp = p.Hp, L = p.L;
+  const int ipt = 128 / Hp;                              // x0 fields per 128-row tile
+  const int s_begin = blockIdx.y * p.stages_per_split;
+  int s_end = s_begin + p.stages_per_split;
+  if (s_end > p.n_stage_total) s_end = p.n_stage_total;
+  const int n_st = s_end > s_begin ? s_end - s_begin : 0;
+  const bool h_is_x = (p.hb == p.xb);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kW2Stages; ++s) {
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty_b[s], 3);
+      tc::mbar_init(&full_h[s], 1);
+      tc::mbar_init(&scaled[s], 1);
+      tc::mbar_init(&empty_h[s], 8);
+    }
+    for (int i = 0; i < 2 * kW2StagesA; ++i) {
+      tc::mbar_init(&full_a[i], 4);
+      tc::mbar_init(&empty_a[i], 1);
+    }
+    tc::mbar_init(acc_done, 2);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  float gscale, inv_g;
+  {
+    const float xm = __int_as_float(__ldg(p.stats + 16)), hm = __int_as_float(__ldg(p.stats + 24 + p.layer));
+    const float dm = __int_as_float(__ldg(p.stats + 8 + p.layer));
+    tc::pow2_scale_to_1024(xm * hm * dm * (1.0f / 512.0f), gscale, inv_g);     // 1/t_m <= max|dC| / 512
+  }
+
+  if (warp < 8) {
+    // ---- A producers: lane row = (il, j): A'[row, m] = x'[m, i] * h[m, j] ------------------------------------------
+    const int g = warp >> 2;
+    const int t = threadIdx.x & 127;
+    const int il = t / Hp, j = t - il * Hp;
+    const int i = (blockIdx.x * 2 + g) * ipt + il;
+    const bool live = (i < F) && (j < H);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sh = s % kW2Stages, ph = (s / kW2Stages) & 1;
+      const uint32_t sa = s % kW2StagesA, pa = (s / kW2StagesA) & 1;
+      const float* xs = reinterpret_cast<const float*>(smem + lay.xs_off + sh * lay.x_bytes);       // scaled x0 tile
+      const float* hs = h_is_x ? reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes)
+                               : reinterpret_cast<const float*>(smem + lay.h_off + sh * lay.h_bytes);
+      tc::mbar_wait(&scaled[sh], ph);               // implies full_h and full_b
+      const float4* xrow = reinterpret_cast<const float4*>(xs + (live ? i : 0) * kWgPad);
+      const float4* hrow = reinterpret_cast<const float4*>(hs + (live ? j : 0) * kWgPad);
+      uint32_t zh[32];
+#pragma unroll
+      for (int q4 = 0; q4 < 16; ++q4) {
+        const float4 xv = xrow[q4], hv = hrow[q4];
+        zh[2 * q4] = live ? tc::pack_f16x2(xv.x * hv.x, xv.y * hv.y) : 0u;
+        zh[2 * q4 + 1] = live ? tc::pack_f16x2(xv.z * hv.z, xv.w * hv.w) : 0u;
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty_h[sh]);
+      tc::mbar_wait(&empty_a[g * kW2StagesA + sa], pa ^ 1);
+      tc::fence_after_thread_sync();
+      const uint32_t a_col = tmem_base + lane_base + 256 + (g * kW2StagesA + sa) * 32;     // 8 columns per k-step
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        tc::tmem_st8v(a_col + ks * 8, zh[ks * 8 + 0], zh[ks * 8 + 1], zh[ks * 8 + 2], zh[ks * 8 + 3], zh[ks * 8 + 4],
+                      zh[ks * 8 + 5], zh[ks * 8 + 6], zh[ks * 8 + 7]);
+      tc::tmem_wait_st();
+      tc::fence_before_thread_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_a[g * kW2StagesA + sa]);
+    }
+    // ---- epilogue: accumulator row -> dW[(i,j), :] ---------------------------------------------------
+    if (n_st > 0) {
+      tc::mbar_wait(acc_done, 0);
+      tc::fence_after_thread_sync();
+      float* dst = p.d_w + ((size_t)i * H + j) * L;
+#pragma unroll
+      for (int cb = 0; cb < kMaxL / 16; ++cb) {
+        if (cb * 16 < L) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem_base + lane_base + g * kAccCols + cb * 16, v);
+          tc::tmem_wait_ld();
+          if (live) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) atomicAdd(dst + cb * 16 + c, __uint_as_float(v[c]) * inv_g);
+          }
+        }
+      }
+      tc::fence_before_thread_sync();
+    }
+  } else if (warp < 10) {
+    // ---- MMA issuers: warp 8 -> tile 0, warp 9 -> tile 1 -------------------------------------------------------------
+    const int g = warp - 8;
+    const bool leader = elect_one_sync();
+    const uint32_t idesc = tc::make_idesc_f16(128, (uint32_t)L) | (1u << 16);       // B operand MN-major
+    // dC block descriptor (MN-major): LBO = 128 B (k-group), SBO = 256 B (n-group)
+    const uint64_t desc_hi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+    const uint32_t smem_b_u32 = tc::smem_u32(smem + lay.b_off);
+    const uint32_t blk16 = (uint32_t)tc2_dc_blk(L) >> 4;
+    const uint32_t d_tmem = tmem_base + g * kAccCols;
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sb = s % kW2Stages, pb = (s / kW2Stages) & 1;
+      const uint32_t sa = s % kW2StagesA, pa = (s / kW2StagesA) & 1;
+      const uint64_t desc0 = desc_hi | (uint64_t)(((smem_b_u32 + sb * (uint32_t)lay.b_bytes) >> 4) & 0x3FFF);
+      const uint32_t a_base = tmem_base + 256 + (g * kW2StagesA + sa) * 32;
+      tc::mbar_wait(&full_b[sb], pb);
+      tc::mbar_wait(&full_a[g * kW2StagesA + sa], pa);
+      tc::fence_after_thread_sync();
+      if (leader) {
+        tc::mma_ts(d_tmem, a_base, desc0, idesc, (uint32_t)(s != 0));
+        tc::mma_ts(d_tmem, a_base + 8, desc0 + blk16, idesc, 1u);
+        tc::mma_ts(d_tmem, a_base + 16, desc0 + 2 * blk16, idesc, 1u);
+        tc::mma_ts(d_tmem, a_base + 24, desc0 + 3 * blk16, idesc, 1u);
+        tc::mma_commit(&empty_a[g * kW2StagesA + sa]);
+        tc::mma_commit(&empty_b[sb]);
+        if (s == n_st - 1) tc::mma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)lay.b_bytes;
+      for (int s = 0; s < n_st; ++s) {
+        const uint32_t sb = s % kW2Stages, pb = (s / kW2Stages) & 1;
+        tc::mbar_wait(&empty_b[sb], pb ^ 1);
+        tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
+        tc::bulk_g2s(smem + lay.b_off + sb * lay.b_bytes, p.dc_tiles + (size_t)(s_begin + s) * bytes, bytes, &full_b[sb]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 11) {
+    // ---- x0 / h tile loader: one bulk async copy each per 64-row stage ---------------------------------------------
+    if (lane == 0) {
+      const uint32_t x_bytes = (uint32_t)lay.x_bytes, h_bytes = (uint32_t)(H * kWgPad * 4);
+      for (int s = 0; s < n_st; ++s) {
+        const uint32_t sh = s % kW2Stages, ph = (s / kW2Stages) & 1;
+        tc::mbar_wait(&empty_h[sh], ph ^ 1);
+        const size_t blk = (size_t)(s_begin + s);
+        tc::mbar_arrive_expect_tx(&full_h[sh], x_bytes + (h_is_x ? 0u : h_bytes));
+        tc::bulk_g2s(smem + lay.x_off + sh * lay.x_bytes, p.xb + blk * (size_t)(F * kWgPad), x_bytes, &full_h[sh]);
+        if (!h_is_x)
+          tc::bulk_g2s(smem + lay.h_off + sh * lay.h_bytes, p.hb + blk * (size_t)(H * kWgPad), h_bytes, &full_h[sh]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- scaler: x'[i][m] = x0[i][m] * G / t_m for the 64 rows of the stage (lane <-> rows lane and lane + 32) -------------
+    for (int s = 0; s < n_st; ++s) {
+      const uint32_t sh = s % kW2Stages, ph = (s / kW2Stages) & 1;
+      tc::mbar_wait(&full_h[sh], ph);
+      tc::mbar_wait(&full_b[sh], ph);
+      const uint8_t* bst = smem + lay.b_off + sh * lay.b_bytes;
+      const float c0 = *reinterpret_cast<const float*>(bst + (lane >> 4) * tc2_dc_blk(L) + 32 * L + (lane & 15) * 4) * gscale;
+      const float c1 = *reinterpret_cast<const float*>(bst + (2 + (lane >> 4)) * tc2_dc_blk(L) + 32 * L + (lane & 15) * 4) * gscale;
+      const float* xs = reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes);
+      float* xd = reinterpret_cast<float*>(smem + lay.xs_off + sh * lay.x_bytes);
+      for (int i = 0; i < F; ++i) {
+        xd[i * kWgPad + lane] = xs[i * kWgPad + lane] * c0;
+        xd[i * kWgPad + 32 + lane] = xs[i * kWgPad + 32 + lane] * c1;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        tc::mbar_arrive(&scaled[sh]);
+        tc::mbar_arrive(&empty_b[sh]);         // the 1/t_m words have been read (third arrival next to the two issuers)
+      }
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 8) {
+    tc::fence_after_thread_sync();
+    tc::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -775,6 +1037,7 @@ bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D) {
     if (p.L[k] % 16 || p.L[k] > kMaxL) return false;
     if (p.hid_n[k] % 16 || p.pool_lo[k] % 16 || p.pool_n[k] % 16) return false;
     if (p.hid_n[k] > 0 && p.pool_lo[k] != 0 && p.pool_lo[k] != p.hid_n[k]) return false;
+    if (!cin_tc2_wgrad_supported(p.F, p.Hp[k], p.L[k])) return false;
   }
   return tc2_bwd_layout(tc2_bwd_b_stage(p), p.F).total <= 227 * 1024;
 }
@@ -805,6 +1068,25 @@ static int tc2_launch_dgrad(const CinTcBwdParams& p_in, cudaStream_t st) {
   return DTB_OK;
 }
 
+// per-(batch row, layer) max|d_pooled| -> out[B, n_layers]
+int cin_tc2_dpmax(const float* d_pooled, float* out, const int* pcol0_host, const int* pool_n_host, int B, int P, int n_layers,
+                  cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(d_pooled) & 15) || (P & 3)) {
+    set_error("dtb_cin_bwd: fp16 single pass needs d_pooled 16-byte aligned with a row length divisible by 4");
+    return DTB_ERR_INVALID_ARG;
+  }
+  DpmaxTab tab{};
+  for (int k = 0; k < n_layers; ++k) {
+    tab.pcol0[k] = pcol0_host[k];
+    tab.pool_n[k] = pool_n_host[k];
+  }
+  int blocks = (B + 7) / 8;
+  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+  cin_tc2_dpmax_kernel<<<blocks, 256, 0, st>>>(d_pooled, out, B, P, n_layers, tab);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
 int cin_tc2_launch_dgrad(const CinTcBwdParams& p, int D, cudaStream_t st) {
   if (D == 16) return tc2_launch_dgrad<16>(p, st);
   if (D == 32) return tc2_launch_dgrad<32>(p, st);
@@ -816,6 +1098,29 @@ int cin_tc2_dbias(const uint8_t* dc_tiles, float* d_bias, int L, int n_blocks16,
   int blocks = (int)(((int64_t)n_blocks16 * L + 255) / 256);
   if (blocks > sm_count() * 8) blocks = sm_count() * 8;
   cin_tc2_dbias_kernel<<<blocks, 256, 0, st>>>(dc_tiles, d_bias, L, n_blocks16);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+bool cin_tc2_wgrad_supported(int F, int Hp, int L) { return w2_layout(L, Hp, F).total <= 227 * 1024 && (Hp == 32 || Hp == 64); }
+
+// one layer: xb / hb block-transposed operand tiles, dc_tiles the layer's fp16 blocks, d_w accumulated
+int cin_tc2_launch_wgrad(const float* xb, const float* hb, const uint8_t* dc_tiles, float* d_w, int F, int H, int Hp, int L,
+                         int n_stage_total, const int* stats, int layer, cudaStream_t st) {
+  CinTc2WgradParams w{};
+  w.xb = xb; w.hb = hb; w.dc_tiles = dc_tiles; w.d_w = d_w;
+  w.F = F; w.H = H; w.Hp = Hp; w.L = L; w.n_stage_total = n_stage_total; w.stats = stats; w.layer = layer;
+  const int ipt = 128 / Hp;
+  const int n_tiles = (F + ipt - 1) / ipt;
+  const int n_pairs = (n_tiles + 1) / 2;
+  int splits = sm_count() / n_pairs;
+  if (splits < 1) splits = 1;
+  if (splits > n_stage_total) splits = n_stage_total;
+  w.stages_per_split = (n_stage_total + splits - 1) / splits;
+  splits = (n_stage_total + w.stages_per_split - 1) / w.stages_per_split;
+  const W2Smem wl = w2_layout(L, Hp, F);
+  DTB_CUDA_OK(cudaFuncSetAttribute(cin_tc2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wl.total));
+  cin_tc2_wgrad_kernel<<<dim3(n_pairs, splits), kW2Threads, wl.total, st>>>(w);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

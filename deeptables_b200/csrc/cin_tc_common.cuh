@@ -72,7 +72,8 @@ struct CinTcBwdParams {
   unsigned long long hb_off[kCinMaxLayers];      // float offset of the block-transposed h_{k+1} tiles (as in CinTcParams)
   int b_stage_bytes;
   int compact;                                    // saved activations in the compact format (cin_tc_compact)
-  const int* wmax;                                // experiment 6 only: bit pattern of max|W_k| per layer
+  const int* wmax;                                // fp16 variants: statistics words (max|W_k| per layer at [k], max|dC_k| at [8 + k])
+  const float* dpmax;                             // cin_tc2: max|d_pooled[b, pooled columns of layer k]|, [B, n_layers]
 };
 
 
@@ -82,6 +83,11 @@ int cin_tc2_launch_fwd(const CinTcParams& p, int D, cudaStream_t st);
 bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D);
 int cin_tc2_pack_pairs(const float* w_k, uint8_t* dst, int F, int H, int Hp, int L, const int* wmax_k, cudaStream_t st);
 int cin_tc2_launch_dgrad(const CinTcBwdParams& p, int D, cudaStream_t st);
+int cin_tc2_dpmax(const float* d_pooled, float* out, const int* pcol0_host, const int* pool_n_host, int B, int P, int n_layers,
+                  cudaStream_t st);
 int cin_tc2_dbias(const uint8_t* dc_tiles, float* d_bias, int L, int n_blocks16, cudaStream_t st);
+bool cin_tc2_wgrad_supported(int F, int Hp, int L);
+int cin_tc2_launch_wgrad(const float* xb, const float* hb, const uint8_t* dc_tiles, float* d_w, int F, int H, int Hp, int L,
+                         int n_stage_total, const int* stats, int layer, cudaStream_t st);
 
 }  // namespace dtb
