@@ -11,6 +11,14 @@ static bool use_tc(const CinShape& s, int precision) {
   return cin_tc_supported(s);
 }
 
+// DTB_CIN_AUTO: single-pass fp16 tensor-core kernels where all three (forward, data gradient, weight gradient) take the
+// shape, else the bf16x3 tensor-core kernels, else the any-shape formulation.  Forward and backward of one step resolve
+// identically (same shape, same process-wide switches).
+static int resolve_precision(const CinShape& s, int precision) {
+  if (precision == DTB_CIN_AUTO && cin_tc_f16_auto(s)) return DTB_CIN_TC_F16X1;
+  return precision;
+}
+
 extern "C" {
 
 int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct) {
@@ -51,6 +59,7 @@ int dtb_cin_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
   }
   if (B <= 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  precision = resolve_precision(s, precision);
   if (use_tc(s, precision)) {
     const int single = precision == DTB_CIN_TC_BF16X1 || precision == DTB_CIN_TC_F16X1;
     return cin_tc_fwd(s, idx, table, row_offsets, weights, bias, pooled, saved, workspace, workspace_bytes, B,
@@ -80,6 +89,7 @@ static int cin_bwd_impl(const int32_t* idx, const float* table, const int64_t* r
   }
   if (B <= 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  precision = resolve_precision(s, precision);
   if (use_tc(s, precision))
     return cin_tc_bwd(s, idx, table, row_offsets, weights, d_pooled, saved, grad_table, d_weights, d_bias,
                       workspace, workspace_bytes, B, act, precision == DTB_CIN_TC_BF16X1 ? 1 : 3,

@@ -16,6 +16,7 @@ int cin_fp32_bwd(const CinShape& s, const int32_t* idx, const float* table, cons
                  cudaStream_t st);
 
 bool cin_tc_supported(const CinShape& s);
+bool cin_tc_f16_auto(const CinShape& s);     // precision "auto" resolves to the single-pass fp16 kernels for this shape
 size_t cin_tc_saved_bytes(const CinShape& s, int B);
 size_t cin_tc_workspace_bytes(const CinShape& s, int B, int training);
 // n_pass: 3 = bf16x3 split (fp32-grade), 1 = single pass; f16: single pass on scaled fp16 operands (n_pass must be 1)

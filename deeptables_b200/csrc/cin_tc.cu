@@ -557,6 +557,22 @@ bool cin_tc_supported(const CinShape& s) {
   return tc_layout(bstage, s.F).total <= 227 * 1024;
 }
 
+// precision "auto": the single-pass fp16 kernels of cin_tc2.cu when forward, data gradient and weight gradient all
+// support the shape (and the compact saved-activation format is in force), else the bf16x3 kernels of this file
+bool cin_tc_f16_auto(const CinShape& s) {
+  if (g_tc_f16_v1 || !cin_tc_supported(s) || !cin_tc_compact(s)) return false;
+  CinTcParams f{};
+  CinTcBwdParams b{};
+  f.F = b.F = s.F; f.n_layers = b.n_layers = s.n_layers; f.n_pass = 1; f.compact = b.compact = 1;
+  f.saved = reinterpret_cast<float*>(16);       // "training": the stricter of the two forward checks
+  for (int k = 0; k < s.n_layers; ++k) {
+    f.L[k] = b.L[k] = s.L[k]; f.H[k] = b.H[k] = s.H[k]; f.Hp[k] = b.Hp[k] = round_up(s.H[k], kSubK);
+    f.pool_lo[k] = b.pool_lo[k] = s.pool_lo[k]; f.pool_n[k] = b.pool_n[k] = s.pool_n[k];
+    f.hid_n[k] = b.hid_n[k] = (k + 1 < s.n_layers) ? s.H[k + 1] : 0;
+  }
+  return cin_tc2_fwd_supported(f, s.D) && cin_tc2_bwd_supported(b, s.D);
+}
+
 static size_t wpack_bytes(const CinShape& s) {
   size_t b = 0;
   for (int k = 0; k < s.n_layers; ++k) b += (size_t)s.F * s.L[k] * round_up(s.H[k], kSubK) * 4;

@@ -192,14 +192,17 @@ int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row
                       float* d_weights, float* d_bias, void* workspace, size_t workspace_bytes, int B, int F,
                       int D, const int* layer_sizes_host, int n_layers, int direct, int act, int precision,
                       int phase, void* stream);
-/* precision: 0 = auto (tensor-core bf16x3 split when the shape is supported, else fp32 SIMT),
- *            1 = force the any-shape materialising formulation (fp32-grade bf16x3 GEMMs of csrc/dense_tc.cu), 2 = tensor-core bf16x3, 3 = tensor-core bf16x1. */
+/* precision:
+ *   0 = auto: ONE tensor pass on fp16 operands scaled by exact powers of two (per GEMM row / per layer; csrc/cin_tc2.cu:
+ *       forward, data gradient and weight gradient, embedding dim 16 or 32, layer sizes multiples of 32, <= 64 hidden
+ *       fields) -- error ~2e-4 of the output scale, inside the 1e-3 parity bar; shapes outside it fall to 2, then to 1;
+ *   1 = the any-shape materialising formulation (outer product in HBM chunks + the bf16x3 GEMMs of csrc/dense_tc.cu);
+ *   2 = tensor-core bf16x3 split (hi*hi + lo*hi + hi*lo, ~2^-16 per product: fp32-grade); 3 = one bf16 pass (4e-3: tests only);
+ *   4 = force the single fp16 pass (error when the shape is outside it). */
 #define DTB_CIN_AUTO 0
 #define DTB_CIN_FP32 1
 #define DTB_CIN_TC_BF16X3 2
 #define DTB_CIN_TC_BF16X1 3
-/* 4: forward on ONE tensor pass with fp16 operands scaled by exact powers of two (per GEMM row / per layer); the
- * backward of a model that ran this forward uses the bf16x3 kernels.  Not the default; embedding dim 16 only. */
 #define DTB_CIN_TC_F16X1 4
 int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct);
 /* Test hooks for the tensor-core path.  set_variant: 1 (default) feeds the on-the-fly A operand to
