@@ -1619,8 +1619,12 @@ int cin_tc_bwd(const CinShape& s, const int32_t* idx, const float* table, const 
         const int64_t n_w = (int64_t)s.F * s.H[k] * s.L[k];
         cin_tc_wmax_kernel<<<(int)((n_w + 255) / 256 < 64 ? (n_w + 255) / 256 : 64), 256, 0, st>>>(weights + s.w_off[k], n_w, stats + k);
         DTB_LAUNCH_OK();
-        const int rc2 = cin_tc2_pack_pairs(weights + s.w_off[k], ws + p.wpack_off[k], s.F, s.H[k], p.Hp[k], s.L[k], stats + k, st);
-        if (rc2 != DTB_OK) return rc2;
+        const int64_t total = (int64_t)s.F * s.L[k] * p.Hp[k];
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        cin_tc_pack_t_f16_kernel<<<blocks, 256, 0, st>>>(weights + s.w_off[k], ws + p.wpack_off[k], s.F, s.H[k], p.Hp[k], s.L[k],
+                                                         stats + k);
+        DTB_LAUNCH_OK();
       }
     }
   }

@@ -24,9 +24,9 @@
 
 namespace dtb {
 
-constexpr int kT2Threads = 608;        // warps 0-15 producer + epilogue, 16 / 17 MMA issue for tile 0 / 1 (16 owns TMEM), 18 weight loader
+constexpr int kT2Threads = 640;        // warps 0-15 producer + epilogue, 16 / 17 MMA issue for tile 0 / 1 (16 owns TMEM), 18 / 19 weight loaders
 constexpr int kT2StagesA = 4;
-constexpr int kT2StagesB = 6;
+constexpr int kT2StagesB = 4;          // weight stages PER TILE (forward: each tile streams its own copy of the chunks)
 constexpr int kT2ACols = 32;           // TMEM columns of one (stage, tile) operand block: fp16 [128 x 64]
 
 struct T2Smem {
@@ -35,11 +35,11 @@ struct T2Smem {
 __host__ __device__ inline T2Smem tc2_layout(int b_stage_bytes, int F) {
   T2Smem l;
   l.b_off = 0;
-  l.x0_off = kT2StagesB * b_stage_bytes;
+  l.x0_off = 2 * kT2StagesB * b_stage_bytes;      // one weight ring per tile
   l.mx_off = l.x0_off + 2 * 128 * F * 4;          // x0s[tile][r][i][d]
   l.bar_off = l.mx_off + 2 * 2 * 2 * 128 * 4;     // row maxima [tile][parity][half][t]
   l.bar_off = (l.bar_off + 15) / 16 * 16;
-  l.total = l.bar_off + 256;
+  l.total = l.bar_off + 320;
   return l;
 }
 
@@ -52,27 +52,35 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
   float* x0s = reinterpret_cast<float*>(smem + lay.x0_off);
   float* mxs = reinterpret_cast<float*>(smem + lay.mx_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
-  uint64_t* full_a = bars;                        // [stage] 16 producer warps (both tiles)
-  uint64_t* empty_a = bars + 4;                   // [stage] commit
-  uint64_t* full_b = bars + 8;                    // [stage] bulk copy (tx)
-  uint64_t* empty_b = bars + 14;                  // [stage] commit
-  uint64_t* acc_full = bars + 20;                 // commit after the last granule of a layer (both tiles)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  // The two M = 128 tiles of the CTA run INDEPENDENT pipelines (own operand stages, own weight ring, own issuing warp
+  // and loader) and tile 1 starts half a layer late: while one tile reads out its accumulator -- which nothing of its own
+  // can overlap, the next layer's operand depends on it -- the other tile's MMAs keep the tensor pipe busy.  Sharing each
+  // weight chunk between the tiles, as the bf16x3 kernel does, would lock them in step; with ONE fp16 image per chunk
+  // two private streams cost what its shared hi + lo stream costs (~21 B/clk/SM from L2).
+  uint64_t* full_a = bars;                        // [tile][stage] 8 producer warps
+  uint64_t* empty_a = bars + 8;                   // [tile][stage] commit
+  uint64_t* full_b = bars + 16;                   // [tile][stage] bulk copy (tx)
+  uint64_t* empty_b = bars + 24;                  // [tile][stage] commit
+  uint64_t* acc_full = bars + 32;                 // [tile] commit after the last granule of a layer
+  uint64_t* start1 = bars + 34;                   // tile 0's issuer -> tile 1: go (after half of tile 0's first layer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = p.F;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kT2StagesA; ++s) {
-      tc::mbar_init(&full_a[s], 16);
-      tc::mbar_init(&empty_a[s], 2);          // one tcgen05.commit per issuing warp
+    for (int s = 0; s < 2 * kT2StagesA; ++s) {
+      tc::mbar_init(&full_a[s], 8);
+      tc::mbar_init(&empty_a[s], 1);
     }
-    for (int s = 0; s < kT2StagesB; ++s) {
+    for (int s = 0; s < 2 * kT2StagesB; ++s) {
       tc::mbar_init(&full_b[s], 1);
-      tc::mbar_init(&empty_b[s], 2);
+      tc::mbar_init(&empty_b[s], 1);
     }
-    tc::mbar_init(acc_full, 2);
+    tc::mbar_init(&acc_full[0], 1);
+    tc::mbar_init(&acc_full[1], 1);
+    tc::mbar_init(start1, 1);
     tc::fence_barrier_init();
   }
   if (warp == 16) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -92,6 +100,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
     float* mxg = mxs + (size_t)g * 2 * 2 * 128;     // [parity][half][t]
     uint32_t gran = 0, layer_cnt = 0;
     float h[32];
+    if (g == 1) tc::mbar_wait(start1, 0);           // stagger: see the barrier table above
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       const int row0 = (st * 2 + g) * R;
       const int b = row0 + r;
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
           uint32_t zh[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c) zh[c] = tc::pack_f16x2(xi * h[2 * c], xi * h[2 * c + 1]);
-          tc::mbar_wait(&empty_a[sa], pa ^ 1);
+          tc::mbar_wait(&empty_a[g * kT2StagesA + sa], pa ^ 1);
           tc::fence_after_thread_sync();
           const uint32_t a_col = tmem_base + lane_base + 2 * kAccCols + (sa * 2 + g) * kT2ACols + q * (nh >> 1);
           tc::tmem_st8v(a_col, zh[0], zh[1], zh[2], zh[3], zh[4], zh[5], zh[6], zh[7]);
@@ -159,10 +168,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
           tc::tmem_wait_st();
           tc::fence_before_thread_sync();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&full_a[sa]);
+          if (lane == 0) tc::mbar_arrive(&full_a[g * kT2StagesA + sa]);
         }
         // ---- epilogue of layer k: this thread's share of its accumulator row ------------------------------------
-        tc::mbar_wait(acc_full, layer_cnt & 1);
+        tc::mbar_wait(&acc_full[g], layer_cnt & 1);
         ++layer_cnt;
         tc::fence_after_thread_sync();
         const int hid_n = p.hid_n[k], pool_lo = p.pool_lo[k], pool_n = p.pool_n[k];
@@ -291,9 +300,10 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
     // (ncu source view, profiles/r2_cin_tc2_ncu.txt).  Two warps on different SM sub-partitions each issue one tile.
     const int g = warp - 16;
     const bool leader = elect_one_sync();
-    const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
+    const uint32_t smem_b_u32 = tc::smem_u32(smem_b) + g * kT2StagesB * (uint32_t)p.b_stage_bytes;
     const uint32_t d_tmem = tmem_base + g * kAccCols;
     uint32_t gran = 0, chunk = 0;
+    bool go_sent = (g != 0);
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = 0; k < p.n_layers; ++k) {
         const int Hp = p.Hp[k], L = p.L[k];
@@ -306,8 +316,8 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
           const uint32_t sa = gran % kT2StagesA, pa = (gran / kT2StagesA) & 1;
           const uint32_t a_base = tmem_base + 2 * kAccCols + (sa * 2 + g) * kT2ACols;
           const uint64_t desc0 = desc_hi | (uint64_t)(((smem_b_u32 + sb * (uint32_t)p.b_stage_bytes) >> 4) & 0x3FFF);
-          tc::mbar_wait(&full_b[sb], pb);
-          tc::mbar_wait(&full_a[sa], pa);
+          tc::mbar_wait(&full_b[g * kT2StagesB + sb], pb);
+          tc::mbar_wait(&full_a[g * kT2StagesA + sa], pa);
           tc::fence_after_thread_sync();
           if (leader) {
             tc::mma_ts(d_tmem, a_base, desc0, idesc, (uint32_t)(i != 0));
@@ -316,18 +326,23 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
               tc::mma_ts(d_tmem, a_base + 16, desc0 + 2 * kstep, idesc, 1u);
               tc::mma_ts(d_tmem, a_base + 24, desc0 + 3 * kstep, idesc, 1u);
             }
-            tc::mma_commit(&empty_a[sa]);
-            tc::mma_commit(&empty_b[sb]);
-            if (i == F - 1) tc::mma_commit(acc_full);
+            tc::mma_commit(&empty_a[g * kT2StagesA + sa]);
+            tc::mma_commit(&empty_b[g * kT2StagesB + sb]);
+            if (i == F - 1) tc::mma_commit(&acc_full[g]);
+            if (!go_sent && (i == F / 2 || i == F - 1)) tc::mma_commit(start1);
           }
+          if (i == F / 2 || i == F - 1) go_sent = true;
           __syncwarp();
         }
       }
     }
   } else {
-    // ================================ weight loader ============================================
+    // ================================ weight loaders: warp 18 -> tile 0's ring, warp 19 -> tile 1's ===============
+    const int g = warp - 18;
     if (lane == 0) {
+      uint8_t* ring = smem_b + (size_t)g * kT2StagesB * p.b_stage_bytes;
       uint32_t chunk = 0;
+      if (g == 1) tc::mbar_wait(start1, 0);
       for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int k = 0; k < p.n_layers; ++k) {
           const uint32_t bytes = (uint32_t)p.L[k] * p.Hp[k] * 2;       // one fp16 image
@@ -335,9 +350,9 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
           const uint8_t* src = p.wpack + p.wpack_off[k];
           for (int i = 0; i < F; ++i, ++chunk) {
             const uint32_t sb = chunk % kT2StagesB, pb = (chunk / kT2StagesB) & 1;
-            tc::mbar_wait(&empty_b[sb], pb ^ 1);
-            tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
-            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[sb]);
+            tc::mbar_wait(&empty_b[g * kT2StagesB + sb], pb ^ 1);
+            tc::mbar_arrive_expect_tx(&full_b[g * kT2StagesB + sb], bytes);
+            tc::bulk_g2s(ring + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[g * kT2StagesB + sb]);
           }
         }
       }
@@ -358,13 +373,15 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_fwd_kernel(const __grid
 // Per 2 x 128-row super tile, layers last -> first:
 //   dC_k = (d_pooled part + dh_{k+1}) * relu'(T_k), scaled per row into fp16 (exact power of two from the row's max, the
 //          two halves exchange their maxima) -> TMEM A operand (written ONCE per layer) + fp16 tiles in HBM for wgrad;
-//   per PAIR of x0 fields (i0, i1):  dZ[m, (il, j)] = sum_l dC[m, l] W[(i_il, j), l]   one N = 2*Hp (128) MMA chain, K = L
+//   per x0 field i:  dZ[m, j] = sum_l dC[m, l] W[(i, j), l]      one N = Hp MMA chain, K = L, two accumulators per tile
 //   read-out: dx0[m, i] += sum_j dZ h_k[m, j] ;  dh_k[m, j] += dZ x0[m, i]              each thread its half of j
-// What changed against the one-thread-per-row kernel, whose tensor pipe was 48 % busy: N = 128 MMAs instead of N = 64
-// (the A-from-TMEM form feeds the same operand bytes per MMA for half the tensor work at N = 64), one accumulator per
-// tile with the two tiles in ping-pong (tile 0's read-out runs under tile 1's MMAs), a read-out split between two
-// threads with 32 + 32 live values each (no spills), one tensor pass (fp16) instead of three.
-constexpr int kT2StagesW = 3;          // W pair images (2*Hp x L fp16 = 32 KB each)
+// This kernel is bound by the TMEM read-out of dZ (128 x F*Hp fp32 per tile and layer at ~64 B/clk/SM: ~1.0 ms at
+// 65 536 rows), not by the tensor pipe (0.6 ms of MMAs in one fp16 pass; the bf16x3 kernel was MMA-bound at 2.9 ms).
+// So the organisation serves the read-out: two 64-column accumulators per tile, the issuing warp one field ahead (the
+// MMAs of field i+1 run under the read-out of field i), one issuing warp per tile, the read-out split between two
+// threads with 32 + 32 live values each.  (A first version paired two fields per N = 128 chain with ONE accumulator
+// per tile: every read-out then waited for its own MMAs -- 1.81 ms, tensor pipe 30 %.)
+constexpr int kT2StagesW = 6;          // per-field W images (Hp x L fp16 <= 16 KB each), shared by the two tiles' issuers
 // dC tiles handed from the data-gradient to the weight-gradient kernel: blocks of 16 GEMM rows,
 // [fp16 image, MN-major: (l / 8) groups of 256 B = 2 k-groups x 8 rows x 16 B | 16 floats 1 / t_m]
 __host__ __device__ inline size_t tc2_dc_blk(int L) { return (size_t)32 * L + 64; }
@@ -382,27 +399,6 @@ __host__ __device__ inline T2BwdSmem tc2_bwd_layout(int b_stage_bytes, int F) {
   l.bar_off = (l.bar_off + 15) / 16 * 16;
   l.total = l.bar_off + 256;
   return l;
-}
-
-// weights -> per field PAIR pi: ONE fp16 image of B[n = il*Hp + j][k = l] = W[((2 pi + il)*H + j), l] * s_W, canonical
-// K-major no swizzle (zero rows for j >= H and for the phantom field of an odd F)
-__global__ void cin_tc2_pack_pairs_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int F, int H, int Hp,
-                                          int L, const int* __restrict__ wmax) {
-  float s, inv;
-  tc::pow2_scale_to_1024(__int_as_float(*wmax), s, inv);
-  const int N = 2 * Hp;
-  const int n_pairs = (F + 1) / 2;
-  const int64_t per_img = (int64_t)N * L;
-  const int64_t total = per_img * n_pairs;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int pi = (int)(t / per_img);
-    const int rem = (int)(t - (int64_t)pi * per_img);
-    const int n = rem / L, l = rem - n * L;          // l fastest: coalesced reads
-    const int il = n / Hp, j = n - il * Hp, i = 2 * pi + il;
-    const float v = (i < F && j < H) ? w[((int64_t)i * H + j) * L + l] * s : 0.f;
-    const int64_t off = ((int64_t)(l >> 3) * (N >> 3) + (n >> 3)) * 128 + (n & 7) * 16 + (l & 7) * 2;
-    *reinterpret_cast<__half*>(out + (int64_t)pi * per_img * 2 + off) = __float2half_rn(v);
-  }
 }
 
 // max |d_pooled[b, pooled columns of layer k]| per batch row and layer: the data-gradient kernel scales each dC row
@@ -438,23 +434,22 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
   float* dxs = reinterpret_cast<float*>(smem + lay.dx_off);
   float* mxs = reinterpret_cast<float*>(smem + lay.mx_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
-  uint64_t* a_ready = bars;          // [tile]   8 warps
-  uint64_t* full_b = bars + 2;       // [stage]  bulk copy (tx)
-  uint64_t* empty_b = bars + 5;      // [stage]  one commit per issuing warp
-  uint64_t* acc_full = bars + 8;     // [tile]   commit
-  uint64_t* acc_empty = bars + 10;   // [tile]   8 warps
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* a_ready = bars;          // [tile]        8 warps
+  uint64_t* full_b = bars + 2;       // [stage]       bulk copy (tx)
+  uint64_t* empty_b = bars + 8;      // [stage]       one commit per issuing warp
+  uint64_t* acc_full = bars + 14;    // [tile][buf]   commit
+  uint64_t* acc_empty = bars + 18;   // [tile][buf]   8 warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int F = p.F;
-  const int n_pairs = (F + 1) / 2;
   const int n_super = (p.B + 2 * R - 1) / (2 * R);
 
   if (threadIdx.x == 0) {
-    for (int g = 0; g < 2; ++g) {
-      tc::mbar_init(&a_ready[g], 8);
-      tc::mbar_init(&acc_full[g], 1);
-      tc::mbar_init(&acc_empty[g], 8);
+    for (int g = 0; g < 2; ++g) tc::mbar_init(&a_ready[g], 8);
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 8);
     }
     for (int s = 0; s < kT2StagesW; ++s) {
       tc::mbar_init(&full_b[s], 1);
@@ -603,37 +598,31 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
         }
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) dh[jj] = 0.f;
-        for (int pi = 0; pi < n_pairs; ++pi) {
-          const uint32_t par = acc_cnt & 1;
+        for (int i = 0; i < F; ++i) {
+          const uint32_t buf = acc_cnt & 1, par = (acc_cnt >> 1) & 1;
           ++acc_cnt;
-          tc::mbar_wait(&acc_full[g], par);
+          const float xi = x0g[((size_t)r * F + i) * D + d] * inv_acc;
+          tc::mbar_wait(&acc_full[g * 2 + buf], par);
           tc::fence_after_thread_sync();
+          float dx = 0.f;
 #pragma unroll
-          for (int il = 0; il < 2; ++il) {
-            const int i = 2 * pi + il;
-            if (i < F) {                                   // warp-uniform (the phantom field of an odd F is all zeros)
-              const float xi = x0g[((size_t)r * F + i) * D + d] * inv_acc;
-              float dx = 0.f;
+          for (int blk = 0; blk < 2; ++blk) {
+            if (blk * 16 < nh) {
+              uint32_t v[16];
+              tc::tmem_ld16(t_tile + 64 + buf * 64 + q * nh + blk * 16, v);
+              tc::tmem_wait_ld();
 #pragma unroll
-              for (int blk = 0; blk < 2; ++blk) {
-                if (blk * 16 < nh) {
-                  uint32_t v[16];
-                  tc::tmem_ld16(t_tile + 64 + il * Hp + q * nh + blk * 16, v);
-                  tc::tmem_wait_ld();
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const float dz = __uint_as_float(v[j]);
-                    dx = fmaf(dz, h[blk * 16 + j], dx);
-                    dh[blk * 16 + j] = fmaf(dz, xi, dh[blk * 16 + j]);
-                  }
-                }
+              for (int j = 0; j < 16; ++j) {
+                const float dz = __uint_as_float(v[j]);
+                dx = fmaf(dz, h[blk * 16 + j], dx);
+                dh[blk * 16 + j] = fmaf(dz, xi, dh[blk * 16 + j]);
               }
-              dxg[i * 128 + t] += dx * inv_acc;
             }
           }
           tc::fence_before_thread_sync();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&acc_empty[g]);
+          if (lane == 0) tc::mbar_arrive(&acc_empty[g * 2 + buf]);
+          dxg[i * 128 + t] += dx * inv_acc;
         }
         if (k == 0) {
 #pragma unroll
@@ -669,46 +658,47 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
     const bool leader = elect_one_sync();
     const uint32_t smem_b_u32 = tc::smem_u32(smem_b);
     const uint32_t a_base = tmem_base + g * 256;
-    const uint32_t d_tmem = a_base + 64;
     uint32_t chunk = 0, cnt = 0, layer_cnt = 0;
     for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
       for (int k = p.n_layers - 1; k >= 0; --k, ++layer_cnt) {
         const int Hp = p.Hp[k], L = p.L[k];
-        const uint32_t N = 2 * (uint32_t)Hp;
-        const uint32_t idesc = tc::make_idesc_f16(128, N);
-        const uint32_t lbo_b = (N >> 3) * 128;
+        const uint32_t idesc = tc::make_idesc_f16(128, (uint32_t)Hp);
+        const uint32_t lbo_b = (uint32_t)(Hp >> 3) * 128;
         const uint32_t kstep = (2 * lbo_b) >> 4;
         const uint64_t desc_hi = ((uint64_t)((lbo_b >> 4) & 0x3FFF) << 16) | ((uint64_t)(128 >> 4) << 32) | ((uint64_t)1 << 46);
-        for (int pi = 0; pi < n_pairs; ++pi, ++chunk, ++cnt) {
+        for (int i = 0; i < F; ++i, ++chunk, ++cnt) {
           const uint32_t sb = chunk % kT2StagesW, pb = (chunk / kT2StagesW) & 1;
+          const uint32_t buf = cnt & 1, par = (cnt >> 1) & 1;
           const uint64_t desc0 = desc_hi | (uint64_t)(((smem_b_u32 + sb * (uint32_t)p.b_stage_bytes) >> 4) & 0x3FFF);
+          const uint32_t d_tmem = a_base + 64 + buf * 64;
           tc::mbar_wait(&full_b[sb], pb);
-          if (pi == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
-          tc::mbar_wait(&acc_empty[g], (cnt & 1) ^ 1);
+          if (i == 0) tc::mbar_wait(&a_ready[g], layer_cnt & 1);
+          tc::mbar_wait(&acc_empty[g * 2 + buf], par ^ 1);
           tc::fence_after_thread_sync();
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < kMaxL / 16; ++ks)
               if (ks * 16 < L) tc::mma_ts(d_tmem, a_base + ks * 8, desc0 + ks * kstep, idesc, (uint32_t)(ks != 0));
-            tc::mma_commit(&acc_full[g]);
+            tc::mma_commit(&acc_full[g * 2 + buf]);
             tc::mma_commit(&empty_b[sb]);
           }
           __syncwarp();
         }
       }
     }
-  } else {
+  } else if (warp == 18) {
     if (lane == 0) {
       uint32_t chunk = 0;
       for (int st = blockIdx.x; st < n_super; st += gridDim.x) {
         for (int k = p.n_layers - 1; k >= 0; --k) {
-          const uint32_t bytes = 2u * (uint32_t)p.Hp[k] * (uint32_t)p.L[k] * 2u;
+          const uint32_t bytes = (uint32_t)p.Hp[k] * (uint32_t)p.L[k] * 2u;         // one fp16 image (cin_tc_pack_t_f16_kernel)
+          const uint32_t stride = (uint32_t)p.Hp[k] * (uint32_t)p.L[k] * 4u;        // the pack keeps room for a lo image
           const uint8_t* src = p.wpack + p.wpack_off[k];
-          for (int pi = 0; pi < n_pairs; ++pi, ++chunk) {
+          for (int i = 0; i < F; ++i, ++chunk) {
             const uint32_t sb = chunk % kT2StagesW, pb = (chunk / kT2StagesW) & 1;
             tc::mbar_wait(&empty_b[sb], pb ^ 1);
             tc::mbar_arrive_expect_tx(&full_b[sb], bytes);
-            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)pi * bytes, bytes, &full_b[sb]);
+            tc::bulk_g2s(smem_b + (size_t)sb * p.b_stage_bytes, src + (size_t)i * stride, bytes, &full_b[sb]);
           }
         }
       }
@@ -1037,7 +1027,7 @@ static int tc2_launch(const CinTcParams& p_in, cudaStream_t st) {
 static int tc2_bwd_b_stage(const CinTcBwdParams& p) {
   int b = 0;
   for (int k = 0; k < p.n_layers; ++k) {
-    const int bytes = 2 * p.Hp[k] * p.L[k] * 2;
+    const int bytes = p.Hp[k] * p.L[k] * 2;
     if (bytes > b) b = bytes;
   }
   return b;
@@ -1054,16 +1044,6 @@ bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D) {
     if (!cin_tc2_wgrad_supported(p.F, p.Hp[k], p.L[k])) return false;
   }
   return tc2_bwd_layout(tc2_bwd_b_stage(p), p.F).total <= 227 * 1024;
-}
-
-// packs layer k's pair images at wpack + wpack_off[k] (scale word: wmax[k], already reduced)
-int cin_tc2_pack_pairs(const float* w_k, uint8_t* dst, int F, int H, int Hp, int L, const int* wmax_k, cudaStream_t st) {
-  const int64_t total = (int64_t)((F + 1) / 2) * 2 * Hp * L;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-  cin_tc2_pack_pairs_kernel<<<blocks, 256, 0, st>>>(w_k, dst, F, H, Hp, L, wmax_k);
-  DTB_LAUNCH_OK();
-  return DTB_OK;
 }
 
 template <int D>

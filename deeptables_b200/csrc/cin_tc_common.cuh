@@ -81,7 +81,6 @@ struct CinTcBwdParams {
 bool cin_tc2_fwd_supported(const CinTcParams& p, int D);
 int cin_tc2_launch_fwd(const CinTcParams& p, int D, cudaStream_t st);
 bool cin_tc2_bwd_supported(const CinTcBwdParams& p, int D);
-int cin_tc2_pack_pairs(const float* w_k, uint8_t* dst, int F, int H, int Hp, int L, const int* wmax_k, cudaStream_t st);
 int cin_tc2_launch_dgrad(const CinTcBwdParams& p, int D, cudaStream_t st);
 int cin_tc2_dpmax(const float* d_pooled, float* out, const int* pcol0_host, const int* pool_n_host, int B, int P, int n_layers,
                   cudaStream_t st);

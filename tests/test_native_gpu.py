@@ -383,8 +383,14 @@ def _cin_oracle(x, sizes, direct, filters, biases, act):
 
 
 @pytest.mark.parametrize('f,d,sizes,direct,use_bias,act', CIN_CASES)
-@pytest.mark.parametrize('precision', [1, 0])
+@pytest.mark.parametrize('precision', [1, 2, 0])
 def test_cin_fwd_bwd(nat, f, d, sizes, direct, use_bias, act, precision):
+    """precision 1 = any-shape formulation, 2 = tensor-core bf16x3 (skipped where the shape is outside it), 0 = auto:
+    the single-pass fp16 kernels where they apply (error ~2e-4 of the scale).  Under fp16 a pre-activation within that
+    error of zero can flip its relu-mask bit against the float64 oracle, which moves the gradient rows of that one batch
+    row by percents: the gradient check then asks for 99 % of the entries inside the tolerance and a small norm-wise
+    error; the backward ARITHMETIC of the fp16 kernels is checked against the bf16x3 kernels on identical activations in
+    tests/test_zz_baseline_configs_gpu.py."""
     b = 37
     vocab = [9 + i for i in range(f)]
     tabs, flat, offs = make_table(vocab, d, seed=11)
@@ -396,6 +402,8 @@ def test_cin_fwd_bwd(nat, f, d, sizes, direct, use_bias, act, precision):
     wcat = np.concatenate([x.reshape(-1) for x in filt])
     sizes_c = nat.int_array(sizes)
     n = len(sizes)
+    if precision == 2 and not nat.lib.dtb_cin_tc_supported(f, d, sizes_c, n, int(direct)):
+        pytest.skip('shape outside the tensor-core kernels')
     pw = L.cin_pooled_width(f, dict(cross_layer_size=sizes, direct=direct))
     pooled = torch.empty(b, pw, device='cuda')
     ws_bytes = nat.lib.dtb_cin_workspace_bytes(b, f, d, sizes_c, n, int(direct), 1)
@@ -424,11 +432,19 @@ def test_cin_fwd_bwd(nat, f, d, sizes, direct, use_bias, act, precision):
     grads = torch.autograd.grad(loss, params, allow_unused=True)
     want_t = torch.cat(grads[:f], dim=0).numpy()
     want_w = np.concatenate([gg.numpy().reshape(-1) for gg in grads[f:f + n]])
-    np.testing.assert_allclose(gt.cpu().numpy(), want_t, rtol=tol * 10, atol=tol * np.abs(want_t).max())
-    np.testing.assert_allclose(dw.cpu().numpy(), want_w, rtol=tol * 10, atol=tol * np.abs(want_w).max())
+    def close(got, want_, what):
+        got = got.cpu().numpy()
+        if precision != 0:
+            np.testing.assert_allclose(got, want_, rtol=tol * 10, atol=tol * np.abs(want_).max(), err_msg=what)
+            return
+        ok = np.abs(got - want_) <= tol * 10 * np.abs(want_) + tol * np.abs(want_).max()
+        assert ok.mean() >= 0.99, f'{what}: only {100 * ok.mean():.2f} % of the entries inside the tolerance'
+        assert np.linalg.norm(got - want_) <= 3e-2 * np.linalg.norm(want_), f'{what}: norm-wise error too large'
+
+    close(gt, want_t, 'embedding gradient')
+    close(dw, want_w, 'filter gradient')
     if use_bias:
-        want_b = np.concatenate([gg.numpy() for gg in grads[f + n:]])
-        np.testing.assert_allclose(dbias.cpu().numpy(), want_b, rtol=tol * 10, atol=tol * np.abs(want_b).max())
+        close(dbias, np.concatenate([gg.numpy() for gg in grads[f + n:]]), 'bias gradient')
 
 
 def test_cin_invalid_config_rejected(nat):

@@ -56,7 +56,7 @@ if os.environ.get('CHECKF'):
     # forward of this precision / kernel against the bf16x3 forward
     ref = torch.empty_like(pooled)
     nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(ref), P(saved), P(ws), ws_bytes, B, F, D,
-                                  sizes_c, 3, 0, 1, 0, None, None), 'cin_fwd ref')
+                                  sizes_c, 3, 0, 1, 2, None, None), 'cin_fwd ref')
     torch.cuda.synchronize()
     print(f'forward precision {prec} vs bf16x3: max err / scale {float((ref - pooled).abs().max() / ref.abs().max()):.2e}', flush=True)
 if os.environ.get('CHECKB') and prec:
@@ -64,7 +64,7 @@ if os.environ.get('CHECKB') and prec:
     res = []
     nat.check(nat.lib.dtb_cin_fwd(P(idx), P(table), P(offs), P(w), None, P(pooled), P(saved), P(ws), ws_bytes, B, F, D,
                                   sizes_c, 3, 0, 1, prec, None, None), 'cin_fwd')      # ONE forward: same relu masks for both
-    for pr in (0, prec):
+    for pr in (2, prec):           # 2 = bf16x3 explicitly (0 = auto resolves to the fp16 kernels at this shape)
         grad.zero_()
         dw.zero_()
         for phase in (1, 2):
