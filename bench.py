@@ -500,7 +500,9 @@ def main():
                                     'roofline kernel timing evicts L2 by reading a 512 MB buffer between launches'},
             'e2e': {'value': rows / secs_e2e, 'unit': 'rows/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                     'ms_per_step': secs_e2e / args.steps * 1e3},
-            'gpu_launches': int(launches), 'roofline': roof, 'clocks': clocks, 'final_loss': loss,
+            'gpu_launches': int(launches),
+            'cuda_graph': bool(getattr(model, '_graphs', None)) and not getattr(model, '_graph_failed', False),
+            'roofline': roof, 'clocks': clocks, 'final_loss': loss,
             'score_only': score,
         }
         if world == 1 and not args.no_cpu_baseline:

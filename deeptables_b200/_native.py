@@ -29,6 +29,7 @@ _SIGNATURES = {
     'dtb_last_error': (c_char_p, []),
     'dtb_device_sm_count': (c_int, [_IP]),
     'dtb_launch_count': (c_longlong, []),
+    'dtb_launch_count_add': (None, [c_longlong]),
     'dtb_embedding_gather': (c_int, [P, P, P, P, c_int, c_int, c_int, P, P]),
     'dtb_embedding_scatter_add': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_fm_linear_fwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
@@ -48,6 +49,10 @@ _SIGNATURES = {
                                       c_int, c_int, c_int, P]),
     'dtb_adam_rows_apply': (c_int, [P, P, P, P, P, P, P, P, c_int, c_double, c_double, c_float,
                                     c_int, c_int, c_int, P]),
+    'dtb_adam_dense_dev': (c_int, [P, P, P, P, c_int64, P, P, c_double, c_double, c_float, c_int, P]),
+    'dtb_adam_rows_catchup_dev': (c_int, [P, P, P, P, P, P, P, P, c_double, c_double, c_float, c_int, c_int, c_int, P]),
+    'dtb_adam_rows_apply_dev': (c_int, [P, P, P, P, P, P, P, P, P, c_double, c_double, c_float, c_int, c_int, c_int, P]),
+    'dtb_step_increment': (c_int, [P, P]),
     'dtb_adam_rows_flush': (c_int, [P, P, P, P, P, c_int, c_double, c_double, c_float, c_int64, c_int, P]),
     'dtb_grad_rows_pack': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_grad_rows_unpack': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),

@@ -57,7 +57,11 @@ __global__ void adam_rows_kernel(const int32_t* __restrict__ idx, const int64_t*
                                  float* __restrict__ table, float* __restrict__ m, float* __restrict__ v,
                                  float* __restrict__ grad, int32_t* __restrict__ last_step,
                                  const float* __restrict__ alpha_table, int step, float omb1, float omb2,
-                                 float eps, int B, int F, int D) {
+                                 float eps, int B, int F, int D, const int32_t* __restrict__ step_dev) {
+  // CUDA-graph form: the step comes from device memory (`step` is then the offset: 0 = catch up to the steps done so
+  // far, 1 = apply the next one)
+  if (step_dev) step += *step_dev;
+  if (step <= 0) return;
   const int Q = D >> 2;                      // lanes per row (power of two <= 32, checked by the host)
   const int64_t total = (int64_t)B * F * Q;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -158,7 +162,47 @@ int dtb_adam_rows_catchup(const int32_t* idx, const int64_t* row_offsets, float*
   const int64_t total = (int64_t)B * F * (D / 4);
   adam_rows_kernel<0><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
       idx, row_offsets, table, m, v, nullptr, last_step, alpha_table, upto, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, B,
-      F, D);
+      F, D, nullptr);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+// The same two kernels with the step counter in DEVICE memory (*step_dev = optimiser steps completed so far): catch-up
+// to *step_dev, apply step *step_dev + 1.  For train steps captured in a CUDA graph.
+int dtb_adam_rows_catchup_dev(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
+                              int32_t* last_step, const float* alpha_table, const int32_t* step_dev, double beta1,
+                              double beta2, float eps, int B, int F, int D, void* stream) {
+  DTB_CHECK_ARG(idx && row_offsets && table && m && v && last_step && alpha_table && step_dev, "NULL argument");
+  DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128) for the row-wise Adam");
+  if (B <= 0 || F <= 0) return DTB_OK;
+  const int64_t total = (int64_t)B * F * (D / 4);
+  adam_rows_kernel<0><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      idx, row_offsets, table, m, v, nullptr, last_step, alpha_table, 0, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, B, F,
+      D, step_dev);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_adam_rows_apply_dev(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
+                            float* grad_table, int32_t* last_step, const float* alpha_table, const int32_t* step_dev,
+                            double beta1, double beta2, float eps, int B, int F, int D, void* stream) {
+  DTB_CHECK_ARG(idx && row_offsets && table && m && v && grad_table && last_step && alpha_table && step_dev,
+                "NULL argument");
+  DTB_CHECK_ARG(rows_shape_ok(D), "embedding dim must be 4*2^k (<=128) for the row-wise Adam");
+  if (B <= 0 || F <= 0) return DTB_OK;
+  const int64_t total = (int64_t)B * F * (D / 4);
+  adam_rows_kernel<1><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
+      idx, row_offsets, table, m, v, grad_table, last_step, alpha_table, 1, (float)(1.0 - beta1), (float)(1.0 - beta2), eps, B,
+      F, D, step_dev);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+__global__ void step_increment_kernel(int32_t* step_dev) { *step_dev += 1; }
+
+int dtb_step_increment(int32_t* step_dev, void* stream) {
+  DTB_CHECK_ARG(step_dev, "NULL argument");
+  step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }
@@ -174,7 +218,7 @@ int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* t
   const int64_t total = (int64_t)B * F * (D / 4);
   adam_rows_kernel<1><<<rows_grid(total), 256, 0, (cudaStream_t)stream>>>(
       idx, row_offsets, table, m, v, grad_table, last_step, alpha_table, step, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
-      B, F, D);
+      B, F, D, nullptr);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -521,7 +521,11 @@ __global__ void __launch_bounds__(kT2Threads, 1) cin_tc2_dgrad_kernel(const __gr
         if (q == 0) {
           // wgrad folds 1/t_m into its on-the-fly operand: one float per row in the unused "lo" slot of the row's
           // 16-row tile block; the layer's max|dC| bound goes to the statistics words (slot 8 + k)
-          *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * tc2_dc_blk(L) + 32 * L + (t & 15) * 4) = inv_t;
+          // a row whose bound is zero has dC == 0: it must contribute NOTHING.  With 1/t_m = 1 (the scale of a zero bound)
+          // its operand x0 h G would overflow fp16 to inf and inf * 0 = NaN poisoned the whole filter gradient (found
+          // on the five-net config, where rows with an exactly zero upstream gradient exist)
+          *reinterpret_cast<float*>(p.dc_tiles + p.dc_off[k] + (m_pad >> 4) * tc2_dc_blk(L) + 32 * L + (t & 15) * 4) =
+              bound > 0.f ? inv_t : 0.f;
           float wm = bound;
 #pragma unroll
           for (int off = 16; off >= 1; off >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, off));
@@ -741,7 +745,7 @@ __global__ void cin_tc2_dbias_kernel(const uint8_t* __restrict__ dc_tiles, float
 //     do ONE multiply per element (x' h) instead of three;
 //   * one MMA-issuing warp per tile; 4 operand stages (an fp16 operand block is 32 TMEM columns, not 64);
 //   * dC blocks without the unused "lo" half: 16.6 KB per 64-row stage instead of 32 KB from L2.
-constexpr int kW2Threads = 416;       // warps 0-7 producers (+ epilogue), 8/9 MMA issue tile 0/1, 10 dC loader, 11 x0/h loader, 12 scaler
+constexpr int kW2Threads = 448;       // warps 0-7 producers (+ epilogue), 8/9 MMA issue tile 0/1, 10 dC loader, 11 x0/h loader, 12/13 scalers
 constexpr int kW2Stages = 3;          // x0 / h / dC stages of 64 rows
 constexpr int kW2StagesA = 4;         // operand blocks in TMEM per tile
 
@@ -801,9 +805,9 @@ __global__ void __launch_bounds__(kW2Threads, 1) cin_tc2_wgrad_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < kW2Stages; ++s) {
       tc::mbar_init(&full_b[s], 1);
-      tc::mbar_init(&empty_b[s], 3);
+      tc::mbar_init(&empty_b[s], 4);          // two issuers + two scalers
       tc::mbar_init(&full_h[s], 1);
-      tc::mbar_init(&scaled[s], 1);
+      tc::mbar_init(&scaled[s], 2);
       tc::mbar_init(&empty_h[s], 8);
     }
     for (int i = 0; i < 2 * kW2StagesA; ++i) {
@@ -830,7 +834,11 @@ __global__ void __launch_bounds__(kW2Threads, 1) cin_tc2_wgrad_kernel(const __gr
     // ---- A producers: lane row = (il, j): A'[row, m] = x'[m, i] * h[m, j] ------------------------------------------
     const int g = warp >> 2;
     const int t = threadIdx.x & 127;
-    const int il = t / Hp, j = t - il * Hp;
+    // GEMM row t <-> (hidden field j = t / ipt, x0 field il = t % ipt): the ipt lanes that share j read the same h row
+    // (one 16-byte segment per group instead of one per lane).  This kernel is shared-memory bound -- every product
+    // needs two operands from the stage tiles -- and with the (il, j) order of cin_tc_wgrad_kernel a warp's h reads took
+    // 4 wavefronts per LDS.128; now 32 / ipt distinct segments = 2 (Hp = 64) or 1 (Hp = 32).
+    const int il = t % ipt, j = t / ipt;
     const int i = (blockIdx.x * 2 + g) * ipt + il;
     const bool live = (i < F) && (j < H);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -939,38 +947,35 @@ __global__ void __launch_bounds__(kW2Threads, 1) cin_tc2_wgrad_kernel(const __gr
     }
     __syncwarp();
   } else {
-    // ---- scaler: x'[i][m] = x0[i][m] * G / t_m for the 64 rows of the stage (lane <-> rows lane and lane + 32) -------------
+    // ---- scalers (warps 12, 13: even / odd fields): x'[i][m] = x0[i][m] * G / t_m for the 64 rows of the stage; a lane
+    //      owns rows 2 lane and 2 lane + 1 (8-byte accesses) ------------------------------------------------------------
+    const int sw = warp - 12;
     for (int s = 0; s < n_st; ++s) {
       const uint32_t sh = s % kW2Stages, ph = (s / kW2Stages) & 1;
       tc::mbar_wait(&full_h[sh], ph);
       tc::mbar_wait(&full_b[sh], ph);
       const uint8_t* bst = smem + lay.b_off + sh * lay.b_bytes;
-      const float c0 = *reinterpret_cast<const float*>(bst + (lane >> 4) * tc2_dc_blk(L) + 32 * L + (lane & 15) * 4) * gscale;
-      const float c1 = *reinterpret_cast<const float*>(bst + (2 + (lane >> 4)) * tc2_dc_blk(L) + 32 * L + (lane & 15) * 4) * gscale;
+      const float2 c = *reinterpret_cast<const float2*>(bst + (lane >> 3) * tc2_dc_blk(L) + 32 * L + (lane & 7) * 8);
+      const float c0 = c.x * gscale, c1 = c.y * gscale;
       const float* xs = reinterpret_cast<const float*>(smem + lay.x_off + sh * lay.x_bytes);
       float* xd = reinterpret_cast<float*>(smem + lay.xs_off + sh * lay.x_bytes);
-      // 8 fields at a time with all 16 loads in flight (a rolled loop was the kernel's bottleneck: one warp, one
-      // shared-memory round trip per field and stage -- 35 % of all stall samples sat on the producers' wait for it)
-      for (int i0 = 0; i0 < F; i0 += 8) {
-        float a[8], b[8];
+      // 8 fields at a time with all loads in flight (a rolled loop made this warp the kernel's bottleneck)
+      for (int i0 = sw; i0 < F; i0 += 16) {
+        float2 a[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int i = i0 + u < F ? i0 + u : F - 1;
-          a[u] = xs[i * kWgPad + lane];
-          b[u] = xs[i * kWgPad + 32 + lane];
+          const int i = i0 + 2 * u < F ? i0 + 2 * u : sw;
+          a[u] = *reinterpret_cast<const float2*>(xs + i * kWgPad + 2 * lane);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (i0 + u < F) {
-            xd[(i0 + u) * kWgPad + lane] = a[u] * c0;
-            xd[(i0 + u) * kWgPad + 32 + lane] = b[u] * c1;
-          }
-        }
+        for (int u = 0; u < 8; ++u)
+          if (i0 + 2 * u < F)
+            *reinterpret_cast<float2*>(xd + (i0 + 2 * u) * kWgPad + 2 * lane) = make_float2(a[u].x * c0, a[u].y * c1);
       }
       __syncwarp();
       if (lane == 0) {
         tc::mbar_arrive(&scaled[sh]);
-        tc::mbar_arrive(&empty_b[sh]);         // the 1/t_m words have been read (third arrival next to the two issuers)
+        tc::mbar_arrive(&empty_b[sh]);         // the 1/t_m words have been read
       }
     }
   }

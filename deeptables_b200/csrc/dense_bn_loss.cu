@@ -316,9 +316,13 @@ __global__ void dropout_kernel(const float* __restrict__ X, float* __restrict__ 
 // ------------------------------------------------------------------------------------------
 // Adam (dense)
 // ------------------------------------------------------------------------------------------
+// alpha_table / step_dev (both or neither): the step size is read from alpha_table[*step_dev + 1] -- a step captured
+// in a CUDA graph must not bake the host's step counter into its kernel arguments
 __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                   float* __restrict__ g, int64_t n, float alpha, float omb1, float omb2,
-                                  float eps, int zero_grad) {
+                                  float eps, int zero_grad, const float* __restrict__ alpha_table,
+                                  const int32_t* __restrict__ step_dev) {
+  if (step_dev) alpha = alpha_table[*step_dev + 1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * blockDim.x) {
     float pi = p[i], mi = m[i], vi = v[i];
@@ -334,7 +338,9 @@ __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, 
 // optimiser at world >= 4) is HBM-bound and scalar accesses leave bandwidth on the table.
 __global__ void adam_dense_vec4_kernel(float4* __restrict__ p, float4* __restrict__ m, float4* __restrict__ v,
                                        float4* __restrict__ g, int64_t n4, float alpha, float omb1, float omb2,
-                                       float eps, int zero_grad) {
+                                       float eps, int zero_grad, const float* __restrict__ alpha_table,
+                                       const int32_t* __restrict__ step_dev) {
+  if (step_dev) alpha = alpha_table[*step_dev + 1];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     float4 p4 = p[i], m4 = m[i], v4 = v[i];
@@ -504,9 +510,8 @@ int dtb_dropout(const float* X, float* Y, int64_t n, float rate, unsigned long l
   return DTB_OK;
 }
 
-int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, double beta1, double beta2,
-                   float eps, int zero_grad, void* stream) {
-  DTB_CHECK_ARG(p && m && v && g, "NULL argument");
+static int adam_dense_impl(float* p, float* m, float* v, float* g, int64_t n, float alpha, const float* alpha_table,
+                           const int32_t* step_dev, double beta1, double beta2, float eps, int zero_grad, void* stream) {
   if (n <= 0) return DTB_OK;
   // keras multiplies by the python double (1 - beta) rounded to fp32, not by 1.f - float(beta)
   const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2);
@@ -516,16 +521,29 @@ int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alph
   if (n4 > 0) {
     adam_dense_vec4_kernel<<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
-        reinterpret_cast<float4*>(g), n4, alpha, omb1, omb2, eps, zero_grad);
+        reinterpret_cast<float4*>(g), n4, alpha, omb1, omb2, eps, zero_grad, alpha_table, step_dev);
     DTB_LAUNCH_OK();
   }
   const int64_t done = n4 * 4;
   if (done < n) {
     adam_dense_kernel<<<ew_grid(n - done), 256, 0, (cudaStream_t)stream>>>(p + done, m + done, v + done, g + done,
-                                                                           n - done, alpha, omb1, omb2, eps, zero_grad);
+                                                                           n - done, alpha, omb1, omb2, eps, zero_grad,
+                                                                           alpha_table, step_dev);
     DTB_LAUNCH_OK();
   }
   return DTB_OK;
+}
+
+int dtb_adam_dense(float* p, float* m, float* v, float* g, int64_t n, float alpha, double beta1, double beta2,
+                   float eps, int zero_grad, void* stream) {
+  DTB_CHECK_ARG(p && m && v && g, "NULL argument");
+  return adam_dense_impl(p, m, v, g, n, alpha, nullptr, nullptr, beta1, beta2, eps, zero_grad, stream);
+}
+
+int dtb_adam_dense_dev(float* p, float* m, float* v, float* g, int64_t n, const float* alpha_table,
+                       const int32_t* step_dev, double beta1, double beta2, float eps, int zero_grad, void* stream) {
+  DTB_CHECK_ARG(p && m && v && g && alpha_table && step_dev, "NULL argument");
+  return adam_dense_impl(p, m, v, g, n, 0.f, alpha_table, step_dev, beta1, beta2, eps, zero_grad, stream);
 }
 
 }  // extern "C"

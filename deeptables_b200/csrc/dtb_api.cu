@@ -38,6 +38,9 @@ int dtb_version(void) { return 200; }
 
 long long dtb_launch_count(void) { return dtb::g_launches.load(); }
 
+// a replayed CUDA graph launches the kernels that were counted once at capture time: the host adds them per replay
+void dtb_launch_count_add(long long n) { dtb::g_launches.fetch_add(n, std::memory_order_relaxed); }
+
 const char* dtb_last_error(void) { return dtb::g_err; }
 
 int dtb_device_sm_count(int* out_host) {

@@ -182,6 +182,9 @@ class DeepModel:
         self.table = None
         self._loss_acc = None
         self._alpha = None
+        self._step_dev = None              # optimiser step counter in device memory (CUDA-graph replay of the train step)
+        self._graphs = {}
+        self._graph_failed = False
         if model_file is not None:
             self._load_model(model_file)
 
@@ -340,9 +343,17 @@ class DeepModel:
             t.last_step.fill_(self._step)
             t.lazy_active = True
 
-    def _catch_up(self, cat, upto):
+    def _catch_up(self, cat, upto, dev_step=False):
         t = self.table
-        if t is None or not t.lazy_active or t.last_step is None or upto <= 0:
+        if t is None or not t.lazy_active or t.last_step is None:
+            return
+        if dev_step:          # CUDA-graph form: "steps done so far" is read from device memory
+            check(N.lib.dtb_adam_rows_catchup_dev(ptr(cat), ptr(t.row_offsets), ptr(t.weight), ptr(t.m), ptr(t.v),
+                                                  ptr(t.last_step), ptr(self._alpha), ptr(self._step_dev), E.ADAM_B1,
+                                                  E.ADAM_B2, E.ADAM_EPS, cat.shape[0], t.n_fields, t.dim, stream_ptr()),
+                  'adam_rows_catchup_dev')
+            return
+        if upto <= 0:
             return
         check(N.lib.dtb_adam_rows_catchup(ptr(cat), ptr(t.row_offsets), ptr(t.weight), ptr(t.m), ptr(t.v),
                                           ptr(t.last_step), ptr(self._alpha_table(upto)), upto, E.ADAM_B1,
@@ -351,13 +362,26 @@ class DeepModel:
 
     def train_step(self, cat, cont, y, sample_weight=None):
         """forward + loss + backward + (DP exchange) + Adam on one device-resident batch.
-        Returns the batch predictions; the summed loss accumulates in ``self._loss_acc``."""
+        Returns the batch predictions; the summed loss accumulates in ``self._loss_acc``.
+
+        Single-GPU steps without dropout or sample weights are captured ONCE per batch shape in a CUDA graph and replayed
+        (``DTB_CUDA_GRAPH=0`` disables it): a step is ~90 launches of kernels that take microseconds at small batch sizes
+        (DeepFM at 8 192 rows), where the host's launch path -- not the GPU -- would set the pace."""
+        if self._graph_eligible(cat, cont, y, sample_weight):
+            return self._train_step_graphed(cat, cont, y)
+        prob = self._train_step_body(cat, cont, y, sample_weight, dev_step=False)
+        self._step += 1
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
+        return prob
+
+    def _train_step_body(self, cat, cont, y, sample_weight, dev_step):
         scope = self._scope
         t = self.table
         if t is not None:
             t.ensure_training_state()
             self._select_table_optimizer(self.world_size * cat.shape[0] * t.n_fields)
-            self._catch_up(cat, self._step)
+            self._catch_up(cat, self._step, dev_step)
         if t is not None:
             t.pending_bwd = 0
             t.on_grad_final = (lambda: self._begin_table_exchange(cat)) if (self._dist and t.lazy_adam) else None
@@ -367,10 +391,26 @@ class DeepModel:
         dp.scale_for_mean(dz)
         z.backward(dz)
         step = self._step + 1
-        alpha = E.adam_alpha(step)
         union_cat = cat
         if self._dist:
             union_cat = self._exchange_gradients(cat)
+        if dev_step:
+            check(N.lib.dtb_adam_dense_dev(ptr(scope.flat_p), ptr(scope.flat_m), ptr(scope.flat_v), ptr(scope.flat_g),
+                                           scope.flat_p.numel(), ptr(self._alpha), ptr(self._step_dev), E.ADAM_B1,
+                                           E.ADAM_B2, E.ADAM_EPS, 1, stream_ptr()), 'adam_dense_dev')
+            if t is not None:
+                if t.lazy_active:
+                    check(N.lib.dtb_adam_rows_apply_dev(ptr(union_cat), ptr(t.row_offsets), ptr(t.weight), ptr(t.m), ptr(t.v),
+                                                        ptr(t.grad), ptr(t.last_step), ptr(self._alpha), ptr(self._step_dev),
+                                                        E.ADAM_B1, E.ADAM_B2, E.ADAM_EPS, union_cat.shape[0], t.n_fields,
+                                                        t.dim, stream_ptr()), 'adam_rows_apply_dev')
+                else:
+                    check(N.lib.dtb_adam_dense_dev(ptr(t.weight), ptr(t.m), ptr(t.v), ptr(t.grad), t.weight.numel(),
+                                                   ptr(self._alpha), ptr(self._step_dev), E.ADAM_B1, E.ADAM_B2, E.ADAM_EPS, 1,
+                                                   stream_ptr()), 'adam_dense_dev(table)')
+            check(N.lib.dtb_step_increment(ptr(self._step_dev), stream_ptr()), 'step_increment')
+            return prob
+        alpha = E.adam_alpha(step)
         check(N.lib.dtb_adam_dense(ptr(scope.flat_p), ptr(scope.flat_m), ptr(scope.flat_v), ptr(scope.flat_g),
                                    scope.flat_p.numel(), alpha, E.ADAM_B1, E.ADAM_B2, E.ADAM_EPS, 1,
                                    stream_ptr()), 'adam_dense')
@@ -385,7 +425,72 @@ class DeepModel:
                 check(N.lib.dtb_adam_dense(ptr(t.weight), ptr(t.m), ptr(t.v), ptr(t.grad), t.weight.numel(),
                                            alpha, E.ADAM_B1, E.ADAM_B2, E.ADAM_EPS, 1, stream_ptr()),
                       'adam_dense(table)')
-        self._step = step
+        return prob
+
+    # ---- CUDA-graph replay of the train step ---------------------------------------------------------------------------
+    def _has_dropout(self):
+        cfg = self.config
+        if cfg.embedding_dropout or cfg.dense_dropout:
+            return True
+        if any(float(u[1]) > 0 for u in (cfg.dnn_params or {}).get('hidden_units', ())):
+            return True
+        return bool((cfg.autoint_params or {}).get('dropout_rate', 0)) and 'autoint_nets' in cfg.nets
+
+    def _graph_eligible(self, cat, cont, y, sample_weight):
+        if self._dist or sample_weight is not None or os.environ.get('DTB_CUDA_GRAPH', '1') == '0':
+            return False
+        if self._graph_failed or self._step < 1:       # the first step runs eagerly (allocations, lazy initialisation)
+            return False
+        if getattr(self, '_no_graph', None) is None:
+            self._no_graph = self._has_dropout() or any(callable(n) for n in self.config.nets)
+        return not self._no_graph
+
+    def _train_step_graphed(self, cat, cont, y):
+        t = self.table
+        key = (None if cat is None else tuple(cat.shape), None if cont is None else tuple(cont.shape), tuple(y.shape),
+               None if t is None else t.lazy_active)
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if self._alpha is None or self._alpha.numel() <= self._step + 2:
+            self._graphs.clear()                       # the alpha table moves when it grows: captured pointers are stale
+            self._alpha_table(self._step + 200000)
+        if t is not None:
+            t.ensure_training_state()
+            self._select_table_optimizer(cat.shape[0] * t.n_fields)
+            key = key[:3] + (t.lazy_active,)
+        entry = self._graphs.get(key)
+        if entry is None:
+            sc = None if cat is None else torch.empty_like(cat)
+            sx = None if cont is None else torch.empty_like(cont)
+            sy = torch.empty_like(y)
+            self._step_dev.fill_(self._step)
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                l0 = N.lib.dtb_launch_count()
+                with torch.cuda.graph(graph):
+                    prob = self._train_step_body(sc, sx, sy, None, dev_step=True)
+                n_launch = N.lib.dtb_launch_count() - l0          # kernels of this library inside one replay
+            except Exception as exc:                       # capture unsupported here: say so once, run eagerly from now on
+                self._graph_failed = True
+                import warnings
+                warnings.warn(f'deeptables_b200: CUDA-graph capture of the train step failed ({type(exc).__name__}: {exc}); '
+                              f'continuing with eager launches')
+                torch.cuda.synchronize()
+                prob = self._train_step_body(cat, cont, y, None, dev_step=False)
+                self._step += 1
+                return prob
+            N.lib.dtb_launch_count_add(-n_launch)                # counted at capture, not executed yet
+            entry = self._graphs[key] = (graph, sc, sx, sy, prob, n_launch)
+        graph, sc, sx, sy, prob, n_launch = entry
+        if sc is not None:
+            sc.copy_(cat)
+        if sx is not None:
+            sx.copy_(cont)
+        sy.copy_(y)
+        graph.replay()
+        N.lib.dtb_launch_count_add(n_launch)
+        self._step += 1
         return prob
 
     def _row_exchange_fns(self, cat):
@@ -778,6 +883,8 @@ class DeepModel:
             self._step = step
         else:
             self._step = 0
+        if self._step_dev is not None:
+            self._step_dev.fill_(self._step)
 
     def release(self):
         self.model = None

@@ -46,6 +46,8 @@ const char* dtb_last_error(void);
 int dtb_device_sm_count(int* out_host);
 /* number of kernels this library has launched so far (every kernel on the path is hand-written) */
 long long dtb_launch_count(void);
+/* kernels launched by replaying a CUDA graph captured through this library (counted once at capture): added per replay */
+void dtb_launch_count_add(long long n);
 
 /* ---- MultiColumnEmbedding (layers.py:889-904) ------------------------------------------- */
 /* out[B,F,D] = table rows; the materialising form used by custom nets / tests. */
@@ -149,6 +151,18 @@ int dtb_adam_rows_apply(const int32_t* idx, const int64_t* row_offsets, float* t
 int dtb_adam_rows_flush(float* table, float* m, float* v, int32_t* last_step,
                         const float* alpha_table, int upto, double beta1, double beta2, float eps,
                         int64_t n_rows, int D, void* stream);
+/* CUDA-graph forms: the optimiser step counter lives in DEVICE memory (*step_dev = steps completed so far), so a
+ * captured train step replays with the right bias correction: dense = step *step_dev + 1 with alpha_table[*step_dev + 1];
+ * rows catch-up to *step_dev; rows apply = step *step_dev + 1; dtb_step_increment bumps the counter at the end. */
+int dtb_adam_dense_dev(float* p, float* m, float* v, float* g, int64_t n, const float* alpha_table,
+                       const int32_t* step_dev, double beta1, double beta2, float eps, int zero_grad, void* stream);
+int dtb_adam_rows_catchup_dev(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
+                              int32_t* last_step, const float* alpha_table, const int32_t* step_dev, double beta1,
+                              double beta2, float eps, int B, int F, int D, void* stream);
+int dtb_adam_rows_apply_dev(const int32_t* idx, const int64_t* row_offsets, float* table, float* m, float* v,
+                            float* grad_table, int32_t* last_step, const float* alpha_table, const int32_t* step_dev,
+                            double beta1, double beta2, float eps, int B, int F, int D, void* stream);
+int dtb_step_increment(int32_t* step_dev, void* stream);
 
 /* Data-parallel exchange of the embedding gradient by rows (deepmodel.py:88-103: MirroredStrategy
  * exchanges embedding gradients as IndexedSlices too).  pack: every (b,f) reference claims its row once

@@ -167,8 +167,8 @@ def test_ctypes_signatures_match_the_header_prototypes():
         for k, (c_decl, ct) in enumerate(zip(params, argtypes)):
             assert classify_c(c_decl) == classify_ct(ct), f'{name} arg {k} ({c_decl!r}) bound as {ct}'
         ret = ret.replace('extern', '').replace('"C"', '').strip()
-        want = 'ptr' if '*' in ret else classify_c(ret + ' x')
-        got = 'ptr' if res in (ctypes.c_char_p, ctypes.c_void_p) else classify_ct(res)
+        want = 'ptr' if '*' in ret else ('void' if ret == 'void' else classify_c(ret + ' x'))
+        got = 'void' if res is None else ('ptr' if res in (ctypes.c_char_p, ctypes.c_void_p) else classify_ct(res))
         assert want == got, f'{name}: return type {ret!r} bound as {res}'
     assert seen == set(nat._SIGNATURES), sorted(set(nat._SIGNATURES) ^ seen)
 

@@ -29,6 +29,30 @@ cont[half:] = cont[:half]
 y = (torch.rand(b, generator=g) < 0.25).float()
 d_idx, d_cont, d_y = idx.cuda(), cont.cuda(), y.cuda().view(-1, 1)
 scope, t = model._scope, model.table
+_orig_bwd = E.CINFn.backward
+
+
+def _spy(ctx, g_):
+    ws, saved = ctx.ws, ctx.saved_buf
+    out = _orig_bwd(ctx, g_)
+    torch.cuda.synchronize()
+    m_pad = ((b + 15) // 16) * 256
+    wpack = 26 * 128 * (32 + 64 + 64) * 4
+    dc = 3 * (m_pad // 16) * 64 * 128
+    end = wpack + 1024 + dc + 1024
+    st_i = ws[end - 256:end].view(torch.int32)
+    st_f = ws[end - 256:end].view(torch.float32)
+    print('   stats words: max|W_k|', [f'{float(v):.3e}' for v in st_f[0:3]], ' max|dC_k| bound', [f'{float(v):.3e}' for v in st_f[8:11]],
+          ' max|x0|', f'{float(st_f[16]):.3e}', ' max|h_k|', [f'{float(v):.3e}' for v in st_f[24:27]], flush=True)
+    print('   forward maxima (saved head):', [f'{float(v):.3e}' for v in saved[:16].view(torch.float32)], flush=True)
+    print('   d_pooled: max', f'{float(g_.abs().max()):.3e}', 'finite', bool(torch.isfinite(g_).all()),
+          ' dW finite per layer', [bool(torch.isfinite(x).all()) for x in out[1].split([676 * 128, 1664 * 128, 1664 * 128])], flush=True)
+    dpm = ws[end:end + b * 8 * 4].view(torch.float32).view(b, 8)[:, :3]
+    print('   dpmax: min', [f'{float(v):.3e}' for v in dpm.min(0).values], 'max', [f'{float(v):.3e}' for v in dpm.max(0).values], flush=True)
+    return out
+
+
+E.CINFn.backward = staticmethod(_spy)
 orig_adam = E.N.lib.dtb_adam_dense
 for step in range(4):
     model._loss_acc.zero_()
