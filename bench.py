@@ -71,6 +71,7 @@ def parse_args():
     ap.add_argument('--cpu-sample-rows', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cin-precision', type=int, default=0)
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of the CUDA-graph replay of the train step')
     ap.add_argument('--cin-exp', type=int, default=0,
                     help='profiling only: experiment build of the CIN backward kernels (cin_tc.cu), 0 = product kernels')
     ap.add_argument('--id-dist', default='uniform', choices=['uniform', 'zipf'],
@@ -387,6 +388,8 @@ def main():
     if args.impl == 'reference':
         run_reference(args)
         return
+    if args.no_graph:
+        os.environ['DTB_CUDA_GRAPH'] = '0'
     import torch
     import torch.distributed as dist
     world = int(os.environ.get('WORLD_SIZE', '1'))

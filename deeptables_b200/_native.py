@@ -96,9 +96,18 @@ def last_error():
     return msg.decode() if msg else ''
 
 
+_DEBUG_CAPTURE = os.environ.get('DTB_DEBUG_CAPTURE', '') == '1'
+
+
 def check(rc, what=''):
     if rc != 0:
         raise RuntimeError(f'deeptables_b200 native call {what} failed (code {rc}): {last_error()}')
+    if _DEBUG_CAPTURE:          # debug aid: name the first native call after which a stream capture is no longer valid
+        import torch
+        try:
+            torch.cuda.is_current_stream_capturing()
+        except Exception as exc:
+            raise RuntimeError(f'stream capture invalid right after native call {what!r}: {exc}') from exc
 
 
 def ptr(t):

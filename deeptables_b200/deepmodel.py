@@ -122,6 +122,54 @@ class _Scope:
         self.frozen = True
 
 
+class _HostBatches:
+    """Input pipeline for data sets that should not (or cannot) live in HBM: the encoded columns stay in PINNED host
+    memory, a batch is gathered on the host into one of two pinned staging buffers and copied on a side stream while the
+    previous step computes (double buffering).  Replaces the reference's ``tf.data`` path (utils/dataset_generator.py:36-72,
+    241-257: ``from_tensor_slices`` over ``.tolist()`` of the whole frame, shuffle buffer = N, batch, prefetch); the default
+    path keeps the whole encoded data set in HBM (160 B/row at the Criteo shape: 10 M rows = 1.6 GB of 180 GB)."""
+
+    def __init__(self, device, *tensors):
+        self.device = device
+        self.src = [None if t is None else t.contiguous().pin_memory() for t in tensors]
+        self.stream = torch.cuda.Stream(device=device)
+        self.slots = [None, None]
+        self.k = 0
+
+    def prefetch(self, sel):
+        """Start the gather + copy of the rows ``sel`` (CPU int64 tensor); returns a handle for ``get``."""
+        slot = self.k & 1
+        self.k += 1
+        n = sel.numel()
+        if self.slots[slot] is None or self.slots[slot][0] < n:
+            self.slots[slot] = (n, [None if t is None else torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                                    for t in self.src], None)
+        _, stage, prev = self.slots[slot]
+        if prev is not None:
+            prev.synchronize()                    # the copy that last used this staging buffer has finished
+        outs = []
+        with torch.cuda.stream(self.stream):
+            for t, st in zip(self.src, stage):
+                if t is None:
+                    outs.append(None)
+                    continue
+                torch.index_select(t, 0, sel, out=st[:n])
+                outs.append(st[:n].to(self.device, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.slots[slot] = (self.slots[slot][0], stage, ev)
+        return outs, ev
+
+    @staticmethod
+    def get(handle):
+        outs, ev = handle
+        torch.cuda.current_stream().wait_event(ev)
+        for o in outs:
+            if o is not None:
+                o.record_stream(torch.cuda.current_stream())
+        return outs
+
+
 class KerasLikeModel:
     """What ``DeepModel.model`` holds: the built network (parameters + forward)."""
 
@@ -545,8 +593,9 @@ class DeepModel:
     # ------------------------------------------------------------------------------------------
     # host <-> device input plumbing  (replaces utils/dataset_generator.py:36-72)
     # ------------------------------------------------------------------------------------------
-    def _to_device_inputs(self, X):
-        """DataFrame / dict of arrays -> (cat int32 [N,F] | None, cont float32 [N,C] | None)."""
+    def _to_device_inputs(self, X, device=None):
+        """DataFrame / dict of arrays -> (cat int32 [N,F] | None, cont float32 [N,C] | None) on ``device`` (default: the GPU)."""
+        device = self.device if device is None else device
         cat = cont = None
         if self.n_fields:
             names = [c.name for c in self.categorical_columns]
@@ -555,21 +604,22 @@ class DeepModel:
                 # the reference ships ids as float32 and casts back (dataset_generator.py:41-42,
                 # layers.py:893-895); exact below 2**24
                 arr = arr.astype(np.int64)
-            cat = torch.as_tensor(np.ascontiguousarray(arr.astype(np.int32))).to(self.device, non_blocking=True)
+            cat = torch.as_tensor(np.ascontiguousarray(arr.astype(np.int32))).to(device, non_blocking=True)
         if self.n_cont:
             parts = [_columns(X, c.column_names).astype(np.float32) for c in self.continuous_columns]
             arr = parts[0] if len(parts) == 1 else np.concatenate(parts, axis=1)
-            cont = torch.as_tensor(np.ascontiguousarray(arr)).to(self.device, non_blocking=True)
+            cont = torch.as_tensor(np.ascontiguousarray(arr)).to(device, non_blocking=True)
         return cat, cont
 
-    def _to_device_labels(self, y):
+    def _to_device_labels(self, y, device=None):
+        device = self.device if device is None else device
         y = np.asarray(y)
         if self.task == consts.TASK_MULTICLASS:
             onehot = np.zeros((len(y), self.num_classes), dtype=np.float32)
             onehot[np.arange(len(y)), y.astype(np.int64).reshape(-1)] = 1.0
             y = onehot
         y = y.astype(np.float32).reshape(len(y), -1)
-        return torch.as_tensor(np.ascontiguousarray(y)).to(self.device, non_blocking=True)
+        return torch.as_tensor(np.ascontiguousarray(y)).to(device, non_blocking=True)
 
     def train_on_batch(self, x_cat, x_cont, y, sample_weight=None):
         """Public per-batch entry (Keras ``Model.train_on_batch`` analogue): HOST arrays/tensors in,
@@ -623,19 +673,31 @@ class DeepModel:
             agreed = torch.tensor([steps_per_epoch], dtype=torch.int64, device=self.device)
             torch.distributed.all_reduce(agreed, op=torch.distributed.ReduceOp.MIN)
             steps_per_epoch = int(agreed.item())
-        cat, cont = self._to_device_inputs(X)
-        yd = self._to_device_labels(y)
+        # where the training rows live: HBM (default) or pinned host memory behind a double-buffered loader
+        # (DTB_DATA_ON_HOST=1, or automatically when the encoded data set would take more than a quarter of the free HBM)
+        row_bytes = 4 * (self.n_fields + self.n_cont + (self.num_classes if self.task == consts.TASK_MULTICLASS else 1))
+        free_hbm = torch.cuda.mem_get_info(self.device)[0]
+        on_host = os.environ.get('DTB_DATA_ON_HOST', '') == '1' or n * row_bytes > free_hbm // 4
+        if on_host:
+            cat, cont = self._to_device_inputs(X, device='cpu')
+            yd = self._to_device_labels(y, device='cpu')
+        else:
+            cat, cont = self._to_device_inputs(X)
+            yd = self._to_device_labels(y)
         vcat, vcont = self._to_device_inputs(X_val)
         vy = self._to_device_labels(y_val)
         sw = None
         if class_weight is not None:
-            cw = torch.ones(int(max(class_weight)) + 1, dtype=torch.float32, device=self.device)
+            cw = torch.ones(int(max(class_weight)) + 1, dtype=torch.float32)
             for k, v in class_weight.items():
                 cw[int(k)] = float(v)
-            sw = cw[np.asarray(y).astype(np.int64).reshape(-1)]
+            sw = cw[torch.as_tensor(np.asarray(y).astype(np.int64).reshape(-1))]
         if sample_weight is not None:
-            s2 = torch.as_tensor(np.asarray(sample_weight, dtype=np.float32)).to(self.device)
+            s2 = torch.as_tensor(np.asarray(sample_weight, dtype=np.float32))
             sw = s2 if sw is None else sw * s2
+        if sw is not None and not on_host:
+            sw = sw.to(self.device)
+        loader = _HostBatches(self.device, cat, cont, yd, sw) if on_host else None
 
         history = History()
         callbacks = list(callbacks or [])
@@ -652,19 +714,31 @@ class DeepModel:
         for epoch in range(initial_epoch, epochs):
             for cb in callbacks:
                 _call(cb, 'on_epoch_begin', epoch, None)
-            perm = torch.randperm(n, device=self.device) if shuffle else torch.arange(n, device=self.device)
+            pdev = 'cpu' if on_host else self.device
+            perm = torch.randperm(n, device=pdev) if shuffle else torch.arange(n, device=pdev)
             self._loss_acc.zero_()
             seen = 0
             probs, targets = [], []
-            for step in range(steps_per_epoch):
+
+            def rows_of(step):
                 lo = (step * batch_size) % max(n, 1)
                 sel = perm[lo:lo + batch_size]
                 if drop_remainder and sel.numel() < batch_size:
                     sel = perm[:batch_size]
-                bc = cat[sel] if cat is not None else None
-                bx = cont[sel] if cont is not None else None
-                by = yd[sel]
-                bw = sw[sel] if sw is not None else None
+                return sel
+
+            pending = loader.prefetch(rows_of(0)) if on_host and steps_per_epoch > 0 else None
+            for step in range(steps_per_epoch):
+                if on_host:
+                    bc, bx, by, bw = loader.get(pending)
+                    if step + 1 < steps_per_epoch:
+                        pending = loader.prefetch(rows_of(step + 1))      # next batch travels while this step computes
+                else:
+                    sel = rows_of(step)
+                    bc = cat[sel] if cat is not None else None
+                    bx = cont[sel] if cont is not None else None
+                    by = yd[sel]
+                    bw = sw[sel] if sw is not None else None
                 p = self.train_step(bc, bx, by, bw)
                 seen += by.shape[0]
                 if metric_fns:

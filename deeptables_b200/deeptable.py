@@ -204,6 +204,35 @@ class DefaultPreprocessor:
         return list(self._cont_names)
 
 
+def _calc_scores(y_true, y_pred, y_proba, task, metrics, pos_label, classes):
+    """Scores of one fold for ``oof_metrics`` (the reference delegates to hypernets' calc_score): metric name -> value."""
+    from sklearn import metrics as M
+    out = {}
+    for m in metrics:
+        key = (m if isinstance(m, str) else getattr(m, '__name__', str(m))).lower()
+        if key in ('auc', 'roc_auc'):
+            out[key] = M.roc_auc_score(y_true, y_proba[:, -1]) if task == consts.TASK_BINARY else \
+                M.roc_auc_score(y_true, y_proba, multi_class='ovo', labels=classes)
+        elif key in ('accuracy', 'acc'):
+            out[key] = M.accuracy_score(y_true, y_pred)
+        elif key in ('f1', 'f1_score'):
+            out[key] = M.f1_score(y_true, y_pred, pos_label=pos_label) if task == consts.TASK_BINARY else \
+                M.f1_score(y_true, y_pred, average='macro')
+        elif key in ('logloss', 'log_loss'):
+            out[key] = M.log_loss(y_true, y_proba, labels=classes)
+        elif key in ('mse', 'mean_squared_error'):
+            out[key] = M.mean_squared_error(y_true, y_pred)
+        elif key in ('rmse',):
+            out[key] = float(np.sqrt(M.mean_squared_error(y_true, y_pred)))
+        elif key in ('mae', 'mean_absolute_error'):
+            out[key] = M.mean_absolute_error(y_true, y_pred)
+        elif key in ('r2', 'r2_score'):
+            out[key] = M.r2_score(y_true, y_pred)
+        else:
+            raise NotImplementedError(f'oof metric {m!r}')
+    return out
+
+
 class DeepTable:
     """Reference user API (deeptable.py:27-330 docstring surface)."""
 
@@ -271,6 +300,92 @@ class DeepTable:
         self.__current_model = model
         return model, history
 
+    def fit_cross_validation(self, X, y, X_eval=None, X_test=None, num_folds=5, stratified=False, iterators=None,
+                             batch_size=None, epochs=1, verbose=1, callbacks=None, n_jobs=1, random_state=9527,
+                             shuffle=True, class_weight=None, sample_weight=None, initial_epoch=0, steps_per_epoch=None,
+                             validation_steps=None, validation_freq=1, max_queue_size=10, workers=1,
+                             use_multiprocessing=False, oof_metrics=None):
+        """K-fold training with out-of-fold probabilities (reference deeptable.py:373-517).  One model per fold is fitted on
+        the fold's training rows with the held-out rows as validation data, scores the held-out rows (-> the out-of-fold
+        matrix), X_eval and X_test (-> fold means), is saved next to the run's outputs and registered in the model set as
+        ``<nets>-kfold-<n>`` (``predict(..., model_selector='all')`` averages them).  Returns
+        ``(oof_proba, eval_proba_mean, test_proba_mean[, oof_scores])`` with binary probabilities as ``[1-p, p]`` columns.
+        The folds run one after the other on this process' GPU (``n_jobs`` is accepted for signature parity)."""
+        from sklearn.model_selection import KFold, StratifiedKFold
+        self.__modelset.clear()
+        X, y = self.preprocessor.fit_transform(X, y)
+        if X_eval is not None:
+            X_eval = self.preprocessor.transform_X(X_eval)
+        if X_test is not None:
+            X_test = self.preprocessor.transform_X(X_test)
+        if iterators is None:
+            if stratified and self.task != consts.TASK_REGRESSION:
+                iterators = StratifiedKFold(n_splits=num_folds, shuffle=True, random_state=random_state)
+            else:
+                iterators = KFold(n_splits=num_folds, shuffle=True, random_state=random_state)
+        y = np.array(y)
+        n_rows = X.shape[0]
+        width = self.num_classes if self.task in (consts.TASK_MULTICLASS, consts.TASK_MULTILABEL) else 1
+        oof_proba = np.full((n_rows, width), np.nan)
+        eval_mean = test_mean = None
+        if class_weight is None and self.config.apply_class_weight and self.task == consts.TASK_BINARY:
+            vals, counts = np.unique(y, return_counts=True)
+            class_weight = {int(v): float(len(y) / (len(vals) * c)) for v, c in zip(vals, counts)}
+        callbacks = self._inject_callbacks(callbacks)
+        sw_all = None if sample_weight is None else np.asarray(sample_weight)
+        oof_scores = [] if oof_metrics is not None else None
+        os.makedirs(self.output_path, exist_ok=True)
+        for n_fold, (train_idx, valid_idx) in enumerate(iterators.split(X, y)):
+            model = deepmodel.DeepModel(self.task, self.num_classes, self.config, self.preprocessor.categorical_columns,
+                                        self.preprocessor.continuous_columns)
+            history = model.fit(X.iloc[train_idx], y[train_idx], batch_size=batch_size, epochs=epochs, verbose=verbose,
+                                callbacks=callbacks, validation_data=(X.iloc[valid_idx], y[valid_idx]), shuffle=shuffle,
+                                class_weight=class_weight, sample_weight=None if sw_all is None else sw_all[train_idx],
+                                initial_epoch=initial_epoch, steps_per_epoch=steps_per_epoch,
+                                validation_steps=validation_steps, validation_freq=validation_freq)
+            fold_oof = model.predict(X.iloc[valid_idx])
+            oof_proba[valid_idx] = fold_oof.reshape(len(valid_idx), -1)
+            if X_eval is not None:
+                pe = model.predict(X_eval) / num_folds
+                eval_mean = pe if eval_mean is None else eval_mean + pe
+            if X_test is not None:
+                pt = model.predict(X_test) / num_folds
+                test_mean = pt if test_mean is None else test_mean + pt
+            if oof_metrics is not None:
+                y_true = self.preprocessor.inverse_transform_y(y[valid_idx])
+                y_proba = self._fix_softmax_proba(fold_oof.copy()) if self.task == consts.TASK_BINARY else fold_oof.copy()
+                y_pred = self.proba2predict(y_proba, encode_to_label=True)
+                oof_scores.append(_calc_scores(y_true, y_pred, y_proba, self.task, oof_metrics, self.pos_label, self.classes_))
+            name = f'{"+".join(self.nets)}-kfold-{n_fold + 1}'
+            model.save(f'{self.output_path}{"_".join(self.nets)}-kfold-{n_fold + 1}.npz')
+            self.__modelset[name] = (model, history.history)
+            self.__current_model = model
+        nan_idx = np.argwhere(np.isnan(oof_proba).any(1)).ravel()
+        if self.task == consts.TASK_BINARY:
+            oof_fixed = self._fix_softmax_proba(oof_proba.copy())
+            eval_fixed = self._fix_softmax_proba(eval_mean.copy()) if eval_mean is not None else None
+            test_fixed = self._fix_softmax_proba(test_mean.copy()) if test_mean is not None else None
+            if test_mean is not None:
+                import pandas as pd
+                pd.DataFrame(test_mean.reshape(-1)).to_csv(f'{self.output_path}{"_".join(self.nets)}-cv-{num_folds}.csv',
+                                                           index=False)
+        else:
+            oof_fixed = oof_proba.reshape(n_rows) if self.task == consts.TASK_REGRESSION else oof_proba
+            eval_fixed, test_fixed = eval_mean, test_mean
+        if len(nan_idx) > 0:
+            oof_fixed[nan_idx] = np.nan
+        if oof_metrics is not None:
+            return oof_fixed, eval_fixed, test_fixed, oof_scores
+        return oof_fixed, eval_fixed, test_fixed
+
+    @staticmethod
+    def _fix_softmax_proba(proba):
+        """(n, 1) sigmoid output -> (n, 2) columns [1-p, p] (hypernets' fix_binary_predict_proba_result)."""
+        if proba is None:
+            return None
+        proba = proba.reshape(len(proba), -1)
+        return np.hstack([1.0 - proba, proba]) if proba.shape[1] == 1 else proba
+
     def _inject_callbacks(self, callbacks):
         callbacks = list(callbacks or [])
         if self.monitor is None or any(isinstance(cb, EarlyStopping) for cb in callbacks):
@@ -284,6 +399,8 @@ class DeepTable:
     def get_model(self, model_selector=consts.MODEL_SELECTOR_CURRENT, brevity=True):
         if model_selector in (consts.MODEL_SELECTOR_CURRENT, consts.MODEL_SELECTOR_BEST):
             return self.__current_model
+        if model_selector == consts.MODEL_SELECTOR_ALL:
+            return [m for m, _ in self.__modelset.values()]
         if model_selector in self.__modelset:
             return self.__modelset[model_selector][0]
         raise ValueError(f'{model_selector} does not exist.')
@@ -298,6 +415,10 @@ class DeepTable:
             raise ValueError(f'"{model_selector}" not found in modelset.')
         if auto_transform_data:
             X = self.preprocessor.transform_X(X)
+        if isinstance(model, list):         # 'all': mean of the model set's probabilities (reference deeptable.py:541-552)
+            if not model:
+                raise ValueError('the model set is empty')
+            return sum(m.predict(X, batch_size=batch_size, verbose=verbose) for m in model) / len(model)
         return model.predict(X, batch_size=batch_size, verbose=verbose)
 
     def predict_proba(self, X, batch_size=128, verbose=0, model_selector=consts.MODEL_SELECTOR_CURRENT,

@@ -1,5 +1,7 @@
 """GPU parity of the assembled model (DeepModel) against the CPU oracle's model restatement:
 forward, gradients-through-training (Adam trajectories) and the public fit/predict surface."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -150,6 +152,50 @@ def test_deeptable_fit_predict_evaluate_save_load(tmp_path):
         bad = df.copy()
         bad.columns = list(bad.columns[:-1]) + [bad.columns[0]]
         deeptable.DeepTable(config=conf).fit(bad, y, epochs=1, verbose=0)
+
+
+def test_fit_cross_validation_oof_and_model_set(tmp_path):
+    """reference deeptable.py:373-517 / tests/models/deeptable_cv_test.py: out-of-fold matrix complete, fold means for
+    X_eval / X_test, one registered model per fold, model_selector='all' = mean of the folds, oof_metrics scores."""
+    from deeptables_b200 import deeptable, deepnets
+    g = np.random.default_rng(3)
+    n = 1200
+    df = pd.DataFrame({'a': g.choice(list('abcdef'), size=n), 'b': g.choice(['x', 'y', 'z'], size=n),
+                       'u': g.normal(size=n), 'v': g.exponential(size=n)})
+    logit = (df['a'] == 'a') * 2.0 + df['u'] * 1.5 - 0.5
+    y = np.where(g.random(n) < 1 / (1 + np.exp(-logit)), 1, 0)
+    conf = deeptable.ModelConfig(nets=deepnets.DeepFM, embedding_dropout=0, metrics=['AUC'], auto_scale=True,
+                                 earlystopping_patience=3, home_dir=str(tmp_path / 'out'))
+    dt = deeptable.DeepTable(config=conf)
+    oof, ev, te, scores = dt.fit_cross_validation(df, y, X_eval=df.head(50), X_test=df.tail(40), num_folds=3, stratified=True,
+                                                  batch_size=64, epochs=3, verbose=0, oof_metrics=['auc', 'accuracy'])
+    assert oof.shape == (n, 2) and not np.isnan(oof).any() and np.allclose(oof.sum(1), 1.0, atol=1e-6)
+    assert ev.shape == (50, 2) and te.shape == (40, 2)
+    assert len(scores) == 3 and all(0.5 < sc['auc'] <= 1.0 for sc in scores)
+    from sklearn.metrics import roc_auc_score
+    assert roc_auc_score(y, oof[:, 1]) > 0.7
+    models = dt.get_model('all')
+    assert len(models) == 3
+    p_all = dt.predict_proba(df.head(30), model_selector='all')
+    p_each = [dt.predict_proba(df.head(30), model_selector=f'{"+".join(conf.nets)}-kfold-{k + 1}') for k in range(3)]
+    np.testing.assert_allclose(p_all, sum(p_each) / 3, rtol=1e-5, atol=1e-6)
+    assert len([f for f in os.listdir(dt.output_path) if f.endswith('.npz')]) == 3
+
+
+def test_fit_with_rows_in_pinned_host_memory(monkeypatch):
+    """DTB_DATA_ON_HOST=1: the encoded rows stay in pinned host memory and reach the GPU through the double-buffered
+    loader (the replacement of utils/dataset_generator.py for data sets beyond HBM); same steps arithmetic, it learns."""
+    model, conf = build(['linear', 'fm_nets', 'dnn_nets'], [7, 5, 9], 4, 2)
+    g = np.random.default_rng(11)
+    n = 2000
+    df = pd.DataFrame({'c0': g.integers(0, 7, n), 'c1': g.integers(0, 5, n), 'c2': g.integers(0, 9, n),
+                       'n0': g.normal(size=n), 'n1': g.normal(size=n)})
+    y = ((df['c0'] == 3) * 2.0 + df['n0'] > 0.5).astype(np.float32).values
+    monkeypatch.setenv('DTB_DATA_ON_HOST', '1')
+    hist = model.fit(df, y, batch_size=128, epochs=4, verbose=0, validation_split=0.2,
+                     sample_weight=np.ones(n, dtype=np.float32))
+    assert len(hist.history['loss']) == 4 and hist.history['loss'][-1] < hist.history['loss'][0]
+    assert hist.history['val_AUC'][-1] > 0.8
 
 
 def test_fit_steps_arithmetic_and_history_keys():
