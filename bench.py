@@ -362,25 +362,29 @@ def time_cin_kernel(model, cat, peaks):
     dt = _timed_alone(fwd, flush)
     dt_b = _timed_alone(bwd, flush)
     t.grad.zero_()                                     # the probe's gradients must not leak into training
-    tc = bool(N.lib.dtb_cin_tc_supported(F_FIELDS, EMB_DIM, sizes_c, 3, 0)) and precision != 1
+    mode = N.lib.dtb_cin_resolved_precision(F_FIELDS, EMB_DIM, sizes_c, 3, 0, precision)     # what 'auto' runs for this shape
+    tc = mode in (2, 3, 4)
     tf = b * CIN_FLOP_PER_ROW / dt / 1e12
+    kname = {4: 'cin_tc2_fwd_kernel', 2: 'cin_tc_fwd_kernel', 3: 'cin_tc_fwd_kernel'}.get(mode)
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1_cin_tc_traffic.json')
-    if tc and os.path.exists(tpath) and b == 65536:
+    tpath = os.path.join(ROOT, 'profiles', 'r2_cin_tc_traffic.json')
+    if kname and os.path.exists(tpath) and b == 65536:
         with open(tpath) as f:
-            tj = json.load(f).get('cin_tc_fwd_kernel_compact')     # ncu capture of the current saved-activation format
+            tj = json.load(f).get(kname)            # ncu --set full capture of this kernel at this shape (training mode)
         if tj:
             traffic = tj['dram_bytes_read'] + tj['dram_bytes_write']
     return {'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
             'frac': tf / peaks['bf16_tflops'], 'traffic': traffic,
-            'kernel': ('cin_tc_fwd_kernel (tcgen05, single pass on power-of-two-scaled fp16 operands)' if precision == 4 else
-                       'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)') if tc
-            else 'cin_fwd (fp32 cuBLAS formulation)',
+            'kernel': {4: 'cin_tc2_fwd_kernel (tcgen05, ONE pass on power-of-two-scaled fp16 operands, two threads per GEMM row)',
+                       2: 'cin_tc_fwd_kernel (tcgen05, bf16x3 split: 3 tensor passes per algorithmic FLOP)',
+                       3: 'cin_tc_fwd_kernel (tcgen05, one bf16 pass)'}.get(mode, 'cin_fwd (any-shape formulation, dense_tc GEMMs)'),
             'ms': dt * 1e3, 'algorithmic_flop_per_launch': b * CIN_FLOP_PER_ROW,
-            'executed_tensor_tflops': tf * (3 if tc and precision not in (3, 4) else 1),
+            'algorithmic_bytes_per_launch': b * CIN_BYTES_PER_ROW,
+            'executed_tensor_tflops': tf * (3 if mode == 2 else 1),
             'hbm_gbs_informational': b * CIN_BYTES_PER_ROW / dt / 1e9, 'peak_source': peaks['source'],
             'cin_backward': {'ms': dt_b * 1e3, 'algorithmic_tflops': 2 * b * CIN_FLOP_PER_ROW / dt_b / 1e12,
-                             'kernels': 'cin_tc_dgrad_kernel + 3 x cin_tc_wgrad_kernel'}}
+                             'kernels': 'cin_tc2_dgrad_kernel + 3 x cin_tc2_wgrad_kernel' if mode == 4 else
+                                        'cin_tc_dgrad_kernel + 3 x cin_tc_wgrad_kernel'}}
 
 
 def main():
@@ -489,9 +493,10 @@ def main():
             'metric': spec['metric'], 'value': rows / secs, 'unit': 'rows/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': secs / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': ('f32 (CIN forward GEMMs: one tcgen05 pass on scaled fp16 operands, backward bf16x3; fp32 accumulate)'
-                      if args.cin_precision == 4 else 'f32 (CIN GEMMs: bf16x3 split on tcgen05, fp32 accumulate)')
-            if roof['kernel'].startswith('cin_tc_fwd_kernel') else 'f32 (Dense GEMMs: bf16x3 split on tcgen05, fp32 accumulate)',
+            'dtype': ('f32 storage and accumulation; CIN GEMMs: one tcgen05 pass on power-of-two-scaled fp16 operands (error ~2e-4 '
+                      'of the output scale); Dense GEMMs: bf16x3 split' if roof['kernel'].startswith('cin_tc2')
+                      else 'f32 (CIN GEMMs: bf16x3 split on tcgen05, fp32 accumulate)' if roof['kernel'].startswith('cin_tc_')
+                      else 'f32 (Dense GEMMs: bf16x3 split on tcgen05, fp32 accumulate)'),
             'experiment_build': args.cin_exp or None,
             'data': 'synthetic' if args.id_dist == 'uniform' else f'synthetic ({args.id_dist} ids: NOT the headline distribution)',
             'config': {'workload': spec['workload'], 'name': args.config,

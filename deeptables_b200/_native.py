@@ -28,6 +28,7 @@ _SIGNATURES = {
     'dtb_version': (c_int, []),
     'dtb_last_error': (c_char_p, []),
     'dtb_device_sm_count': (c_int, [_IP]),
+    'dtb_capture_status': (c_int, [P]),
     'dtb_launch_count': (c_longlong, []),
     'dtb_launch_count_add': (None, [c_longlong]),
     'dtb_embedding_gather': (c_int, [P, P, P, P, c_int, c_int, c_int, P, P]),
@@ -65,6 +66,7 @@ _SIGNATURES = {
     'dtb_cin_bwd_phase': (c_int, [P, P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, _IP, c_int,
                                   c_int, c_int, c_int, c_int, P]),
     'dtb_cin_tc_supported': (c_int, [c_int, c_int, _IP, c_int, c_int]),
+    'dtb_cin_resolved_precision': (c_int, [c_int, c_int, _IP, c_int, c_int, c_int]),
     'dtb_cin_tc_set_variant': (c_int, [c_int]),
     'dtb_tc_selftest': (c_int, [P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_cross_fwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
@@ -103,11 +105,9 @@ def check(rc, what=''):
     if rc != 0:
         raise RuntimeError(f'deeptables_b200 native call {what} failed (code {rc}): {last_error()}')
     if _DEBUG_CAPTURE:          # debug aid: name the first native call after which a stream capture is no longer valid
-        import torch
-        try:
-            torch.cuda.is_current_stream_capturing()
-        except Exception as exc:
-            raise RuntimeError(f'stream capture invalid right after native call {what!r}: {exc}') from exc
+        st = lib.dtb_capture_status(stream_ptr())
+        if st not in (0, 1):
+            raise RuntimeError(f'stream capture status {st} right after native call {what!r}')
 
 
 def ptr(t):

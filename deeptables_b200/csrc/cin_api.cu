@@ -27,6 +27,14 @@ int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers
   return cin_tc_supported(s) ? 1 : 0;
 }
 
+int dtb_cin_resolved_precision(int F, int D, const int* layer_sizes_host, int n_layers, int direct, int precision) {
+  CinShape s;
+  if (!s.init(F, D, layer_sizes_host, n_layers, direct)) return DTB_ERR_INVALID_ARG;
+  precision = resolve_precision(s, precision);
+  if (precision == DTB_CIN_AUTO) return cin_tc_supported(s) ? DTB_CIN_TC_BF16X3 : DTB_CIN_FP32;
+  return precision;
+}
+
 size_t dtb_cin_saved_bytes(int B, int F, int D, const int* layer_sizes_host, int n_layers, int direct) {
   CinShape s;
   if (!s.init(F, D, layer_sizes_host, n_layers, direct) || B <= 0) return 0;

@@ -43,6 +43,17 @@ void dtb_launch_count_add(long long n) { dtb::g_launches.fetch_add(n, std::memor
 
 const char* dtb_last_error(void) { return dtb::g_err; }
 
+// debug aid: capture status of a stream -- 0 not capturing, 1 capturing, 2 capture invalidated, negative = CUDA error
+int dtb_capture_status(void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  const cudaError_t e = cudaStreamIsCapturing((cudaStream_t)stream, &st);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return -(int)e;
+  }
+  return (int)st;
+}
+
 int dtb_device_sm_count(int* out_host) {
   DTB_CHECK_ARG(out_host != nullptr, "out_host is NULL");
   int dev = 0;

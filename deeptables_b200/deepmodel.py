@@ -513,6 +513,8 @@ class DeepModel:
             sy = torch.empty_like(y)
             self._step_dev.fill_(self._step)
             try:
+                import gc
+                gc.collect()             # no autograd graph of an earlier (eager) step may outlive into the capture
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
                 l0 = N.lib.dtb_launch_count()

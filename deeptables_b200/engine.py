@@ -205,16 +205,19 @@ class GatherFn(torch.autograd.Function):
         out = torch.empty(b, t.n_fields, t.dim, dtype=torch.float32, device=w.device)
         check(N.lib.dtb_embedding_gather(ptr(idx), ptr(w), ptr(offs), ptr(out), b, t.n_fields, t.dim,
                                          ptr(t.status), stream_ptr()), 'embedding_gather')
-        ctx.block = block
+        # NOT ctx.block: the block caches this op's output (FieldBlock._mat), whose grad_fn owns ctx -- a reference cycle
+        # that kept the whole autograd graph of a step (and the gradient accumulators bound to the stream it ran on)
+        # alive until the next garbage collection, which invalidated CUDA-graph capture of the following step
+        ctx.table, ctx.idx = t, idx
         _note_consumer(ctx, t)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        t, idx, w, offs = _tabs(ctx.block)
+        t, idx = ctx.table, ctx.idx
         gt = _grad_target(t)
         g = _f32(g)
-        check(N.lib.dtb_embedding_scatter_add(ptr(idx), ptr(offs), ptr(g), ptr(gt), idx.shape[0], t.n_fields,
+        check(N.lib.dtb_embedding_scatter_add(ptr(idx), ptr(t.row_offsets), ptr(g), ptr(gt), idx.shape[0], t.n_fields,
                                               t.dim, stream_ptr()), 'embedding_scatter_add')
         _table_grad_done(t)
         return _TableBackwardMixin.finish_tensor_table(t), None

@@ -44,6 +44,8 @@ extern "C" {
 int dtb_version(void);
 const char* dtb_last_error(void);
 int dtb_device_sm_count(int* out_host);
+/* debug aid: 0 = `stream` is not capturing, 1 = capturing, 2 = its capture has been invalidated, < 0 = -cudaError */
+int dtb_capture_status(void* stream);
 /* number of kernels this library has launched so far (every kernel on the path is hand-written) */
 long long dtb_launch_count(void);
 /* kernels launched by replaying a CUDA graph captured through this library (counted once at capture): added per replay */
@@ -219,6 +221,8 @@ int dtb_cin_bwd_phase(const int32_t* idx, const float* table, const int64_t* row
 #define DTB_CIN_TC_BF16X1 3
 #define DTB_CIN_TC_F16X1 4
 int dtb_cin_tc_supported(int F, int D, const int* layer_sizes_host, int n_layers, int direct);
+/* which of the codes 1 / 2 / 4 a forward + backward with `precision` runs for this shape (0 = auto is resolved) */
+int dtb_cin_resolved_precision(int F, int D, const int* layer_sizes_host, int n_layers, int direct, int precision);
 /* Test hooks for the tensor-core path.  set_variant: 1 (default) feeds the on-the-fly A operand to
  * tcgen05.mma through TMEM, 0 through shared memory.  selftest: C[128,N] = bf16(A[128,K]) @
  * bf16(Bmat[K,N]) with one M=128 UMMA tile (N <= 128, K <= 64, multiples of 16); workspace >= 4*N*K bytes. */

@@ -192,10 +192,10 @@ def test_fit_with_rows_in_pinned_host_memory(monkeypatch):
                        'n0': g.normal(size=n), 'n1': g.normal(size=n)})
     y = ((df['c0'] == 3) * 2.0 + df['n0'] > 0.5).astype(np.float32).values
     monkeypatch.setenv('DTB_DATA_ON_HOST', '1')
-    hist = model.fit(df, y, batch_size=128, epochs=4, verbose=0, validation_split=0.2,
+    hist = model.fit(df, y, batch_size=128, epochs=40, verbose=0, validation_split=0.2,
                      sample_weight=np.ones(n, dtype=np.float32))
-    assert len(hist.history['loss']) == 4 and hist.history['loss'][-1] < hist.history['loss'][0]
-    assert hist.history['val_AUC'][-1] > 0.8
+    assert len(hist.history['loss']) == 40 and hist.history['loss'][-1] < 0.6 * hist.history['loss'][0]
+    assert hist.history['val_AUC'][-1] > 0.9            # rows, labels and weights stay paired through the loader
 
 
 def test_fit_steps_arithmetic_and_history_keys():

@@ -442,7 +442,10 @@ def test_cin_fwd_bwd(nat, f, d, sizes, direct, use_bias, act, precision):
             np.testing.assert_allclose(got, want_, rtol=tol * 10, atol=tol * np.abs(want_).max(), err_msg=what)
             return
         ok = np.abs(got - want_) <= tol * 10 * np.abs(want_) + tol * np.abs(want_).max()
-XX
+        # 37 batch rows: ONE flipped mask bit moves that row's share of every filter entry
+        assert ok.mean() >= 0.95, f'{what}: only {100 * ok.mean():.2f} % of the entries inside the tolerance'
+        rel = np.linalg.norm(got - want_) / np.linalg.norm(want_)
+        assert rel <= 5e-2, f'{what}: norm-wise error {rel:.2e}'
 
     close(gt, want_t, 'embedding gradient')
     close(dw, want_w, 'filter gradient')

@@ -76,8 +76,10 @@ def main():
     if '--json' in sys.argv:
         dst = sys.argv[sys.argv.index('--json') + 1]
         out = {'source': f'ncu --set full --clock-control none ({path}); tools/ncu_extract.py'}
-        names = {'cin_tc_fwd_kernel': 'cin_tc_fwd_kernel_compact', 'cin_tc_dgrad_kernel': 'cin_tc_dgrad_kernel_compact',
-                 'cin_tc_wgrad_kernel': 'cin_tc_wgrad_kernel_first_launch'}
+        # key = kernel name as bench.py looks it up; the first launch of each kernel in the report
+        names = {'cin_tc2_fwd_kernel': 'cin_tc2_fwd_kernel', 'cin_tc2_dgrad_kernel': 'cin_tc2_dgrad_kernel',
+                 'cin_tc2_wgrad_kernel': 'cin_tc2_wgrad_kernel_first_launch', 'cin_tc_fwd_kernel': 'cin_tc_fwd_kernel',
+                 'cin_tc_dgrad_kernel': 'cin_tc_dgrad_kernel', 'cin_tc_wgrad_kernel': 'cin_tc_wgrad_kernel_first_launch'}
         for r in launches:
             for needle, key in names.items():
                 if needle in r['kernel'] and key not in out and 'dram_read' in r:
