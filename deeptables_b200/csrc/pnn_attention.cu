@@ -375,6 +375,191 @@ __global__ void attention_core_bwd_kernel(const float* __restrict__ qkvr, const 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same two kernels with the head width as a template parameter (DH = 1, 2, 4, ... 64): q / dout / k / v rows and
+// the per-thread accumulators live in REGISTERS (the generic kernels above index `acc[kMaxDh]` with a run-time bound, i.e.
+// from local memory, and every lane re-read its q row from shared memory at a stride of 4D floats = one bank: a 32-way
+// conflict on the innermost loop -- 8.6 ms per launch at 65 536 rows x 26 fields x D = 32, 2 % of the HBM rate).  Shared
+// rows are padded by 4 floats; key / value reads are warp broadcasts.
+// ------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256) attention_core_fwd_t_kernel(const float* __restrict__ qkvr, float* __restrict__ Y, int B, int F, int D,
+                                                                    int heads, int use_res) {
+  extern __shared__ float sm[];     // [F][4D + 4]
+  const int RS = 4 * D + 4;
+  const float scale = rsqrtf((float)DH);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b * F * 4 * D);
+    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {           // D float4 per field row
+      const int f = e / D, c4 = e - f * D;
+      *reinterpret_cast<float4*>(sm + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t < heads * F) {
+      const int h = t / F, i = t - h * F;
+      float q[DH], acc[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        q[c] = sm[(size_t)i * RS + h * DH + c] * scale;
+        acc[c] = 0.f;
+      }
+      float m = -INFINITY;
+      for (int j = 0; j < F; ++j) {
+        const float* k = sm + (size_t)j * RS + D + h * DH;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        m = fmaxf(m, s);
+      }
+      float sum = 0.f;
+      for (int j = 0; j < F; ++j) {
+        const float* k = sm + (size_t)j * RS + D + h * DH;
+        const float* v = k + D;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        const float pj = __expf(s - m);
+        sum += pj;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) acc[c] = fmaf(pj, v[c], acc[c]);
+      }
+      const float inv = 1.f / sum;
+      float* y = Y + ((size_t)b * F + i) * D + h * DH;
+      const float* res = sm + (size_t)i * RS + 3 * D + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        float o = acc[c] * inv;
+        if (use_res) o += res[c];
+        y[c] = fmaxf(o, 0.f);
+      }
+    }
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* __restrict__ qkvr, const float* __restrict__ Y,
+                                                                    const float* __restrict__ dY, float* __restrict__ d_qkvr, int B,
+                                                                    int F, int D, int heads, int use_res) {
+  extern __shared__ float sm[];
+  const int RS = 4 * D + 4, RZ = D + 4;
+  float* blk = sm;                          // [F][4D + 4] inputs
+  float* dz = sm + (size_t)F * RS;          // [F][D + 4]  dLoss / d(pre-relu output)
+  float* st = dz + (size_t)F * RZ;          // [heads*F][3]: max, 1/sum, delta
+  const float scale = rsqrtf((float)DH);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b * F * 4 * D);
+    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
+      const int f = e / D, c4 = e - f * D;
+      *reinterpret_cast<float4*>(blk + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+    }
+    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
+      const size_t o = (size_t)b * F * D + e;
+      const int f = e / D, c = e - f * D;
+      dz[(size_t)f * RZ + c] = Y[o] > 0.f ? dY[o] : 0.f;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    float* dst = d_qkvr + (size_t)b * F * 4 * D;
+    // phase 1: thread (h, i): softmax statistics, delta = dout . out, dQ row, dRes row
+    if (t < heads * F) {
+      const int h = t / F, i = t - h * F;
+      float q[DH], dout[DH], dq[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        q[c] = blk[(size_t)i * RS + h * DH + c] * scale;
+        dout[c] = dz[(size_t)i * RZ + h * DH + c];
+        dq[c] = 0.f;
+      }
+      float m = -INFINITY;
+      for (int j = 0; j < F; ++j) {
+        const float* k = blk + (size_t)j * RS + D + h * DH;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        m = fmaxf(m, s);
+      }
+      float sum = 0.f, dsum = 0.f;       // dsum = sum_j p_j (dout . v_j)  (un-normalised)
+      for (int j = 0; j < F; ++j) {
+        const float* k = blk + (size_t)j * RS + D + h * DH;
+        const float* v = k + D;
+        float s = 0.f, dv = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+          s = fmaf(q[c], k[c], s);
+          dv = fmaf(dout[c], v[c], dv);
+        }
+        const float pj = __expf(s - m);
+        sum += pj;
+        dsum = fmaf(pj, dv, dsum);
+      }
+      const float inv = 1.f / sum;
+      const float delta = dsum * inv;
+      st[t * 3 + 0] = m;
+      st[t * 3 + 1] = inv;
+      st[t * 3 + 2] = delta;
+      for (int j = 0; j < F; ++j) {
+        const float* k = blk + (size_t)j * RS + D + h * DH;
+        const float* v = k + D;
+        float s = 0.f, dv = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+          s = fmaf(q[c], k[c], s);
+          dv = fmaf(dout[c], v[c], dv);
+        }
+        const float ds = __expf(s - m) * inv * (dv - delta);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, k[c], dq[c]);
+      }
+      float* o = dst + (size_t)i * 4 * D + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        o[c] = dq[c] * scale;
+        o[3 * D + c] = use_res ? dout[c] : 0.f;
+      }
+    }
+    __syncthreads();
+    // phase 2: thread (h, j): dK row, dV row
+    if (t < heads * F) {
+      const int h = t / F, j = t - h * F;
+      float k[DH], v[DH], dk[DH], dvv[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        k[c] = blk[(size_t)j * RS + D + h * DH + c];
+        v[c] = blk[(size_t)j * RS + 2 * D + h * DH + c];
+        dk[c] = 0.f;
+        dvv[c] = 0.f;
+      }
+      for (int i = 0; i < F; ++i) {
+        const float* q = blk + (size_t)i * RS + h * DH;
+        const float* dout = dz + (size_t)i * RZ + h * DH;
+        const float* s3 = st + (h * F + i) * 3;
+        float s = 0.f, dv = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+          s = fmaf(q[c], k[c], s);
+          dv = fmaf(dout[c], v[c], dv);
+        }
+        const float pij = __expf(s * scale - s3[0]) * s3[1];
+        const float ds = pij * (dv - s3[2]);
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+          dk[c] = fmaf(ds, q[c], dk[c]);
+          dvv[c] = fmaf(pij, dout[c], dvv[c]);
+        }
+      }
+      float* o = dst + (size_t)j * 4 * D + h * DH;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) {
+        o[D + c] = dk[c] * scale;
+        o[2 * D + c] = dvv[c];
+      }
+    }
+  }
+}
+
 }  // namespace dtb
 
 using namespace dtb;
@@ -436,12 +621,28 @@ int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int
   DTB_CHECK_ARG(D / heads <= kMaxDh && heads * F <= 1024, "head width <= 64 and heads*fields <= 1024");
   if (B == 0) return DTB_OK;
   const int threads = (heads * F + 31) / 32 * 32;
-  const size_t smem = (size_t)F * 4 * D * sizeof(float);
-  DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count() * 8;
   if (grid > B) grid = B;
-  attention_core_fwd_kernel<<<grid, threads < 64 ? 64 : threads, smem, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads,
-                                                                                                 use_residual);
+  const int dh = D / heads;
+  const int nthr = threads < 64 ? 64 : threads;
+  if (D % 4 == 0 && nthr <= 256 && (reinterpret_cast<uintptr_t>(qkvr) & 15) == 0) {
+    const size_t smem_t = (size_t)F * (4 * D + 4) * sizeof(float);
+#define DTB_ATT_FWD(DHV)                                                                                                   \
+  case DHV:                                                                                                                \
+    DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_fwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                     (int)smem_t));                                                                         \
+    attention_core_fwd_t_kernel<DHV><<<grid, nthr, smem_t, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads, use_residual); \
+    DTB_LAUNCH_OK();                                                                                                       \
+    return DTB_OK;
+    switch (dh) {
+      DTB_ATT_FWD(1) DTB_ATT_FWD(2) DTB_ATT_FWD(4) DTB_ATT_FWD(8) DTB_ATT_FWD(16) DTB_ATT_FWD(32) DTB_ATT_FWD(64)
+      default: break;
+    }
+#undef DTB_ATT_FWD
+  }
+  const size_t smem = (size_t)F * 4 * D * sizeof(float);
+  DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_core_fwd_kernel<<<grid, nthr, smem, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads, use_residual);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }
@@ -453,12 +654,29 @@ int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, f
   DTB_CHECK_ARG(D / heads <= kMaxDh && heads * F <= 1024, "head width <= 64 and heads*fields <= 1024");
   if (B == 0) return DTB_OK;
   const int threads = (heads * F + 31) / 32 * 32;
-  const size_t smem = ((size_t)F * 5 * D + (size_t)heads * F * 3) * sizeof(float);
-  DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = sm_count() * 8;
   if (grid > B) grid = B;
-  attention_core_bwd_kernel<<<grid, threads < 64 ? 64 : threads, smem, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F,
-                                                                                                 D, heads, use_residual);
+  const int dh = D / heads;
+  const int nthr = threads < 64 ? 64 : threads;
+  if (D % 4 == 0 && nthr <= 256 && (reinterpret_cast<uintptr_t>(qkvr) & 15) == 0) {
+    const size_t smem_t = ((size_t)F * (4 * D + 4) + (size_t)F * (D + 4) + (size_t)heads * F * 3) * sizeof(float);
+#define DTB_ATT_BWD(DHV)                                                                                                \
+  case DHV:                                                                                                             \
+    DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)smem_t));                                                                      \
+    attention_core_bwd_t_kernel<DHV><<<grid, nthr, smem_t, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D, heads, \
+                                                                                   use_residual);                       \
+    DTB_LAUNCH_OK();                                                                                                    \
+    return DTB_OK;
+    switch (dh) {
+      DTB_ATT_BWD(1) DTB_ATT_BWD(2) DTB_ATT_BWD(4) DTB_ATT_BWD(8) DTB_ATT_BWD(16) DTB_ATT_BWD(32) DTB_ATT_BWD(64)
+      default: break;
+    }
+#undef DTB_ATT_BWD
+  }
+  const size_t smem = ((size_t)F * 5 * D + (size_t)heads * F * 3) * sizeof(float);
+  DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_core_bwd_kernel<<<grid, nthr, smem, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D, heads, use_residual);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

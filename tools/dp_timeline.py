@@ -21,7 +21,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from deeptables_b200.deepmodel import DeepModel
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
-    conf = bench.make_config(0)
+    conf = bench.make_config('xdeepfm', 0)
     cats = [CategoricalColumn(f'C{i + 1}', 1000000, bench.EMB_DIM) for i in range(bench.F_FIELDS)]
     conts = [ContinuousColumn('input_continuous_all', [f'I{i + 1}' for i in range(bench.N_DENSE)])]
     model = DeepModel('binary', 2, conf, cats, conts, seed=1234)
@@ -46,7 +46,15 @@ def main():
         ks = [e for e in ev if e.get('cat') in ('kernel', 'gpu_memcpy', 'gpu_memset')]
         ks.sort(key=lambda e: e['ts'])
         t0 = ks[0]['ts']
+        # one full cycle of a step: from the loss kernel of the second profiled step to the loss kernel of the third
+        # (loss -> backward -> exchange -> Adam -> next forward)
+        marks = [i for i, e in enumerate(ks) if 'loss_kernel' in e['name']]
+        if len(marks) >= 2:
+            ks = ks[marks[-2]:marks[-1]]
+            t0 = ks[0]['ts']
         with open(f'gpurun_out/dp_timeline_w{world}.txt', 'w') as f:
+            f.write(f'# one data-parallel train step on rank 0 of {world} (torch.profiler; us since the step start, duration, '
+                    f'stream, kernel); step span {ks[-1]["ts"] + ks[-1]["dur"] - t0:.0f} us\n')
             for e in ks:
                 f.write(f"{e['ts'] - t0:10.1f} {e['dur']:9.1f} s{e['args'].get('stream', -1):<4} {e['name'][:90]}\n")
         os.remove(path)
