@@ -220,6 +220,279 @@ __global__ void pnn_bwd_dk_kernel(const int32_t* __restrict__ idx, const float* 
 }
 
 // ------------------------------------------------------------------------------------------
+// PNN kernels with the embedding width as a template parameter (DT = 4, 8, 16, 32).  The generic kernels above keep one
+// pair per thread, re-read the (D x D) kernel slice of the pair from global memory for every batch row, index
+// `gi_acc[kMaxD]` with a run-time bound (local memory) and merge the per-pair contributions with shared-memory float
+// atomics: 6.2 ms for the embedding gradient at 16 384 rows x 26 fields x D = 16.  Here a thread is one (batch row, field):
+// its embedding row and accumulators are registers, the kernel slices of the field's pairs sit in shared memory and are
+// read as 128-bit warp broadcasts (all lanes of a CTA work on the same field), and nothing is merged across threads --
+// the row's gradient leaves as one vector RED per 4 floats.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pair_index(int a, int b, int F) {      // a < b, row-major order of pair_of()
+  return a * (F - 1) - a * (a - 1) / 2 + (b - a - 1);
+}
+
+template <int DT>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&o)[DT]) {
+#pragma unroll
+  for (int c = 0; c < DT / 4; ++c) {
+    const float4 t = *reinterpret_cast<const float4*>(p + 4 * c);
+    o[4 * c] = t.x;
+    o[4 * c + 1] = t.y;
+    o[4 * c + 2] = t.z;
+    o[4 * c + 3] = t.w;
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ void gather_row(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                           const int64_t* __restrict__ row_offsets, int row, int F, int f,
+                                           float (&o)[DT], int64_t* rb_out, int* status) {
+  const int64_t rb = table_row(row_offsets, f, __ldg(idx + (int64_t)row * F + f), DT, status);
+  if (rb_out) *rb_out = rb;
+  if (rb >= 0) {
+#pragma unroll
+    for (int c = 0; c < DT / 4; ++c) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(table + rb) + c);
+      o[4 * c] = t.x;
+      o[4 * c + 1] = t.y;
+      o[4 * c + 2] = t.z;
+      o[4 * c + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < DT; ++c) o[c] = 0.f;
+  }
+}
+
+// kernel slices of `n` pairs into shared memory: ktype 0 -> ks[q][k][d], ktype 1 -> ks[q][d], ktype 2 -> ks[q]
+template <int DT>
+__device__ __forceinline__ void stage_kernel_slices(const float* __restrict__ kern, float* __restrict__ ks, int n, int P,
+                                                    int ktype, int f, int F, bool only_upper) {
+  // pair of slot q: only_upper -> (f, f+1+q); else the other field is o = q < f ? q : q + 1
+  const int per = ktype == 0 ? DT * DT : (ktype == 1 ? DT : 1);
+  for (int e = threadIdx.x; e < n * per; e += blockDim.x) {
+    const int q = e / per, rem = e - q * per;
+    int p;
+    if (only_upper) {
+      p = pair_index(f, f + 1 + q, F);
+    } else {
+      const int o = q < f ? q : q + 1;
+      p = o < f ? pair_index(o, f, F) : pair_index(f, o, F);
+    }
+    float v;
+    if (ktype == 0) {
+      const int k = rem / DT, d = rem - k * DT;
+      v = __ldg(kern + ((size_t)k * P + p) * DT + d);
+    } else if (ktype == 1) {
+      v = __ldg(kern + (size_t)p * DT + rem);
+    } else {
+      v = __ldg(kern + p);
+    }
+    ks[e] = v;
+  }
+}
+
+constexpr int kPnnTRows = 128;       // batch rows (= threads) per CTA of the (row, field) kernels
+
+// grid (F-1, row-chunk groups): CTA x = field i computes the pairs (i, j > i) of its row chunks.  The CTAs of one chunk
+// group are adjacent in launch order, so the 26 field rows of a batch row are fetched from HBM once and re-read from L2.
+// The embedding row of the NEXT pair is requested before the current pair's FMAs.
+template <int DT>
+__global__ void __launch_bounds__(kPnnTRows) pnn_fwd_t_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                                              const int64_t* __restrict__ row_offsets,
+                                                              const float* __restrict__ kern, float* __restrict__ ip,
+                                                              float* __restrict__ op, int B, int F, int P, int ktype,
+                                                              int* status) {
+  extern __shared__ __align__(16) float ks[];
+  const int i = blockIdx.x, n = F - 1 - i;
+  if (op) stage_kernel_slices<DT>(kern, ks, n, P, ktype, i, F, true);
+  __syncthreads();
+  const int p0 = pair_index(i, i + 1, F);
+  const int n_chunks = (B + kPnnTRows - 1) / kPnnTRows;
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int row = chunk * kPnnTRows + threadIdx.x;
+    if (row >= B) continue;
+    float ei[DT], ej[DT], en[DT];
+    gather_row<DT>(idx, table, row_offsets, row, F, i, ei, nullptr, status);
+    gather_row<DT>(idx, table, row_offsets, row, F, i + 1, en, nullptr, i == 0 ? status : nullptr);
+    for (int q = 0; q < n; ++q) {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) ej[d] = en[d];
+      if (q + 1 < n) gather_row<DT>(idx, table, row_offsets, row, F, i + 2 + q, en, nullptr, i == 0 ? status : nullptr);
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) s = fmaf(ei[d], ej[d], s);
+      if (ip) ip[(size_t)row * P + p0 + q] = s;
+      if (op) {
+        float acc = 0.f;
+        if (ktype == 0) {
+          const float* kq = ks + (size_t)q * DT * DT;
+#pragma unroll
+          for (int k = 0; k < DT; ++k) {
+            float kv[DT];
+            load_row<DT>(kq + k * DT, kv);
+            float t = 0.f;
+#pragma unroll
+            for (int d = 0; d < DT; ++d) t = fmaf(ei[d], kv[d], t);
+            acc = fmaf(t, ej[k], acc);
+          }
+        } else if (ktype == 1) {
+          float kv[DT];
+          load_row<DT>(ks + (size_t)q * DT, kv);
+#pragma unroll
+          for (int d = 0; d < DT; ++d) acc = fmaf(ei[d] * ej[d], kv[d], acc);
+        } else {
+          acc = s * ks[q];
+        }
+        op[(size_t)row * P + p0 + q] = acc;
+      }
+    }
+  }
+}
+
+// grid (F, row-chunk groups): thread = (row, field f) accumulates dLoss/d e_f over the F-1 pairs that contain f
+template <int DT>
+__global__ void __launch_bounds__(kPnnTRows) pnn_bwd_de_t_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                                                 const int64_t* __restrict__ row_offsets,
+                                                                 const float* __restrict__ kern,
+                                                                 const float* __restrict__ d_ip,
+                                                                 const float* __restrict__ d_op,
+                                                                 float* __restrict__ grad_table, int B, int F, int P,
+                                                                 int ktype) {
+  extern __shared__ __align__(16) float ks[];
+  const int f = blockIdx.x;
+  if (d_op) stage_kernel_slices<DT>(kern, ks, F - 1, P, ktype, f, F, false);
+  __syncthreads();
+  const int n_chunks = (B + kPnnTRows - 1) / kPnnTRows;
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int row = chunk * kPnnTRows + threadIdx.x;
+    if (row >= B) continue;
+    const int64_t rb = table_row(row_offsets, f, __ldg(idx + (int64_t)row * F + f), DT, nullptr);
+    if (rb < 0) continue;
+    float acc[DT], eo[DT], en[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) acc[d] = 0.f;
+    gather_row<DT>(idx, table, row_offsets, row, F, f == 0 ? 1 : 0, en, nullptr, nullptr);
+    for (int q = 0; q < F - 1; ++q) {
+      const int o = q < f ? q : q + 1;
+      const int p = o < f ? pair_index(o, f, F) : pair_index(f, o, F);
+#pragma unroll
+      for (int d = 0; d < DT; ++d) eo[d] = en[d];
+      if (q + 1 < F - 1) gather_row<DT>(idx, table, row_offsets, row, F, q + 1 < f ? q + 1 : q + 2, en, nullptr, nullptr);
+      if (d_ip) {
+        const float gi = __ldg(d_ip + (size_t)row * P + p);
+#pragma unroll
+        for (int d = 0; d < DT; ++d) acc[d] = fmaf(gi, eo[d], acc[d]);
+      }
+      if (d_op) {
+        const float go = __ldg(d_op + (size_t)row * P + p);
+        if (ktype == 0) {
+          const float* kq = ks + (size_t)q * DT * DT;
+          if (f < o) {
+            // f is the first field of the pair: d e_f[d] = go * sum_k K[k,p,d] e_o[k]
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+              float kv[DT];
+              load_row<DT>(kq + k * DT, kv);
+              const float w = go * eo[k];
+#pragma unroll
+              for (int d = 0; d < DT; ++d) acc[d] = fmaf(w, kv[d], acc[d]);
+            }
+          } else {
+            // f is the second field: d e_f[k] = go * sum_d e_o[d] K[k,p,d]
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+              float kv[DT];
+              load_row<DT>(kq + k * DT, kv);
+              float t = 0.f;
+#pragma unroll
+              for (int d = 0; d < DT; ++d) t = fmaf(eo[d], kv[d], t);
+              acc[k] = fmaf(go, t, acc[k]);
+            }
+          }
+        } else if (ktype == 1) {
+          float kv[DT];
+          load_row<DT>(ks + (size_t)q * DT, kv);
+#pragma unroll
+          for (int d = 0; d < DT; ++d) acc[d] = fmaf(go * kv[d], eo[d], acc[d]);
+        } else {
+          const float w = go * ks[q];
+#pragma unroll
+          for (int d = 0; d < DT; ++d) acc[d] = fmaf(w, eo[d], acc[d]);
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(grad_table + rb);
+#pragma unroll
+    for (int c = 0; c < DT / 4; ++c) {
+      const float4 v = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(dst + c, v);
+    }
+  }
+}
+
+// 'mat' kernel gradient dK[k,p,d] = sum_r d_op[r,p] e_j[r,k] e_i[r,d].  grid (pair groups, row groups), 256 threads:
+// thread = (pair of the group, k) with the D accumulators over d in registers; the rows arrive in chunks of `R` gathered
+// embedding blocks in shared memory.  One vector RED per 4 kernel elements per CTA.
+template <int DT>
+__global__ void __launch_bounds__(256) pnn_bwd_dk_t_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                                           const int64_t* __restrict__ row_offsets,
+                                                           const float* __restrict__ d_op, float* __restrict__ d_kern, int B,
+                                                           int F, int P, int rows_per_cta, int R) {
+  constexpr int kPg = 256 / DT;                  // pairs per group
+  extern __shared__ __align__(16) float sm[];
+  float* es = sm;                                // [R][F][DT]
+  float* gos = sm + (size_t)R * F * DT;          // [R][kPg]
+  const int pl = threadIdx.x / DT, k = threadIdx.x - pl * DT;
+  const int p = blockIdx.x * kPg + pl;
+  const bool live = p < P;
+  int i = 0, j = 1;
+  if (live) pair_of(p, F, i, j);
+  float acc[DT];
+#pragma unroll
+  for (int d = 0; d < DT; ++d) acc[d] = 0.f;
+  const int r_begin = blockIdx.y * rows_per_cta;
+  const int r_end = min(B, r_begin + rows_per_cta);
+  for (int r0 = r_begin; r0 < r_end; r0 += R) {
+    const int nr = min(R, r_end - r0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * F * (DT / 4); e += blockDim.x) {
+      const int r = e / (F * (DT / 4)), rem = e - r * F * (DT / 4);
+      const int f = rem / (DT / 4), c = rem - f * (DT / 4);
+      const int64_t rb = table_row(row_offsets, f, __ldg(idx + (int64_t)(r0 + r) * F + f), DT, nullptr);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rb >= 0) v = __ldg(reinterpret_cast<const float4*>(table + rb) + c);
+      reinterpret_cast<float4*>(es)[e] = v;
+    }
+    for (int e = threadIdx.x; e < nr * kPg; e += blockDim.x) {
+      const int r = e / kPg, q = e - r * kPg;
+      const int pp = blockIdx.x * kPg + q;
+      gos[e] = pp < P ? __ldg(d_op + (size_t)(r0 + r) * P + pp) : 0.f;
+    }
+    __syncthreads();
+    if (live) {
+      for (int r = 0; r < nr; ++r) {
+        const float* er = es + (size_t)r * F * DT;
+        const float w = gos[r * kPg + pl] * er[j * DT + k];
+        float ei[DT];
+        load_row<DT>(er + i * DT, ei);
+#pragma unroll
+        for (int d = 0; d < DT; ++d) acc[d] = fmaf(w, ei[d], acc[d]);
+      }
+    }
+  }
+  if (live) {
+    float4* dst = reinterpret_cast<float4*>(d_kern + ((size_t)k * P + p) * DT);
+#pragma unroll
+    for (int c = 0; c < DT / 4; ++c) {
+      const float4 v = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(dst + c, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // attention core.  qkvr: [B, F, 4*D] = relu projections [Q | K | V | R] of each field row.
 // One CTA per batch row; thread = (head, field).
 // ------------------------------------------------------------------------------------------
@@ -272,7 +545,7 @@ __global__ void attention_core_fwd_kernel(const float* __restrict__ qkvr, float*
 
 __global__ void attention_core_bwd_kernel(const float* __restrict__ qkvr, const float* __restrict__ Y,
                                           const float* __restrict__ dY, float* __restrict__ d_qkvr, int B, int F,
-                                          int D, int heads, int use_res) {
+                                          int D, int heads, int use_res, int mask_in) {
   extern __shared__ float sm[];
   float* blk = sm;                          // [F][4D] inputs
   float* dz = sm + (size_t)F * 4 * D;       // [F][D]   dLoss / d(pre-relu output)
@@ -334,9 +607,10 @@ __global__ void attention_core_bwd_kernel(const float* __restrict__ qkvr, const 
         for (int c = 0; c < dh; ++c) dq[c] += ds * k[c];
       }
       float* o = dst + (size_t)i * 4 * D + h * dh;
+      const float* res = blk + (size_t)i * 4 * D + 3 * D + h * dh;
       for (int c = 0; c < dh; ++c) {
-        o[c] = dq[c] * scale;
-        o[3 * D + c] = use_res ? dout[c] : 0.f;
+        o[c] = (mask_in && !(q[c] > 0.f)) ? 0.f : dq[c] * scale;
+        o[3 * D + c] = (use_res && !(mask_in && !(res[c] > 0.f))) ? dout[c] : 0.f;
       }
     }
     __syncthreads();
@@ -368,8 +642,8 @@ __global__ void attention_core_bwd_kernel(const float* __restrict__ qkvr, const 
       }
       float* o = dst + (size_t)j * 4 * D + h * dh;
       for (int c = 0; c < dh; ++c) {
-        o[D + c] = dk[c] * scale;
-        o[2 * D + c] = dvv[c];
+        o[D + c] = (mask_in && !(k[c] > 0.f)) ? 0.f : dk[c] * scale;
+        o[2 * D + c] = (mask_in && !(v[c] > 0.f)) ? 0.f : dvv[c];
       }
     }
   }
@@ -382,58 +656,102 @@ __global__ void attention_core_bwd_kernel(const float* __restrict__ qkvr, const 
 // conflict on the innermost loop -- 8.6 ms per launch at 65 536 rows x 26 fields x D = 32, 2 % of the HBM rate).  Shared
 // rows are padded by 4 floats; key / value reads are warp broadcasts.
 // ------------------------------------------------------------------------------------------
+// q/k/v/dout slices of DH floats out of shared memory: 128-bit loads when DH is a multiple of 4 (the scalar form costs one
+// shared-memory wavefront per float, and with one per FMA the kernels ran at the LDS issue rate: 0.93 / 2.7 ms forward /
+// backward per launch at 65 536 rows x 26 fields x 4 heads of 8)
+template <int DH>
+__device__ __forceinline__ void lds_row(const float* __restrict__ p, float (&o)[DH]) {
+  if constexpr (DH % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * c);
+      o[4 * c] = t.x;
+      o[4 * c + 1] = t.y;
+      o[4 * c + 2] = t.z;
+      o[4 * c + 3] = t.w;
+    }
+  } else if constexpr (DH == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    o[0] = t.x;
+    o[1] = t.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o[c] = p[c];
+  }
+}
+
+template <int DH>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[DH]) {
+  if constexpr (DH % 4 == 0) {
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c)
+      *reinterpret_cast<float4*>(p + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+  } else if constexpr (DH == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < DH; ++c) p[c] = v[c];
+  }
+}
+
 template <int DH>
 __global__ void __launch_bounds__(256) attention_core_fwd_t_kernel(const float* __restrict__ qkvr, float* __restrict__ Y, int B, int F, int D,
-                                                                    int heads, int use_res) {
-  extern __shared__ float sm[];     // [F][4D + 4]
+                                                                    int heads, int use_res, int R) {
+  extern __shared__ __align__(16) float sm_all[];     // [R][F][4D + 4]
   const int RS = 4 * D + 4;
   const float scale = rsqrtf((float)DH);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  const int hf = heads * F;
+  const int rr = threadIdx.x / hf, t = threadIdx.x - rr * hf;       // batch row of the CTA's group, (head, field)
+  float* sm = sm_all + (size_t)rr * F * RS;
+  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b * F * 4 * D);
-    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {           // D float4 per field row
-      const int f = e / D, c4 = e - f * D;
-      *reinterpret_cast<float4*>(sm + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+    const int nr = min(R, B - b0);
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0 * F * 4 * D);
+    for (int e = threadIdx.x; e < nr * F * D; e += blockDim.x) {      // D float4 per field row
+      const int f = e / D, c4 = e - f * D;                            // f counts field rows across the group
+      *reinterpret_cast<float4*>(sm_all + (size_t)f * RS + 4 * c4) = __ldg(src + e);
     }
     __syncthreads();
-    const int t = threadIdx.x;
-    if (t < heads * F) {
+    const int b = b0 + rr;
+    if (rr < nr) {
       const int h = t / F, i = t - h * F;
-      float q[DH], acc[DH];
+      float q[DH], acc[DH], kk[DH], vv[DH];
+      lds_row<DH>(sm + (size_t)i * RS + h * DH, q);
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
-        q[c] = sm[(size_t)i * RS + h * DH + c] * scale;
+        q[c] *= scale;
         acc[c] = 0.f;
       }
       float m = -INFINITY;
       for (int j = 0; j < F; ++j) {
-        const float* k = sm + (size_t)j * RS + D + h * DH;
+        lds_row<DH>(sm + (size_t)j * RS + D + h * DH, kk);
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], kk[c], s);
         m = fmaxf(m, s);
       }
       float sum = 0.f;
       for (int j = 0; j < F; ++j) {
         const float* k = sm + (size_t)j * RS + D + h * DH;
-        const float* v = k + D;
+        lds_row<DH>(k, kk);
+        lds_row<DH>(k + D, vv);
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], kk[c], s);
         const float pj = __expf(s - m);
         sum += pj;
 #pragma unroll
-        for (int c = 0; c < DH; ++c) acc[c] = fmaf(pj, v[c], acc[c]);
+        for (int c = 0; c < DH; ++c) acc[c] = fmaf(pj, vv[c], acc[c]);
       }
       const float inv = 1.f / sum;
-      float* y = Y + ((size_t)b * F + i) * D + h * DH;
-      const float* res = sm + (size_t)i * RS + 3 * D + h * DH;
+      lds_row<DH>(sm + (size_t)i * RS + 3 * D + h * DH, vv);       // residual
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
         float o = acc[c] * inv;
-        if (use_res) o += res[c];
-        y[c] = fmaxf(o, 0.f);
+        if (use_res) o += vv[c];
+        acc[c] = fmaxf(o, 0.f);
       }
+      store_row<DH>(Y + ((size_t)b * F + i) * D + h * DH, acc);
     }
   }
 }
@@ -441,109 +759,127 @@ __global__ void __launch_bounds__(256) attention_core_fwd_t_kernel(const float* 
 template <int DH>
 __global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* __restrict__ qkvr, const float* __restrict__ Y,
                                                                     const float* __restrict__ dY, float* __restrict__ d_qkvr, int B,
-                                                                    int F, int D, int heads, int use_res) {
-  extern __shared__ float sm[];
+                                                                    int F, int D, int heads, int use_res, int mask_in,
+                                                                    int R) {
+  extern __shared__ __align__(16) float sm_all[];
   const int RS = 4 * D + 4, RZ = D + 4;
-  float* blk = sm;                          // [F][4D + 4] inputs
-  float* dz = sm + (size_t)F * RS;          // [F][D + 4]  dLoss / d(pre-relu output)
-  float* st = dz + (size_t)F * RZ;          // [heads*F][3]: max, 1/sum, delta
+  const int hf = heads * F;
+  const int rr = threadIdx.x / hf, t = threadIdx.x - rr * hf;       // batch row of the CTA's group, (head, field)
+  float* blk_all = sm_all;                              // [R][F][4D + 4] inputs
+  float* dz_all = sm_all + (size_t)R * F * RS;          // [R][F][D + 4]  dLoss / d(pre-relu output)
+  float* st_all = dz_all + (size_t)R * F * RZ;          // [R][heads*F][4]: max, 1/sum, delta, -
+  float* blk = blk_all + (size_t)rr * F * RS;
+  float* dz = dz_all + (size_t)rr * F * RZ;
+  float* st = st_all + (size_t)rr * hf * 4;
   const float scale = rsqrtf((float)DH);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
     __syncthreads();
-    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b * F * 4 * D);
-    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
-      const int f = e / D, c4 = e - f * D;
-      *reinterpret_cast<float4*>(blk + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+    const int nr = min(R, B - b0);
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0 * F * 4 * D);
+    for (int e = threadIdx.x; e < nr * F * D; e += blockDim.x) {
+      const int f = e / D, c4 = e - f * D;                            // f counts field rows across the group
+      *reinterpret_cast<float4*>(blk_all + (size_t)f * RS + 4 * c4) = __ldg(src + e);
     }
-    for (int e = threadIdx.x; e < F * D; e += blockDim.x) {
-      const size_t o = (size_t)b * F * D + e;
-      const int f = e / D, c = e - f * D;
-      dz[(size_t)f * RZ + c] = Y[o] > 0.f ? dY[o] : 0.f;
+    {
+      const float4* y4 = reinterpret_cast<const float4*>(Y + (size_t)b0 * F * D);
+      const float4* dy4 = reinterpret_cast<const float4*>(dY + (size_t)b0 * F * D);
+      const int d4 = D / 4;
+      for (int e = threadIdx.x; e < nr * F * d4; e += blockDim.x) {
+        const int f = e / d4, c4 = e - f * d4;
+        const float4 y = __ldg(y4 + e), g = __ldg(dy4 + e);
+        *reinterpret_cast<float4*>(dz_all + (size_t)f * RZ + 4 * c4) =
+            make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
+      }
     }
     __syncthreads();
-    const int t = threadIdx.x;
+    const int b = b0 + rr;
+    const bool live = rr < nr;
     float* dst = d_qkvr + (size_t)b * F * 4 * D;
     // phase 1: thread (h, i): softmax statistics, delta = dout . out, dQ row, dRes row
-    if (t < heads * F) {
+    if (live) {
       const int h = t / F, i = t - h * F;
-      float q[DH], dout[DH], dq[DH];
+      float q[DH], dout[DH], dq[DH], kk[DH], vv[DH];
+      lds_row<DH>(blk + (size_t)i * RS + h * DH, q);
+      lds_row<DH>(dz + (size_t)i * RZ + h * DH, dout);
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
-        q[c] = blk[(size_t)i * RS + h * DH + c] * scale;
-        dout[c] = dz[(size_t)i * RZ + h * DH + c];
+        q[c] *= scale;
         dq[c] = 0.f;
       }
       float m = -INFINITY;
       for (int j = 0; j < F; ++j) {
-        const float* k = blk + (size_t)j * RS + D + h * DH;
+        lds_row<DH>(blk + (size_t)j * RS + D + h * DH, kk);
         float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < DH; ++c) s = fmaf(q[c], k[c], s);
+        for (int c = 0; c < DH; ++c) s = fmaf(q[c], kk[c], s);
         m = fmaxf(m, s);
       }
-      float sum = 0.f, dsum = 0.f;       // dsum = sum_j p_j (dout . v_j)  (un-normalised)
+      // one sweep: with p_j = exp(s_j - m) un-normalised, dQ = (sum_j p_j dv_j k_j - delta sum_j p_j k_j) / sum_j p_j
+      float sum = 0.f, dsum = 0.f;       // dsum = sum_j p_j (dout . v_j)
+      float pk[DH];
+#pragma unroll
+      for (int c = 0; c < DH; ++c) pk[c] = 0.f;
       for (int j = 0; j < F; ++j) {
         const float* k = blk + (size_t)j * RS + D + h * DH;
-        const float* v = k + D;
+        lds_row<DH>(k, kk);
+        lds_row<DH>(k + D, vv);
         float s = 0.f, dv = 0.f;
 #pragma unroll
         for (int c = 0; c < DH; ++c) {
-          s = fmaf(q[c], k[c], s);
-          dv = fmaf(dout[c], v[c], dv);
+          s = fmaf(q[c], kk[c], s);
+          dv = fmaf(dout[c], vv[c], dv);
         }
         const float pj = __expf(s - m);
+        const float w = pj * dv;
         sum += pj;
-        dsum = fmaf(pj, dv, dsum);
+        dsum += w;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) {
+          dq[c] = fmaf(w, kk[c], dq[c]);
+          pk[c] = fmaf(pj, kk[c], pk[c]);
+        }
       }
       const float inv = 1.f / sum;
       const float delta = dsum * inv;
-      st[t * 3 + 0] = m;
-      st[t * 3 + 1] = inv;
-      st[t * 3 + 2] = delta;
-      for (int j = 0; j < F; ++j) {
-        const float* k = blk + (size_t)j * RS + D + h * DH;
-        const float* v = k + D;
-        float s = 0.f, dv = 0.f;
-#pragma unroll
-        for (int c = 0; c < DH; ++c) {
-          s = fmaf(q[c], k[c], s);
-          dv = fmaf(dout[c], v[c], dv);
-        }
-        const float ds = __expf(s - m) * inv * (dv - delta);
-#pragma unroll
-        for (int c = 0; c < DH; ++c) dq[c] = fmaf(ds, k[c], dq[c]);
-      }
+      *reinterpret_cast<float4*>(st + t * 4) = make_float4(m, inv, delta, 0.f);
       float* o = dst + (size_t)i * 4 * D + h * DH;
+      if (mask_in) lds_row<DH>(blk + (size_t)i * RS + 3 * D + h * DH, vv);      // residual projection (relu output)
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
-        o[c] = dq[c] * scale;
-        o[3 * D + c] = use_res ? dout[c] : 0.f;
+        dq[c] = (dq[c] - delta * pk[c]) * inv * scale;
+        if (!use_res) dout[c] = 0.f;
+        if (mask_in) {                    // gradient w.r.t. the PRE-relu projections: zero where the relu output is zero
+          if (!(q[c] > 0.f)) dq[c] = 0.f;
+          if (!(vv[c] > 0.f)) dout[c] = 0.f;
+        }
       }
+      store_row<DH>(o, dq);
+      store_row<DH>(o + 3 * D, dout);
     }
     __syncthreads();
     // phase 2: thread (h, j): dK row, dV row
-    if (t < heads * F) {
+    if (live) {
       const int h = t / F, j = t - h * F;
-      float k[DH], v[DH], dk[DH], dvv[DH];
+      float k[DH], v[DH], dk[DH], dvv[DH], q[DH], dout[DH];
+      lds_row<DH>(blk + (size_t)j * RS + D + h * DH, k);
+      lds_row<DH>(blk + (size_t)j * RS + 2 * D + h * DH, v);
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
-        k[c] = blk[(size_t)j * RS + D + h * DH + c];
-        v[c] = blk[(size_t)j * RS + 2 * D + h * DH + c];
         dk[c] = 0.f;
         dvv[c] = 0.f;
       }
       for (int i = 0; i < F; ++i) {
-        const float* q = blk + (size_t)i * RS + h * DH;
-        const float* dout = dz + (size_t)i * RZ + h * DH;
-        const float* s3 = st + (h * F + i) * 3;
+        lds_row<DH>(blk + (size_t)i * RS + h * DH, q);
+        lds_row<DH>(dz + (size_t)i * RZ + h * DH, dout);
+        const float4 s3 = *reinterpret_cast<const float4*>(st + (h * F + i) * 4);
         float s = 0.f, dv = 0.f;
 #pragma unroll
         for (int c = 0; c < DH; ++c) {
           s = fmaf(q[c], k[c], s);
           dv = fmaf(dout[c], v[c], dv);
         }
-        const float pij = __expf(s * scale - s3[0]) * s3[1];
-        const float ds = pij * (dv - s3[2]);
+        const float pij = __expf(s * scale - s3.x) * s3.y;
+        const float ds = pij * (dv - s3.z);
 #pragma unroll
         for (int c = 0; c < DH; ++c) {
           dk[c] = fmaf(ds, q[c], dk[c]);
@@ -553,9 +889,14 @@ __global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* 
       float* o = dst + (size_t)j * 4 * D + h * DH;
 #pragma unroll
       for (int c = 0; c < DH; ++c) {
-        o[D + c] = dk[c] * scale;
-        o[2 * D + c] = dvv[c];
+        dk[c] *= scale;
+        if (mask_in) {
+          if (!(k[c] > 0.f)) dk[c] = 0.f;
+          if (!(v[c] > 0.f)) dvv[c] = 0.f;
+        }
       }
+      store_row<DH>(o + D, dk);
+      store_row<DH>(o + 2 * D, dvv);
     }
   }
 }
@@ -563,6 +904,23 @@ __global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* 
 }  // namespace dtb
 
 using namespace dtb;
+
+namespace {
+constexpr size_t kPnnTSmemMax = 200 * 1024;
+// the (row, field) kernels need a power-of-two width in 4..32 and 16-byte aligned rows
+// attention kernels: batch rows per CTA so that a CTA has about 128 (head, field) threads
+int att_rows_per_cta(int hf) { return hf >= 128 ? 1 : 128 / hf; }
+int att_threads(int R, int hf) {
+  const int t = (R * hf + 31) / 32 * 32;
+  return t < 64 ? 64 : t;
+}
+bool pnn_t_shape(int D, const void* table, const void* grad_table) {
+  if (D != 4 && D != 8 && D != 16 && D != 32) return false;
+  if (reinterpret_cast<uintptr_t>(table) & 15) return false;
+  if (grad_table && (reinterpret_cast<uintptr_t>(grad_table) & 15)) return false;
+  return true;
+}
+}  // namespace
 
 extern "C" {
 
@@ -577,6 +935,26 @@ int dtb_pnn_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
   if (P > 1024) {
     set_error("dtb_pnn_fwd: %d pairs exceed one CTA", P);
     return DTB_ERR_UNSUPPORTED;
+  }
+  {
+    const size_t per = kernel_type == 0 ? (size_t)D * D : (kernel_type == 1 ? (size_t)D : 1);
+    const size_t smem_t = op ? (size_t)(F - 1) * per * sizeof(float) : 0;
+    if (pnn_t_shape(D, table, nullptr) && smem_t <= kPnnTSmemMax) {
+      // chunk groups: about 8 resident CTAs per SM in total, each CTA amortising its kernel-slice staging over its chunks
+      int groups = ceil_div(sm_count() * 8, F - 1);
+      if (groups > ceil_div(B, kPnnTRows)) groups = ceil_div(B, kPnnTRows);
+      const dim3 grid(F - 1, groups);
+#define DTB_PNN_FWD(DV)                                                                                                  \
+  case DV:                                                                                                               \
+    DTB_CUDA_OK(cudaFuncSetAttribute(pnn_fwd_t_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));  \
+    pnn_fwd_t_kernel<DV><<<grid, kPnnTRows, smem_t, (cudaStream_t)stream>>>(idx, table, row_offsets, op_kernel, ip, op,  \
+                                                                            B, F, P, kernel_type, status);              \
+    break;
+      switch (D) { DTB_PNN_FWD(4) DTB_PNN_FWD(8) DTB_PNN_FWD(16) DTB_PNN_FWD(32) }
+#undef DTB_PNN_FWD
+      DTB_LAUNCH_OK();
+      return DTB_OK;
+    }
   }
   const int threads = (P + 31) / 32 * 32;
   const size_t smem = (size_t)kPnnRows * F * D * sizeof(float);
@@ -597,11 +975,50 @@ int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
   const int P = F * (F - 1) / 2;
   const int threads = (P + 31) / 32 * 32;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)2 * kPnnRows * F * D * sizeof(float);
-  DTB_CUDA_OK(cudaFuncSetAttribute(pnn_bwd_de_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pnn_bwd_de_kernel<<<ceil_div(B, kPnnRows), threads, smem, st>>>(idx, table, row_offsets, op_kernel, d_ip, d_op,
-                                                                  grad_table, B, F, D, P, kernel_type);
+  const size_t per = kernel_type == 0 ? (size_t)D * D : (kernel_type == 1 ? (size_t)D : 1);
+  const size_t smem_t = d_op ? (size_t)(F - 1) * per * sizeof(float) : 0;
+  const bool t_shape = pnn_t_shape(D, table, grad_table) && smem_t <= kPnnTSmemMax;
+  if (t_shape) {
+    int groups = ceil_div(sm_count() * 8, F);
+    if (groups > ceil_div(B, kPnnTRows)) groups = ceil_div(B, kPnnTRows);
+    const dim3 grid(F, groups);
+#define DTB_PNN_DE(DV)                                                                                                   \
+  case DV:                                                                                                               \
+    DTB_CUDA_OK(cudaFuncSetAttribute(pnn_bwd_de_t_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t)); \
+    pnn_bwd_de_t_kernel<DV><<<grid, kPnnTRows, smem_t, st>>>(idx, table, row_offsets, op_kernel, d_ip, d_op, grad_table, \
+                                                             B, F, P, kernel_type);                                     \
+    break;
+    switch (D) { DTB_PNN_DE(4) DTB_PNN_DE(8) DTB_PNN_DE(16) DTB_PNN_DE(32) }
+#undef DTB_PNN_DE
+  } else {
+    const size_t smem = (size_t)2 * kPnnRows * F * D * sizeof(float);
+    DTB_CUDA_OK(cudaFuncSetAttribute(pnn_bwd_de_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pnn_bwd_de_kernel<<<ceil_div(B, kPnnRows), threads, smem, st>>>(idx, table, row_offsets, op_kernel, d_ip, d_op,
+                                                                    grad_table, B, F, D, P, kernel_type);
+  }
   DTB_LAUNCH_OK();
+  if (d_op && kernel_type == 0 && t_shape && (reinterpret_cast<uintptr_t>(d_op_kernel) & 15) == 0) {
+    const int pg = 256 / D, groups = ceil_div(P, pg);
+    int R = 32;
+    while (R > 4 && (size_t)R * (F * D + pg) * sizeof(float) > kPnnTSmemMax / 2) R /= 2;
+    const size_t smem_k = (size_t)R * (F * D + pg) * sizeof(float);
+    if (smem_k <= kPnnTSmemMax) {
+      int row_groups = ceil_div(sm_count() * 2, groups);
+      if (row_groups > ceil_div(B, R)) row_groups = ceil_div(B, R);
+      const int rows_per_cta = ceil_div(ceil_div(B, row_groups), R) * R;
+      const dim3 grid(groups, ceil_div(B, rows_per_cta));
+#define DTB_PNN_DK(DV)                                                                                                   \
+  case DV:                                                                                                               \
+    DTB_CUDA_OK(cudaFuncSetAttribute(pnn_bwd_dk_t_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k)); \
+    pnn_bwd_dk_t_kernel<DV><<<grid, 256, smem_k, st>>>(idx, table, row_offsets, d_op, d_op_kernel, B, F, P, rows_per_cta, \
+                                                       R);                                                              \
+    break;
+      switch (D) { DTB_PNN_DK(4) DTB_PNN_DK(8) DTB_PNN_DK(16) DTB_PNN_DK(32) }
+#undef DTB_PNN_DK
+      DTB_LAUNCH_OK();
+      return DTB_OK;
+    }
+  }
   if (d_op) {
     int ctas = sm_count() * 2;
     if (ctas > B) ctas = B;
@@ -625,13 +1042,17 @@ int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int
   if (grid > B) grid = B;
   const int dh = D / heads;
   const int nthr = threads < 64 ? 64 : threads;
-  if (D % 4 == 0 && nthr <= 256 && (reinterpret_cast<uintptr_t>(qkvr) & 15) == 0) {
-    const size_t smem_t = (size_t)F * (4 * D + 4) * sizeof(float);
+  if (D % 4 == 0 && nthr <= 256 && ((reinterpret_cast<uintptr_t>(qkvr) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0) {
+    const int R = att_rows_per_cta(heads * F);
+    const int nthr_t = att_threads(R, heads * F);
+    const size_t smem_t = (size_t)R * F * (4 * D + 4) * sizeof(float);
+    if (grid > ceil_div(B, R)) grid = ceil_div(B, R);
 #define DTB_ATT_FWD(DHV)                                                                                                   \
   case DHV:                                                                                                                \
     DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_fwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                      (int)smem_t));                                                                         \
-    attention_core_fwd_t_kernel<DHV><<<grid, nthr, smem_t, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads, use_residual); \
+    attention_core_fwd_t_kernel<DHV><<<grid, nthr_t, smem_t, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads,            \
+                                                                                     use_residual, R);                   \
     DTB_LAUNCH_OK();                                                                                                       \
     return DTB_OK;
     switch (dh) {
@@ -648,7 +1069,7 @@ int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int
 }
 
 int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, float* d_qkvr, int B, int F, int D,
-                           int heads, int use_residual, void* stream) {
+                           int heads, int use_residual, int mask_relu_inputs, void* stream) {
   DTB_CHECK_ARG(qkvr && Y && dY && d_qkvr, "NULL argument");
   DTB_CHECK_ARG(B >= 0 && F >= 1 && D >= 1 && heads >= 1 && D % heads == 0, "bad shape (num_heads must divide D)");
   DTB_CHECK_ARG(D / heads <= kMaxDh && heads * F <= 1024, "head width <= 64 and heads*fields <= 1024");
@@ -658,14 +1079,21 @@ int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, f
   if (grid > B) grid = B;
   const int dh = D / heads;
   const int nthr = threads < 64 ? 64 : threads;
-  if (D % 4 == 0 && nthr <= 256 && (reinterpret_cast<uintptr_t>(qkvr) & 15) == 0) {
-    const size_t smem_t = ((size_t)F * (4 * D + 4) + (size_t)F * (D + 4) + (size_t)heads * F * 3) * sizeof(float);
+  if (D % 4 == 0 && nthr <= 256 &&
+      ((reinterpret_cast<uintptr_t>(qkvr) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY) |
+        reinterpret_cast<uintptr_t>(d_qkvr)) & 15) == 0) {
+    const int R = att_rows_per_cta(heads * F);
+    const int nthr_t = att_threads(R, heads * F);
+    const size_t smem_t =
+        (size_t)R * ((size_t)F * (4 * D + 4) + (size_t)F * (D + 4) + (size_t)heads * F * 4) * sizeof(float);
+    if (grid > ceil_div(B, R)) grid = ceil_div(B, R);
 #define DTB_ATT_BWD(DHV)                                                                                                \
   case DHV:                                                                                                             \
     DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                      (int)smem_t));                                                                      \
-    attention_core_bwd_t_kernel<DHV><<<grid, nthr, smem_t, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D, heads, \
-                                                                                   use_residual);                       \
+    attention_core_bwd_t_kernel<DHV><<<grid, nthr_t, smem_t, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D,      \
+                                                                                     heads, use_residual,                \
+                                                                                     mask_relu_inputs, R);               \
     DTB_LAUNCH_OK();                                                                                                    \
     return DTB_OK;
     switch (dh) {
@@ -676,7 +1104,8 @@ int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, f
   }
   const size_t smem = ((size_t)F * 5 * D + (size_t)heads * F * 3) * sizeof(float);
   DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_core_bwd_kernel<<<grid, nthr, smem, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D, heads, use_residual);
+  attention_core_bwd_kernel<<<grid, nthr, smem, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D, heads, use_residual,
+                                                                        mask_relu_inputs);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -368,7 +368,9 @@ class DenseFn(torch.autograd.Function):
     """keras Dense: act(x @ kernel + bias) over the last axis."""
 
     @staticmethod
-    def forward(ctx, x, kernel, bias, act):
+    def forward(ctx, x, kernel, bias, act, grad_premasked=False):
+        """grad_premasked: the consumer's backward already returns the gradient of the PRE-activation (it zeroes it
+        where this layer's relu output is zero: AttentionCoreFn with mask_inputs) -- no activation-gradient pass."""
         x = _f32(x)
         in_dim, out_dim = kernel.shape
         rows = x.numel() // in_dim
@@ -377,6 +379,9 @@ class DenseFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         check(N.lib.dtb_dense_fwd(ptr(x), ptr(kernel), ptr(bias), ptr(y), ptr(ws), ws_bytes, rows, in_dim, out_dim, act,
                                   stream_ptr()), 'dense_fwd')
+        if grad_premasked:
+            assert act == ACT_CODES['relu']
+            act = 0
         ctx.save_for_backward(x, kernel, y if act else None)
         ctx.has_bias, ctx.act = bias is not None, act
         return y
@@ -386,7 +391,9 @@ class DenseFn(torch.autograd.Function):
         x, kernel, y = ctx.saved_tensors
         in_dim, out_dim = kernel.shape
         rows = x.numel() // in_dim
-        dz = dy.contiguous().float().clone()            # overwritten with d(pre-activation)
+        dz = dy.contiguous().float()
+        if ctx.act:
+            dz = dz.clone()                             # overwritten with d(pre-activation)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.zeros_like(kernel)
         db = torch.zeros(out_dim, dtype=torch.float32, device=x.device) if ctx.has_bias else None
@@ -394,7 +401,7 @@ class DenseFn(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device) if ws_bytes else None
         check(N.lib.dtb_dense_bwd(ptr(x), ptr(kernel), ptr(y), ptr(dz), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws_bytes,
                                   rows, in_dim, out_dim, ctx.act, stream_ptr()), 'dense_bwd')
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 class CINFn(torch.autograd.Function):
@@ -516,7 +523,8 @@ class AttentionCoreFn(torch.autograd.Function):
     (layers.py:129-150): per-head softmax(QK^T/sqrt(dh))V + residual, relu."""
 
     @staticmethod
-    def forward(ctx, qkvr, heads, use_residual):
+    def forward(ctx, qkvr, heads, use_residual, mask_inputs=False):
+        """mask_inputs: qkvr are relu outputs and backward returns the gradient of their pre-activations."""
         qkvr = _f32(qkvr)
         b, f, d4 = qkvr.shape
         d = d4 // 4
@@ -524,19 +532,19 @@ class AttentionCoreFn(torch.autograd.Function):
         check(N.lib.dtb_attention_core_fwd(ptr(qkvr), ptr(y), b, f, d, heads, int(use_residual), stream_ptr()),
               'attention_core_fwd')
         ctx.save_for_backward(qkvr, y)
-        ctx.cfg = (heads, int(use_residual))
+        ctx.cfg = (heads, int(use_residual), int(bool(mask_inputs)))
         return y
 
     @staticmethod
     def backward(ctx, dy):
         qkvr, y = ctx.saved_tensors
         b, f, d4 = qkvr.shape
-        heads, use_res = ctx.cfg
+        heads, use_res, mask = ctx.cfg
         dy = _f32(dy)
         dq = torch.empty_like(qkvr)
-        check(N.lib.dtb_attention_core_bwd(ptr(qkvr), ptr(y), ptr(dy), ptr(dq), b, f, d4 // 4, heads, use_res,
+        check(N.lib.dtb_attention_core_bwd(ptr(qkvr), ptr(y), ptr(dy), ptr(dq), b, f, d4 // 4, heads, use_res, mask,
                                            stream_ptr()), 'attention_core_bwd')
-        return dq, None, None
+        return dq, None, None, None
 
 
 TASK_CODES = {'binary': 0, 'multilabel': 0, 'regression': 1, 'multiclass': 2}

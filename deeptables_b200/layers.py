@@ -338,8 +338,10 @@ class MultiheadAttention(Layer):
             ws.append(scope.param(f'{self.name}/{proj}/kernel', (d, d), 'he_uniform'))
             bs.append(scope.param(f'{self.name}/{proj}/bias', (d,), 'zeros'))
         # the four relu(Dense) projections as ONE GEMM: kernels side by side -> [B, F, 4D] = [Q|K|V|R]
-        qkvr = E.DenseFn.apply(x, torch.cat(ws, dim=1), torch.cat(bs), E.ACT_CODES['relu'])
-        out = E.AttentionCoreFn.apply(qkvr, int(self.num_heads), bool(self.use_residual))
+        # the attention backward has the relu outputs in shared memory and applies their mask itself, so the [B*F, 4D]
+        # activation-gradient pass (and the gradient clone it needs) of the projection layer is skipped
+        qkvr = E.DenseFn.apply(x, torch.cat(ws, dim=1), torch.cat(bs), E.ACT_CODES['relu'], True)
+        out = E.AttentionCoreFn.apply(qkvr, int(self.num_heads), bool(self.use_residual), True)
         with scope.name_prefix(self.name):
             return BatchNormalization(name='batch_normalize')(out)
 

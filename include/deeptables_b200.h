@@ -253,11 +253,14 @@ int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
 /* ---- MultiheadAttention core (layers.py:129-150), between the projections and the BN ------- */
 /* qkvr [B, F, 4*D]: the four relu(Dense) projections of each field row, concatenated [Q|K|V|R]
  * (one dtb_dense_fwd with the four kernels side by side).  Y[B,F,D] = relu(concat_h softmax(Q_h
- * K_h^T / sqrt(D/heads)) V_h + R).  Backward: d_qkvr [B,F,4*D] (overwritten). */
+ * K_h^T / sqrt(D/heads)) V_h + R).  Backward: d_qkvr [B,F,4*D] (overwritten); with mask_relu_inputs
+ * the result is zeroed where qkvr is zero, i.e. it is the gradient of the PRE-relu projections (the
+ * caller then runs dtb_dense_bwd with act = linear and skips the activation-gradient pass). */
 int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int heads,
                            int use_residual, void* stream);
 int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, float* d_qkvr, int B,
-                           int F, int D, int heads, int use_residual, void* stream);
+                           int F, int D, int heads, int use_residual, int mask_relu_inputs,
+                           void* stream);
 
 #ifdef __cplusplus
 }

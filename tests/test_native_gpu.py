@@ -688,7 +688,7 @@ def test_cin_tensor_core_backward(nat, f, d, sizes, direct, use_bias, act, b):
 # ---------------------------------------------------------------------------------------------
 # PNN products and the AutoInt attention core
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('f,d,b', [(26, 16, 70), (5, 4, 33), (2, 8, 9), (7, 3, 20)])
+@pytest.mark.parametrize('f,d,b', [(26, 16, 70), (5, 4, 33), (2, 8, 9), (7, 3, 20), (6, 32, 150), (26, 16, 300), (12, 8, 200)])
 @pytest.mark.parametrize('ktype', ['mat', 'vec', 'num'])
 def test_pnn_fwd_bwd(nat, f, d, b, ktype):
     vocab = [11 + i for i in range(f)]
@@ -724,7 +724,8 @@ def test_pnn_fwd_bwd(nat, f, d, b, ktype):
     np.testing.assert_allclose(dk.cpu().numpy(), grads[-1].numpy(), rtol=1e-3, atol=1e-4 * np.abs(grads[-1].numpy()).max())
 
 
-@pytest.mark.parametrize('b,f,d,heads,res', [(40, 26, 32, 4, True), (17, 5, 4, 1, True), (9, 7, 16, 2, False), (3, 1, 8, 8, True)])
+@pytest.mark.parametrize('b,f,d,heads,res', [(40, 26, 32, 4, True), (17, 5, 4, 1, True), (9, 7, 16, 2, False), (3, 1, 8, 8, True),
+                                               (1001, 26, 16, 1, True), (131, 26, 32, 4, False), (70, 3, 64, 1, True)])
 def test_attention_core_fwd_bwd(nat, b, f, d, heads, res):
     g = np.random.default_rng(54)
     qkvr = np.maximum(g.normal(size=(b, f, 4 * d)), 0).astype(np.float32)       # relu outputs
@@ -744,6 +745,10 @@ def test_attention_core_fwd_bwd(nat, b, f, d, heads, res):
     np.testing.assert_allclose(y.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
     dy = g.normal(size=(b, f, d)).astype(np.float32)
     dq = torch.empty(b, f, 4 * d, device='cuda')
-    nat.check(nat.lib.dtb_attention_core_bwd(P(d_in), P(y), P(dev(dy)), P(dq), b, f, d, heads, int(res), None))
+    nat.check(nat.lib.dtb_attention_core_bwd(P(d_in), P(y), P(dev(dy)), P(dq), b, f, d, heads, int(res), 0, None))
     (gx,) = torch.autograd.grad((want * torch.tensor(dy, dtype=torch.float64)).sum(), [x64])
     np.testing.assert_allclose(dq.cpu().numpy(), gx.numpy(), rtol=1e-3, atol=1e-4 * max(1.0, float(gx.abs().max())))
+    # mask_relu_inputs: the same gradient, zeroed where the (relu-output) input is zero
+    dqm = torch.empty(b, f, 4 * d, device='cuda')
+    nat.check(nat.lib.dtb_attention_core_bwd(P(d_in), P(y), P(dev(dy)), P(dqm), b, f, d, heads, int(res), 1, None))
+    assert torch.equal(dqm, dq * (d_in.view(b, f, 4 * d) > 0))
