@@ -374,19 +374,29 @@ __global__ void __launch_bounds__(kPnnTRows) pnn_bwd_de_t_kernel(const int32_t* 
 #pragma unroll
     for (int d = 0; d < DT; ++d) acc[d] = 0.f;
     gather_row<DT>(idx, table, row_offsets, row, F, f == 0 ? 1 : 0, en, nullptr, nullptr);
+    float gi_n = 0.f, go_n = 0.f;
+    {
+      const int p = f == 0 ? pair_index(0, 1, F) : pair_index(0, f, F);
+      if (d_ip) gi_n = __ldg(d_ip + (size_t)row * P + p);
+      if (d_op) go_n = __ldg(d_op + (size_t)row * P + p);
+    }
     for (int q = 0; q < F - 1; ++q) {
       const int o = q < f ? q : q + 1;
-      const int p = o < f ? pair_index(o, f, F) : pair_index(f, o, F);
 #pragma unroll
       for (int d = 0; d < DT; ++d) eo[d] = en[d];
-      if (q + 1 < F - 1) gather_row<DT>(idx, table, row_offsets, row, F, q + 1 < f ? q + 1 : q + 2, en, nullptr, nullptr);
+      const float gi = gi_n, go = go_n;
+      if (q + 1 < F - 1) {                       // next pair's operands are requested before this pair's FMAs
+        const int on = q + 1 < f ? q + 1 : q + 2;
+        const int pn = on < f ? pair_index(on, f, F) : pair_index(f, on, F);
+        gather_row<DT>(idx, table, row_offsets, row, F, on, en, nullptr, nullptr);
+        if (d_ip) gi_n = __ldg(d_ip + (size_t)row * P + pn);
+        if (d_op) go_n = __ldg(d_op + (size_t)row * P + pn);
+      }
       if (d_ip) {
-        const float gi = __ldg(d_ip + (size_t)row * P + p);
 #pragma unroll
         for (int d = 0; d < DT; ++d) acc[d] = fmaf(gi, eo[d], acc[d]);
       }
       if (d_op) {
-        const float go = __ldg(d_op + (size_t)row * P + p);
         if (ktype == 0) {
           const float* kq = ks + (size_t)q * DT * DT;
           if (f < o) {
@@ -457,13 +467,32 @@ __global__ void __launch_bounds__(256) pnn_bwd_dk_t_kernel(const int32_t* __rest
   for (int r0 = r_begin; r0 < r_end; r0 += R) {
     const int nr = min(R, r_end - r0);
     __syncthreads();
-    for (int e = threadIdx.x; e < nr * F * (DT / 4); e += blockDim.x) {
-      const int r = e / (F * (DT / 4)), rem = e - r * F * (DT / 4);
-      const int f = rem / (DT / 4), c = rem - f * (DT / 4);
-      const int64_t rb = table_row(row_offsets, f, __ldg(idx + (int64_t)(r0 + r) * F + f), DT, nullptr);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rb >= 0) v = __ldg(reinterpret_cast<const float4*>(table + rb) + c);
-      reinterpret_cast<float4*>(es)[e] = v;
+    // gather in batches of 8 per thread: 8 index loads in flight, then 8 row loads, then the stores (one load per
+    // iteration left 64 % of the kernel's stall samples on the two dependent latencies)
+    const int n_vec = nr * F * (DT / 4);
+    for (int e0 = threadIdx.x; e0 < n_vec; e0 += 8 * blockDim.x) {
+      int id[8];
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_vec) id[u] = __ldg(idx + (int64_t)r0 * F + e / (DT / 4));     // (r, f) row-major == e / (DT/4)
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * blockDim.x;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < n_vec) {
+          const int rf = e / (DT / 4), c = e - rf * (DT / 4);
+          const int64_t rb = table_row(row_offsets, rf % F, id[u], DT, nullptr);
+          if (rb >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(table + rb) + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * blockDim.x;
+        if (e < n_vec) reinterpret_cast<float4*>(es)[e] = v[u];
+      }
     }
     for (int e = threadIdx.x; e < nr * kPg; e += blockDim.x) {
       const int r = e / kPg, q = e - r * kPg;
@@ -694,24 +723,44 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v
   }
 }
 
+// 16-byte asynchronous global -> shared copies: the next batch-row group is requested before the current one is computed
+// (with the plain load -> store staging a third of the backward kernel's stall samples sat on the load latency in front of
+// the CTA barrier)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int DH>
 __global__ void __launch_bounds__(256) attention_core_fwd_t_kernel(const float* __restrict__ qkvr, float* __restrict__ Y, int B, int F, int D,
-                                                                    int heads, int use_res, int R) {
-  extern __shared__ __align__(16) float sm_all[];     // [R][F][4D + 4]
+                                                                    int heads, int use_res, int R, int nbuf) {
+  extern __shared__ __align__(16) float sm_all[];     // [nbuf][R][F][4D + 4]
   const int RS = 4 * D + 4;
   const float scale = rsqrtf((float)DH);
   const int hf = heads * F;
   const int rr = threadIdx.x / hf, t = threadIdx.x - rr * hf;       // batch row of the CTA's group, (head, field)
-  float* sm = sm_all + (size_t)rr * F * RS;
-  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
-    __syncthreads();
-    const int nr = min(R, B - b0);
-    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0 * F * 4 * D);
-    for (int e = threadIdx.x; e < nr * F * D; e += blockDim.x) {      // D float4 per field row
+  const size_t buf_floats = (size_t)R * F * RS;
+  auto issue = [&](int b0n, int bufn) {
+    const int nrn = min(R, B - b0n);
+    float* dst = sm_all + bufn * buf_floats;
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0n * F * 4 * D);
+    for (int e = threadIdx.x; e < nrn * F * D; e += blockDim.x) {     // D float4 per field row
       const int f = e / D, c4 = e - f * D;                            // f counts field rows across the group
-      *reinterpret_cast<float4*>(sm_all + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+      cp_async16(dst + (size_t)f * RS + 4 * c4, src + e);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  int buf = 0;
+  if ((int)blockIdx.x * R < B) issue(blockIdx.x * R, 0);
+  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
+    const int nr = min(R, B - b0);
+    const int b0n = b0 + gridDim.x * R;
+    cp_async_wait_all();
+    __syncthreads();                     // this group's block is complete; every thread is done with the other buffer
+    if (nbuf == 2 && b0n < B) issue(b0n, buf ^ 1);
+    const float* sm = sm_all + buf * buf_floats + (size_t)rr * F * RS;
     const int b = b0 + rr;
     if (rr < nr) {
       const int h = t / F, i = t - h * F;
@@ -753,6 +802,12 @@ __global__ void __launch_bounds__(256) attention_core_fwd_t_kernel(const float* 
       }
       store_row<DH>(Y + ((size_t)b * F + i) * D + h * DH, acc);
     }
+    if (nbuf == 2) {
+      buf ^= 1;
+    } else if (b0n < B) {
+      __syncthreads();
+      issue(b0n, 0);
+    }
   }
 }
 
@@ -760,38 +815,57 @@ template <int DH>
 __global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* __restrict__ qkvr, const float* __restrict__ Y,
                                                                     const float* __restrict__ dY, float* __restrict__ d_qkvr, int B,
                                                                     int F, int D, int heads, int use_res, int mask_in,
-                                                                    int R) {
+                                                                    int R, int nbuf) {
   extern __shared__ __align__(16) float sm_all[];
   const int RS = 4 * D + 4, RZ = D + 4;
   const int hf = heads * F;
   const int rr = threadIdx.x / hf, t = threadIdx.x - rr * hf;       // batch row of the CTA's group, (head, field)
-  float* blk_all = sm_all;                              // [R][F][4D + 4] inputs
-  float* dz_all = sm_all + (size_t)R * F * RS;          // [R][F][D + 4]  dLoss / d(pre-relu output)
-  float* st_all = dz_all + (size_t)R * F * RZ;          // [R][heads*F][4]: max, 1/sum, delta, -
-  float* blk = blk_all + (size_t)rr * F * RS;
-  float* dz = dz_all + (size_t)rr * F * RZ;
-  float* st = st_all + (size_t)rr * hf * 4;
+  // per buffer: [R][F][4D + 4] inputs | [R][F][D + 4] dY, masked in place to dLoss/d(pre-relu output) | [R][F][D + 4] Y
+  const size_t blk_floats = (size_t)R * F * RS, z_floats = (size_t)R * F * RZ;
+  const size_t buf_floats = blk_floats + 2 * z_floats;
+  float* st = sm_all + nbuf * buf_floats + (size_t)rr * hf * 4;     // [R][heads*F][4]: max, 1/sum, delta, -
   const float scale = rsqrtf((float)DH);
-  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
-    __syncthreads();
-    const int nr = min(R, B - b0);
-    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0 * F * 4 * D);
-    for (int e = threadIdx.x; e < nr * F * D; e += blockDim.x) {
+  const int d4 = D / 4;
+  auto issue = [&](int b0n, int bufn) {
+    const int nrn = min(R, B - b0n);
+    float* dst = sm_all + bufn * buf_floats;
+    const float4* src = reinterpret_cast<const float4*>(qkvr + (size_t)b0n * F * 4 * D);
+    for (int e = threadIdx.x; e < nrn * F * D; e += blockDim.x) {
       const int f = e / D, c4 = e - f * D;                            // f counts field rows across the group
-      *reinterpret_cast<float4*>(blk_all + (size_t)f * RS + 4 * c4) = __ldg(src + e);
+      cp_async16(dst + (size_t)f * RS + 4 * c4, src + e);
     }
-    {
-      const float4* y4 = reinterpret_cast<const float4*>(Y + (size_t)b0 * F * D);
-      const float4* dy4 = reinterpret_cast<const float4*>(dY + (size_t)b0 * F * D);
-      const int d4 = D / 4;
-      for (int e = threadIdx.x; e < nr * F * d4; e += blockDim.x) {
-        const int f = e / d4, c4 = e - f * d4;
-        const float4 y = __ldg(y4 + e), g = __ldg(dy4 + e);
-        *reinterpret_cast<float4*>(dz_all + (size_t)f * RZ + 4 * c4) =
-            make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
-      }
+    const float4* y4 = reinterpret_cast<const float4*>(Y + (size_t)b0n * F * D);
+    const float4* dy4 = reinterpret_cast<const float4*>(dY + (size_t)b0n * F * D);
+    for (int e = threadIdx.x; e < nrn * F * d4; e += blockDim.x) {
+      const int f = e / d4, c4 = e - f * d4;
+      cp_async16(dst + blk_floats + (size_t)f * RZ + 4 * c4, dy4 + e);
+      cp_async16(dst + blk_floats + z_floats + (size_t)f * RZ + 4 * c4, y4 + e);
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if ((int)blockIdx.x * R < B) issue(blockIdx.x * R, 0);
+  for (int b0 = blockIdx.x * R; b0 < B; b0 += gridDim.x * R) {
+    const int nr = min(R, B - b0);
+    const int b0n = b0 + gridDim.x * R;
+    cp_async_wait_all();
+    __syncthreads();                     // this group's blocks are complete; every thread is done with the other buffer
+    if (nbuf == 2 && b0n < B) issue(b0n, buf ^ 1);
+    float* bufp = sm_all + buf * buf_floats;
+    for (int e = threadIdx.x; e < nr * F * d4; e += blockDim.x) {     // relu mask of the attention output
+      const int f = e / d4, c4 = e - f * d4;
+      float4* gp = reinterpret_cast<float4*>(bufp + blk_floats + (size_t)f * RZ + 4 * c4);
+      const float4 y = *reinterpret_cast<const float4*>(bufp + blk_floats + z_floats + (size_t)f * RZ + 4 * c4);
+      float4 g = *gp;
+      g.x = y.x > 0.f ? g.x : 0.f;
+      g.y = y.y > 0.f ? g.y : 0.f;
+      g.z = y.z > 0.f ? g.z : 0.f;
+      g.w = y.w > 0.f ? g.w : 0.f;
+      *gp = g;
     }
     __syncthreads();
+    const float* blk = bufp + (size_t)rr * F * RS;
+    const float* dz = bufp + blk_floats + (size_t)rr * F * RZ;
     const int b = b0 + rr;
     const bool live = rr < nr;
     float* dst = d_qkvr + (size_t)b * F * 4 * D;
@@ -898,6 +972,12 @@ __global__ void __launch_bounds__(256) attention_core_bwd_t_kernel(const float* 
       store_row<DH>(o + D, dk);
       store_row<DH>(o + 2 * D, dvv);
     }
+    if (nbuf == 2) {
+      buf ^= 1;
+    } else if (b0n < B) {
+      __syncthreads();
+      issue(b0n, 0);
+    }
   }
 }
 
@@ -907,9 +987,16 @@ using namespace dtb;
 
 namespace {
 constexpr size_t kPnnTSmemMax = 200 * 1024;
+constexpr size_t kAttSmemMax = 220 * 1024;
 // the (row, field) kernels need a power-of-two width in 4..32 and 16-byte aligned rows
-// attention kernels: batch rows per CTA so that a CTA has about 128 (head, field) threads
-int att_rows_per_cta(int hf) { return hf >= 128 ? 1 : 128 / hf; }
+// attention kernels: batch rows per CTA so that a CTA has about 128 (head, field) threads, two shared-memory buffers
+// (the next group's loads run under this group's arithmetic) unless one row's blocks are too large for that
+void att_plan(int hf, size_t row_bytes, size_t stat_bytes, int& R, int& nbuf) {
+  const size_t budget = 96 * 1024, limit = 200 * 1024;
+  nbuf = 2 * row_bytes + stat_bytes <= limit ? 2 : 1;
+  R = hf >= 128 ? 1 : 128 / hf;
+  while (R > 1 && (size_t)R * (nbuf * row_bytes + stat_bytes) > budget) --R;
+}
 int att_threads(int R, int hf) {
   const int t = (R * hf + 31) / 32 * 32;
   return t < 64 ? 64 : t;
@@ -1043,21 +1130,25 @@ int dtb_attention_core_fwd(const float* qkvr, float* Y, int B, int F, int D, int
   const int dh = D / heads;
   const int nthr = threads < 64 ? 64 : threads;
   if (D % 4 == 0 && nthr <= 256 && ((reinterpret_cast<uintptr_t>(qkvr) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0) {
-    const int R = att_rows_per_cta(heads * F);
+    const size_t row_bytes = (size_t)F * (4 * D + 4) * sizeof(float);
+    int R, nbuf;
+    att_plan(heads * F, row_bytes, 0, R, nbuf);
     const int nthr_t = att_threads(R, heads * F);
-    const size_t smem_t = (size_t)R * F * (4 * D + 4) * sizeof(float);
+    const size_t smem_t = (size_t)nbuf * R * row_bytes;
     if (grid > ceil_div(B, R)) grid = ceil_div(B, R);
+    if (smem_t <= kAttSmemMax) {
 #define DTB_ATT_FWD(DHV)                                                                                                   \
   case DHV:                                                                                                                \
     DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_fwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                      (int)smem_t));                                                                         \
     attention_core_fwd_t_kernel<DHV><<<grid, nthr_t, smem_t, (cudaStream_t)stream>>>(qkvr, Y, B, F, D, heads,            \
-                                                                                     use_residual, R);                   \
+                                                                                     use_residual, R, nbuf);             \
     DTB_LAUNCH_OK();                                                                                                       \
     return DTB_OK;
     switch (dh) {
       DTB_ATT_FWD(1) DTB_ATT_FWD(2) DTB_ATT_FWD(4) DTB_ATT_FWD(8) DTB_ATT_FWD(16) DTB_ATT_FWD(32) DTB_ATT_FWD(64)
       default: break;
+    }
     }
 #undef DTB_ATT_FWD
   }
@@ -1082,23 +1173,27 @@ int dtb_attention_core_bwd(const float* qkvr, const float* Y, const float* dY, f
   if (D % 4 == 0 && nthr <= 256 &&
       ((reinterpret_cast<uintptr_t>(qkvr) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(dY) |
         reinterpret_cast<uintptr_t>(d_qkvr)) & 15) == 0) {
-    const int R = att_rows_per_cta(heads * F);
+    const size_t row_bytes = ((size_t)F * (4 * D + 4) + 2 * (size_t)F * (D + 4)) * sizeof(float);
+    const size_t stat_bytes = (size_t)heads * F * 4 * sizeof(float);
+    int R, nbuf;
+    att_plan(heads * F, row_bytes, stat_bytes, R, nbuf);
     const int nthr_t = att_threads(R, heads * F);
-    const size_t smem_t =
-        (size_t)R * ((size_t)F * (4 * D + 4) + (size_t)F * (D + 4) + (size_t)heads * F * 4) * sizeof(float);
+    const size_t smem_t = (size_t)R * (nbuf * row_bytes + stat_bytes);
     if (grid > ceil_div(B, R)) grid = ceil_div(B, R);
+    if (smem_t <= kAttSmemMax) {
 #define DTB_ATT_BWD(DHV)                                                                                                \
   case DHV:                                                                                                             \
     DTB_CUDA_OK(cudaFuncSetAttribute(attention_core_bwd_t_kernel<DHV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                      (int)smem_t));                                                                      \
     attention_core_bwd_t_kernel<DHV><<<grid, nthr_t, smem_t, (cudaStream_t)stream>>>(qkvr, Y, dY, d_qkvr, B, F, D,      \
                                                                                      heads, use_residual,                \
-                                                                                     mask_relu_inputs, R);               \
+                                                                                     mask_relu_inputs, R, nbuf);         \
     DTB_LAUNCH_OK();                                                                                                    \
     return DTB_OK;
     switch (dh) {
       DTB_ATT_BWD(1) DTB_ATT_BWD(2) DTB_ATT_BWD(4) DTB_ATT_BWD(8) DTB_ATT_BWD(16) DTB_ATT_BWD(32) DTB_ATT_BWD(64)
       default: break;
+    }
     }
 #undef DTB_ATT_BWD
   }
