@@ -74,6 +74,15 @@ _SIGNATURES = {
     'dtb_cross_bwd': (c_int, [P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, P]),
     'dtb_pnn_fwd': (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, c_int, P, P]),
     'dtb_pnn_bwd': (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_afm_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'dtb_afm_fwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    'dtb_afm_bwd': (c_int, [P, P, P, P, P, P, P, P, P, P, P, P, c_size_t, c_int, c_int, c_int, c_int, c_int, P]),
+    'dtb_bilinear_fwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_bilinear_bwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_senet_pool_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_senet_pool_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_senet_scale_fwd': (c_int, [P, P, P, c_int, c_int, c_int, P]),
+    'dtb_senet_scale_bwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
     'dtb_attention_core_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dtb_attention_core_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
 }

@@ -36,6 +36,7 @@ class _Scope:
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(int(seed) if seed is not None else int.from_bytes(os.urandom(4), 'little'))
         self.params = OrderedDict()
+        self.stacked = {}                  # key of a param_stack() tensor -> the reference names of its slices
         self.buffers = OrderedDict()
         self.training = False
         self.frozen = False
@@ -43,6 +44,7 @@ class _Scope:
         self.outputs = {}
         self.anchor = torch.zeros(1, dtype=torch.float32, device=self.device, requires_grad=True)
         self._counters = {}
+        self._indices = {}
         self._prefix = []
         self._seed_counter = 0
 
@@ -55,6 +57,13 @@ class _Scope:
         self._counters = {}
         self._prefix = []
         self.outputs = {}
+        self._indices = {}
+
+    def next_index(self, counter_name):
+        """utils/counter.py:next_num scoped to one forward pass of this model (index begins from 0)."""
+        n = self._indices.get(counter_name, -1) + 1
+        self._indices[counter_name] = n
+        return n
 
     def full_name(self, given, base):
         prefix = '/'.join(self._prefix)
@@ -86,6 +95,22 @@ class _Scope:
             self.params[name] = p
         elif tuple(p.shape) != tuple(int(s) for s in shape):
             raise ValueError(f'parameter {name!r} has shape {tuple(p.shape)}, layer asked for {tuple(shape)}')
+        return p
+
+    def param_stack(self, names, shape, init):
+        """One leaf tensor [len(names), *shape] for a family of same-shaped reference weights that a kernel wants contiguous
+        (BilinearInteraction's per-pair matrices, layers.py:343-356).  ``state_dict`` exposes the slices under the reference's
+        individual names; the optimiser sees one tensor."""
+        key = names[0] + '[*]'
+        p = self.params.get(key)
+        if p is None:
+            if self.frozen:
+                raise RuntimeError(f'parameter {key!r} requested after the model was built')
+            p = torch.stack([L.init_tensor(shape, init, self.device, self.generator) for _ in names]).requires_grad_(True)
+            self.params[key] = p
+            self.stacked[key] = list(names)
+        elif tuple(p.shape) != (len(names),) + tuple(int(s) for s in shape):
+            raise ValueError(f'parameter {key!r} has shape {tuple(p.shape)}, layer asked for {(len(names),) + tuple(shape)}')
         return p
 
     def buffer(self, name, shape, value):
@@ -901,7 +926,11 @@ class DeepModel:
             for i in range(self.n_fields):
                 sd[f'{consts.LAYER_PREFIX_EMBEDDING}categorical_vars_all/embeddings_{i}'] = self.table.field_weight(i)
         for k, v in self._scope.params.items():
-            sd[k] = v.detach()
+            if k in self._scope.stacked:                 # a stacked family: one entry per reference weight name (views)
+                for i, name in enumerate(self._scope.stacked[k]):
+                    sd[name] = v.detach()[i]
+            else:
+                sd[k] = v.detach()
         for k, v in self._scope.buffers.items():
             sd[k] = v
         return sd

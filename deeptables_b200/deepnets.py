@@ -9,8 +9,8 @@ Differences a maintainer should know:
   builders fuse the gather into their interaction kernels;
 * ``get_nets`` keeps the user's order (the reference loses it through ``set()``,
   deepnets.py:486), which only matters for ``stacking_op='concat'``;
-* afm / fgcnn / fibinet builders are outside the hot path of this build and raise
-  ``NotImplementedError``.
+* fgcnn builders are outside the hot path of this build and raise ``NotImplementedError``
+  (SURVEY.md 8f rank 3); afm_nets, fibi_nets and fibi_dnn_nets run on their own kernels (afm.cu, fibinet.cu).
 """
 from inspect import signature
 
@@ -168,15 +168,57 @@ def _out_of_scope(name):
     return fn
 
 
-afm_nets = _out_of_scope('afm_nets')
+def afm_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """Attentional Factorization Machine (reference deepnets.py:99-107)."""
+    if embeddings is None or len(embeddings) < 2:
+        return None
+    afm_output = layers.AFM(params=config.afm_params, name='afm_layer')(embeddings)
+    model_desc.add_net('afm', f'list({len(embeddings)})', _shape(afm_output))
+    return afm_output
+
+
 fg_nets = _out_of_scope('fg_nets')
 fgcnn_cin_nets = _out_of_scope('fgcnn_cin_nets')
 fgcnn_fm_nets = _out_of_scope('fgcnn_fm_nets')
 fgcnn_afm_nets = _out_of_scope('fgcnn_afm_nets')
 fgcnn_ipnn_nets = _out_of_scope('fgcnn_ipnn_nets')
 fgcnn_dnn_nets = _out_of_scope('fgcnn_dnn_nets')
-fibi_nets = _out_of_scope('fibi_nets')
-fibi_dnn_nets = _out_of_scope('fibi_dnn_nets')
+def fibi_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """SENET + BilinearInteraction on the original and on the SENET-like embeddings (reference deepnets.py:344-371).
+    The reference numbers its layers with a process-wide counter (utils/counter.py); here the index counts the fibi nets of
+    THIS model (0 for the first), so that checkpoints do not depend on how many models the process has built."""
+    scope = layers.current_scope()
+    senet_index = scope.next_index('senet_layer')
+    senet_emb_concat = _concat_embeddings(embeddings, f'concat_senet_embedding_{senet_index}')
+    if senet_emb_concat is None:
+        model_desc.add_net('fibi', (None), (None))
+        return None
+    p = config.fibinet_params
+    senet_pooling_op = p.get('senet_pooling_op', 'mean')
+    senet_reduction_ratio = p.get('senet_reduction_ratio', 3)
+    bilinear_type = p.get('bilinear_type', 'field_interaction')
+    senet_embedding = layers.SENET(pooling_op=senet_pooling_op, reduction_ratio=senet_reduction_ratio,
+                                   name=f'senet_layer_{senet_index}')(senet_emb_concat)
+    senet_bilinear_out = layers.BilinearInteraction(bilinear_type=bilinear_type,
+                                                    name=f'senet_bilinear_layer_{senet_index}')(senet_embedding)
+    bilinear_out = layers.BilinearInteraction(bilinear_type=bilinear_type,
+                                              name=f'embedding_bilinear_layer_{senet_index}')(senet_emb_concat)
+    concat_bilinear = Concatenate(axis=1, name=f'concat_bilinear_{senet_index}')([senet_bilinear_out, bilinear_out])
+    model_desc.add_net('fibi', _shape(senet_emb_concat), _shape(concat_bilinear))
+    return concat_bilinear
+
+
+def fibi_dnn_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FiBiNet with DNN as deep classifier (reference deepnets.py:374-386)."""
+    if embeddings is None or len(embeddings) <= 1:
+        return None
+    fibi_output = fibi_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if dense_layer is None:
+        raise ValueError('fibi_dnn_nets concatenates the continuous columns (deepnets.py:382): the model has none')
+    dnn_input = Concatenate(name='concat_bilinear_dense')([Flatten(name='flatten_fibi_output')(fibi_output), dense_layer])
+    dnn_out = dnn(dnn_input, config.dnn_params, cellname='fibi_dnn')
+    model_desc.add_net('fibi-dnn', _shape(fibi_output), _shape(dnn_out))
+    return dnn_out
 
 
 def dnn(x, params, cellname='dnn'):

@@ -518,6 +518,108 @@ class PNNFn(torch.autograd.Function):
         return _TableBackwardMixin.finish_tensor_table(t), dk, None, None, None, None
 
 
+class AFMFn(torch.autograd.Function):
+    """AFM.call up to the attention-pooled pair product (layers.py:790-804), gather fused: [B, D]."""
+
+    @staticmethod
+    def forward(ctx, anchor, att_kernel, att_bias, projection_h, block, act):
+        t, idx, w, offs = _tabs(block)
+        b, f, d = idx.shape[0], t.n_fields, t.dim
+        h = att_kernel.shape[1]
+        pooled = torch.empty(b, d, dtype=torch.float32, device=w.device)
+        check(N.lib.dtb_afm_fwd(ptr(idx), ptr(w), ptr(offs), ptr(att_kernel), ptr(att_bias), ptr(projection_h), ptr(pooled),
+                                b, f, d, h, act, ptr(t.status), stream_ptr()), 'afm_fwd')
+        ctx.block, ctx.cfg = block, (b, f, d, h, act)
+        ctx.save_for_backward(att_kernel, att_bias, projection_h)
+        _note_consumer(ctx, t)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        att_kernel, att_bias, projection_h = ctx.saved_tensors
+        t, idx, w, offs = _tabs(ctx.block)
+        b, f, d, h, act = ctx.cfg
+        g = _f32(g)
+        gt = _grad_target(t)
+        dk, db, dh = torch.zeros_like(att_kernel), torch.zeros_like(att_bias), torch.zeros_like(projection_h)
+        ws_bytes = N.lib.dtb_afm_workspace_bytes(b, f, h)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
+        check(N.lib.dtb_afm_bwd(ptr(idx), ptr(w), ptr(offs), ptr(att_kernel), ptr(att_bias), ptr(projection_h), ptr(g), ptr(gt),
+                                ptr(dk), ptr(db), ptr(dh), ptr(ws), ws_bytes, b, f, d, h, act, stream_ptr()), 'afm_bwd')
+        _table_grad_done(t)
+        return _TableBackwardMixin.finish_tensor_table(t), dk, db, dh, None, None
+
+
+BILINEAR_TYPES = {'field_all': 0, 'field_each': 1, 'field_interaction': 2}
+
+
+class BilinearFn(torch.autograd.Function):
+    """BilinearInteraction.call (layers.py:358-372) on a dense [B, F, D] block; weights stacked [n_w, D, D]."""
+
+    @staticmethod
+    def forward(ctx, x, w, bilinear_type):
+        x = _f32(x)
+        b, f, d = x.shape
+        out = torch.empty(b, f * (f - 1) // 2, d, dtype=torch.float32, device=x.device)
+        check(N.lib.dtb_bilinear_fwd(ptr(x), ptr(w), ptr(out), b, f, d, BILINEAR_TYPES[bilinear_type], stream_ptr()), 'bilinear_fwd')
+        ctx.save_for_backward(x, w)
+        ctx.bt = BILINEAR_TYPES[bilinear_type]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        b, f, d = x.shape
+        g = _f32(g)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w)
+        check(N.lib.dtb_bilinear_bwd(ptr(x), ptr(w), ptr(g), ptr(dx), ptr(dw), b, f, d, ctx.bt, stream_ptr()), 'bilinear_bwd')
+        return dx, dw, None
+
+
+class SenetPoolFn(torch.autograd.Function):
+    """SENET squeeze (layers.py:295-298): mean or max over the embedding axis, [B, F, D] -> [B, F]."""
+
+    @staticmethod
+    def forward(ctx, x, op):
+        x = _f32(x)
+        b, f, d = x.shape
+        z = torch.empty(b, f, dtype=torch.float32, device=x.device)
+        check(N.lib.dtb_senet_pool_fwd(ptr(x), ptr(z), b, f, d, op, stream_ptr()), 'senet_pool_fwd')
+        ctx.save_for_backward(x, z)
+        ctx.op = op
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, z = ctx.saved_tensors
+        b, f, d = x.shape
+        dx = torch.empty_like(x)
+        check(N.lib.dtb_senet_pool_bwd(ptr(x), ptr(z), ptr(_f32(dz)), ptr(dx), b, f, d, ctx.op, stream_ptr()), 'senet_pool_bwd')
+        return dx, None
+
+
+class SenetScaleFn(torch.autograd.Function):
+    """SENET re-weighting (layers.py:301): V = X * A[:, :, None]."""
+
+    @staticmethod
+    def forward(ctx, x, a):
+        x, a = _f32(x), _f32(a)
+        b, f, d = x.shape
+        v = torch.empty_like(x)
+        check(N.lib.dtb_senet_scale_fwd(ptr(x), ptr(a), ptr(v), b, f, d, stream_ptr()), 'senet_scale_fwd')
+        ctx.save_for_backward(x, a)
+        return v
+
+    @staticmethod
+    def backward(ctx, dv):
+        x, a = ctx.saved_tensors
+        b, f, d = x.shape
+        dx, da = torch.empty_like(x), torch.empty_like(a)
+        check(N.lib.dtb_senet_scale_bwd(ptr(x), ptr(a), ptr(_f32(dv)), ptr(dx), ptr(da), b, f, d, stream_ptr()), 'senet_scale_bwd')
+        return dx, da
+
+
 class AttentionCoreFn(torch.autograd.Function):
     """MultiheadAttention.call between the projections and the BatchNormalization
     (layers.py:129-150): per-head softmax(QK^T/sqrt(dh))V + residual, relu."""

@@ -72,6 +72,10 @@ def init_tensor(shape, kind, device, generator=None):
     if kind == 'ones':
         return t.fill_(1.0)
     fan_in, fan_out = _fans(shape)
+    if kind == 'glorot_normal':
+        # keras GlorotNormal: truncated normal (2 sigma) with stddev sqrt(2 / (fan_in + fan_out)) / 0.87962566
+        std = math.sqrt(2.0 / (fan_in + fan_out)) / 0.87962566103423978
+        return torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=generator)
     if kind == 'uniform':
         lim = 0.05
     elif kind == 'glorot_uniform':
@@ -402,15 +406,95 @@ def _out_of_scope(name):
     return _Stub
 
 
-AFM = _out_of_scope('AFM')
+class AFM(Layer):
+    """Attentional FM (reference layers.py:742-812).  Weight names: <name>/dense_attention/{kernel,bias},
+    <name>/projection_h, <name>/dense_out/kernel."""
+
+    def __init__(self, params, name=None):
+        super().__init__(name)
+        self.params = params
+        self.hidden_factor = params.get('hidden_factor', 16)
+        self.dropout_rate = params.get('dropout_rate', 0)
+        self.activation_function = params.get('activation', 'relu')
+        if self.activation_function not in ('relu', 'linear', None):
+            raise NotImplementedError(f'AFM attention activation {self.activation_function!r}: relu or linear')
+
+    def call(self, scope, x):
+        if not isinstance(x, (list, tuple, EmbeddingList)) or len(x) < 2:
+            raise ValueError('A `AttentionalFM` layer should be called on a list of at least 2 inputs')
+        block = _as_block(x)
+        _, f, d = block.shape
+        h = int(self.hidden_factor)
+        wa = scope.param(f'{self.name}/dense_attention/kernel', (d, h), 'glorot_normal')
+        ba = scope.param(f'{self.name}/dense_attention/bias', (h,), 'zeros')
+        wo = scope.param(f'{self.name}/dense_out/kernel', (d, 1), 'glorot_uniform')
+        ph = scope.param(f'{self.name}/projection_h', (h, 1), 'glorot_uniform')
+        act = E.ACT_CODES['relu'] if self.activation_function == 'relu' else E.ACT_CODES['linear']
+        pooled = E.AFMFn.apply(block.table.anchor, wa, ba, ph, block, act)
+        if self.dropout_rate and scope.training:
+            pooled = E.DropoutFn.apply(pooled, float(self.dropout_rate), scope.next_seed())
+        return E.DenseFn.apply(pooled, wo, None, E.ACT_CODES['linear'])
+
+
 FGCNN = _out_of_scope('FGCNN')
-SENET = _out_of_scope('SENET')
-BilinearInteraction = _out_of_scope('BilinearInteraction')
+
+
+class SENET(Layer):
+    """Squeeze-and-excitation re-weighting of the field embeddings (reference layers.py:245-311).
+    Weight names: <name>/dense_att1/{kernel,bias}, <name>/dense_att2/{kernel,bias}."""
+
+    def __init__(self, pooling_op='mean', reduction_ratio=3, name=None):
+        super().__init__(name)
+        self.pooling_op = pooling_op
+        self.reduction_ratio = reduction_ratio
+
+    def call(self, scope, x):
+        x = _materialize(x)
+        if x.dim() != 3:
+            raise ValueError(f'Wrong dimensions of inputs, expected 3 but input {x.dim()}.')
+        f = x.shape[1]
+        red = max(f // self.reduction_ratio, 1)
+        w1 = scope.param(f'{self.name}/dense_att1/kernel', (f, red), 'he_uniform')
+        b1 = scope.param(f'{self.name}/dense_att1/bias', (red,), 'zeros')
+        w2 = scope.param(f'{self.name}/dense_att2/kernel', (red, f), 'he_uniform')
+        b2 = scope.param(f'{self.name}/dense_att2/bias', (f,), 'zeros')
+        z = E.SenetPoolFn.apply(x, 1 if self.pooling_op == 'max' else 0)
+        a1 = E.DenseFn.apply(z, w1, b1, E.ACT_CODES['relu'])
+        a2 = E.DenseFn.apply(a1, w2, b2, E.ACT_CODES['relu'])
+        return E.SenetScaleFn.apply(x, a2)
+
+
+class BilinearInteraction(Layer):
+    """(x_i W) * x_j over the field pairs (reference layers.py:314-382); the per-pair / per-field matrices are one stacked
+    tensor here, exposed under the reference's names (bilinear_weight, bilinear_weight<i>, bilinear_weight<i>_<j>)."""
+
+    def __init__(self, bilinear_type='field_interaction', name=None):
+        super().__init__(name)
+        if bilinear_type not in E.BILINEAR_TYPES:
+            bilinear_type = 'field_interaction'          # the reference's else branch (layers.py:350)
+        self.bilinear_type = bilinear_type
+
+    def call(self, scope, x):
+        x = _materialize(x)
+        if x.dim() != 3:
+            raise ValueError(f'Wrong dimensions of inputs, expected 3 but input {x.dim()}.')
+        _, f, d = x.shape
+        if self.bilinear_type == 'field_all':
+            names = [f'{self.name}/bilinear_weight']
+        elif self.bilinear_type == 'field_each':
+            names = [f'{self.name}/bilinear_weight{i}' for i in range(f - 1)]
+        else:
+            names = [f'{self.name}/bilinear_weight{i}_{j}' for i in range(f) for j in range(i + 1, f)]
+        w = scope.param_stack(names, (d, d), 'glorot_uniform')
+        return E.BilinearFn.apply(x, w, self.bilinear_type)
+
+
 VarLenColumnEmbedding = _out_of_scope('VarLenColumnEmbedding')
 
 dt_custom_objects = {
     'FM': FM, 'CIN': CIN, 'Cross': Cross, 'MultiheadAttention': MultiheadAttention,
-    'InnerProduct': InnerProduct, 'OuterProduct': OuterProduct,
+    'InnerProduct': InnerProduct, 'OuterProduct': OuterProduct, 'AFM': AFM, 'SENET': SENET,
+    'BilinearInteraction': BilinearInteraction,
 }
 
 

@@ -250,6 +250,42 @@ int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
                 const float* op_kernel, const float* d_ip, const float* d_op, float* grad_table,
                 float* d_op_kernel, int B, int F, int D, int kernel_type, void* stream);
 
+/* ---- AFM (layers.py:742-812; afm_nets deepnets.py:99-107), gather fused ---------------------- */
+/* pooled[B,D] = sum_p softmax_p(act((e_i*e_j) att_kernel + att_bias) . projection_h) (e_i*e_j) over
+ * the F(F-1)/2 field pairs in itertools.combinations order (what AFM.call hands to its Dropout and
+ * Dense(1, use_bias=False)).  att_kernel [D,H] row-major, att_bias [H], projection_h [H];
+ * act = DTB_ACT_NONE | DTB_ACT_RELU.  D in {4,8,16,32}, H <= 32, else DTB_ERR_UNSUPPORTED.
+ * Backward: adds into grad_table (same layout as the table) and into d_att_kernel / d_att_bias /
+ * d_projection_h (caller zero-fills); workspace of dtb_afm_workspace_bytes(B,F,H) bytes. */
+size_t dtb_afm_workspace_bytes(int B, int F, int H);
+int dtb_afm_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* att_kernel, const float* att_bias, const float* projection_h,
+                float* pooled, int B, int F, int D, int H, int act, int* status, void* stream);
+int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
+                const float* att_kernel, const float* att_bias, const float* projection_h,
+                const float* d_pooled, float* grad_table, float* d_att_kernel, float* d_att_bias,
+                float* d_projection_h, void* workspace, size_t workspace_bytes, int B, int F, int D,
+                int H, int act, void* stream);
+
+/* ---- FiBiNet: SENET + BilinearInteraction (layers.py:245-382; fibi_nets deepnets.py:344-371) -- */
+/* On a dense block X [B,F,D] (the concatenated embeddings or their SENET re-weighting).
+ * Bilinear: out[b,p,:] = (x_i W_s) * x_j over the F(F-1)/2 pairs in itertools.combinations order;
+ * W [n_w,D,D] row-major, bilinear_type 0 field_all (n_w = 1, s = 0) | 1 field_each (n_w = F-1, s = i)
+ * | 2 field_interaction (n_w = pairs, s = p).  Backward: dX [B,F,D] overwritten (may be NULL), dW
+ * accumulated (caller zero-fills).  D in {4,8,16,32}, else DTB_ERR_UNSUPPORTED.
+ * SENET: Z[b,f] = mean (pooling_op 0) or max (1) over d; V = X * A[:,:,None]; the two Dense layers
+ * between Z and A are dtb_dense_* calls.  Max-pool gradient: ties share it (tf.reduce_max). */
+int dtb_bilinear_fwd(const float* X, const float* W, float* out, int B, int F, int D,
+                     int bilinear_type, void* stream);
+int dtb_bilinear_bwd(const float* X, const float* W, const float* d_out, float* dX, float* dW, int B,
+                     int F, int D, int bilinear_type, void* stream);
+int dtb_senet_pool_fwd(const float* X, float* Z, int B, int F, int D, int pooling_op, void* stream);
+int dtb_senet_pool_bwd(const float* X, const float* Z, const float* dZ, float* dX, int B, int F,
+                       int D, int pooling_op, void* stream);
+int dtb_senet_scale_fwd(const float* X, const float* A, float* V, int B, int F, int D, void* stream);
+int dtb_senet_scale_bwd(const float* X, const float* A, const float* dV, float* dX, float* dA, int B,
+                        int F, int D, void* stream);
+
 /* ---- MultiheadAttention core (layers.py:129-150), between the projections and the BN ------- */
 /* qkvr [B, F, 4*D]: the four relu(Dense) projections of each field row, concatenated [Q|K|V|R]
  * (one dtb_dense_fwd with the four kernels side by side).  Y[B,F,D] = relu(concat_h softmax(Q_h

@@ -300,6 +300,63 @@ def outer_product(embeddings, kernel, kernel_type='mat'):
     return kp
 
 
+def afm(embeddings, att_kernel, att_bias, projection_h, out_kernel, act='relu'):
+    """AFM.call (layers.py:790-807): list of F tensors (B,1,D) -> (B,1).
+    bi = e_i * e_j over itertools.combinations (same order as pair_lists); attention MLP Dense(hidden_factor, act)
+    (kernel (D,H), bias (H)); score = softmax over the PAIRS of (attention . projection_h (H,1)); the score-weighted sum of
+    the pair products (B,D) goes through Dense(1, use_bias=False) (kernel (D,1)).  Dropout is identity (rate 0 / inference)."""
+    if embeddings[0].dim() != 3:
+        raise ValueError(f'Wrong dimensions of inputs, expected 3 but input {embeddings[0].dim()}.')
+    row, col = pair_lists(len(embeddings))
+    p = torch.cat([embeddings[i] for i in row], dim=1)          # (B,P,D)
+    q = torch.cat([embeddings[i] for i in col], dim=1)
+    bi = p * q
+    att = activation(bi @ att_kernel + att_bias, act)           # (B,P,H)
+    score = torch.softmax(torch.tensordot(att, projection_h, dims=([-1], [0])), dim=1)      # (B,P,1)
+    pooled = (score * bi).sum(dim=1)                            # (B,D)
+    return pooled @ out_kernel                                  # (B,1)
+
+
+def afm_pooled(embeddings, att_kernel, att_bias, projection_h, act='relu'):
+    """The (B,D) attention-pooled pair product of afm() (what the fused kernel emits, before Dropout and Dense(1))."""
+    row, col = pair_lists(len(embeddings))
+    bi = torch.cat([embeddings[i] for i in row], dim=1) * torch.cat([embeddings[i] for i in col], dim=1)
+    att = activation(bi @ att_kernel + att_bias, act)
+    score = torch.softmax(torch.tensordot(att, projection_h, dims=([-1], [0])), dim=1)
+    return (score * bi).sum(dim=1)
+
+
+def senet(x, att1_kernel, att1_bias, att2_kernel, att2_bias, pooling_op='mean'):
+    """SENET.call (layers.py:291-303): x (B,F,D).  Z = mean (or max) over the embedding axis (B,F);
+    A = relu(Dense(F)(relu(Dense(max(F // reduction_ratio, 1))(Z)))); V = x * A[:, :, None]."""
+    if x.dim() != 3:
+        raise ValueError(f'Wrong dimensions of inputs, expected 3 but input {x.dim()}.')
+    z = x.amax(dim=-1) if pooling_op == 'max' else x.mean(dim=-1)       # amax: ties share the gradient, as tf.reduce_max does
+    a1 = torch.relu(z @ att1_kernel + att1_bias)
+    a2 = torch.relu(a1 @ att2_kernel + att2_bias)
+    return x * a2.unsqueeze(2)
+
+
+def bilinear_interaction(x, weights, bilinear_type='field_interaction'):
+    """BilinearInteraction.call (layers.py:358-372): x (B,F,D) -> (B,P,D), pair order of itertools.combinations.
+    field_all: one W (D,D), (v_i W) * v_j;  field_each: W_i per first field (F-1 of them);
+    field_interaction: one W per pair, in pair order."""
+    if x.dim() != 3:
+        raise ValueError(f'Wrong dimensions of inputs, expected 3 but input {x.dim()}.')
+    f = x.shape[1]
+    row, col = pair_lists(f)
+    outs = []
+    for n, (i, j) in enumerate(zip(row, col)):
+        if bilinear_type == 'field_all':
+            w = weights[0]
+        elif bilinear_type == 'field_each':
+            w = weights[i]
+        else:
+            w = weights[n]
+        outs.append((x[:, i:i + 1, :] @ w) * x[:, j:j + 1, :])
+    return torch.cat(outs, dim=1)
+
+
 def dnn(x, params, weights, bn_state, training, cellname='dnn'):
     """deepnets.dnn (deepnets.py:401-427): [Dense(use_bias=not bn) -> BN? -> act -> Dropout?]*.
     Dropout layers are identity in this oracle (parity runs use rate 0 / inference)."""

@@ -21,7 +21,30 @@ import torch
 from . import layers_ref as L
 
 SUPPORTED_NETS = ('linear', 'cin_nets', 'fm_nets', 'opnn_nets', 'ipnn_nets', 'pnn_nets', 'dnn_nets',
-                  'cross_nets', 'cross_dnn_nets', 'dcn_nets', 'autoint_nets')
+                  'cross_nets', 'cross_dnn_nets', 'dcn_nets', 'autoint_nets', 'afm_nets', 'fibi_nets', 'fibi_dnn_nets')
+
+
+def bilinear_weight_names(layer, f, bilinear_type):
+    """BilinearInteraction.build (layers.py:343-356): weight names per sharing type, in the order call() uses them."""
+    if bilinear_type == 'field_all':
+        return [f'{layer}/bilinear_weight']
+    if bilinear_type == 'field_each':
+        return [f'{layer}/bilinear_weight{i}' for i in range(f - 1)]
+    return [f'{layer}/bilinear_weight{i}_{j}' for i in range(f) for j in range(i + 1, f)]
+
+
+def _fibi_entries(f, d0, params, index):
+    """fibi_nets (deepnets.py:344-371): SENET + two BilinearInteraction layers; `index` = senet_index."""
+    ratio = params.get('senet_reduction_ratio', 3)
+    bt = params.get('bilinear_type', 'field_interaction')
+    red = max(f // ratio, 1)
+    ents = [(f'senet_layer_{index}/dense_att1/kernel', (f, red), 'he_uniform'),
+            (f'senet_layer_{index}/dense_att1/bias', (red,), 'zeros'),
+            (f'senet_layer_{index}/dense_att2/kernel', (red, f), 'he_uniform'),
+            (f'senet_layer_{index}/dense_att2/bias', (f,), 'zeros')]
+    for lname in (f'senet_bilinear_layer_{index}', f'embedding_bilinear_layer_{index}'):
+        ents += [(n, (d0, d0), 'glorot_uniform') for n in bilinear_weight_names(lname, f, bt)]
+    return ents
 
 
 def _get(cfg, name, default=None):
@@ -53,6 +76,15 @@ def init_weight(rng, shape, kind):
         lim = math.sqrt(6.0 / (fan_in + fan_out))
     elif kind == 'he_uniform':
         lim = math.sqrt(6.0 / fan_in)
+    elif kind == 'glorot_normal':
+        # keras GlorotNormal: truncated normal (2 sigma), stddev sqrt(2 / (fan_in + fan_out)) / 0.87962566
+        std = math.sqrt(2.0 / (fan_in + fan_out)) / 0.87962566103423978
+        out = rng.normal(0.0, std, size=shape)
+        bad = np.abs(out) > 2 * std
+        while bad.any():
+            out[bad] = rng.normal(0.0, std, size=int(bad.sum()))
+            bad = np.abs(out) > 2 * std
+        return torch.from_numpy(out.astype(np.float32))
     elif kind == 'zeros':
         return torch.zeros(shape, dtype=torch.float32)
     elif kind == 'ones':
@@ -94,6 +126,7 @@ def param_spec(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes
     ents += _bn_entries('bn_concat_emb_dense', w)
     widths = {}
     d0 = emb_dims[0] if f else 0
+    n_fibi = 0
     for net in nets:
         if net == 'linear':
             ents.append(('linear_logit/kernel', (f + n_cont, 1), 'glorot_uniform'))
@@ -162,6 +195,27 @@ def param_spec(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes
                 e, width = _dnn_entries(w, _get(config, 'dnn_params'), 'dcn')
                 ents += e
                 widths[net] = w + width
+        elif net == 'afm_nets':
+            if f < 2:
+                continue
+            h = _get(config, 'afm_params').get('hidden_factor', 16)      # the layer reads 'hidden_factor' (layers.py:773)
+            ents += [('afm_layer/dense_attention/kernel', (d0, h), 'glorot_normal'),
+                     ('afm_layer/dense_attention/bias', (h,), 'zeros'),
+                     ('afm_layer/dense_out/kernel', (d0, 1), 'glorot_uniform'),
+                     ('afm_layer/projection_h', (h, 1), 'glorot_uniform')]
+            widths[net] = 1
+        elif net in ('fibi_nets', 'fibi_dnn_nets'):
+            if f < 1 or (net == 'fibi_dnn_nets' and f < 2):
+                continue
+            ents += _fibi_entries(f, d0, _get(config, 'fibinet_params'), n_fibi)
+            n_fibi += 1
+            pairs = f * (f - 1) // 2
+            if net == 'fibi_nets':
+                widths[net] = 2 * pairs * d0
+            else:
+                e, width = _dnn_entries(2 * pairs * d0 + n_cont, _get(config, 'dnn_params'), 'fibi_dnn')
+                ents += e
+                widths[net] = width
         elif net == 'autoint_nets':
             if not f:
                 continue
@@ -244,6 +298,7 @@ def forward(state, config, cat_idx, cont, n_fields, training, task='binary', ret
         return y
 
     outs = {}
+    n_fibi = 0
     for net in nets:
         if net == 'linear':
             outs[net] = L.linear(embeddings, dense_layer, state['linear_logit/kernel'])
@@ -281,6 +336,30 @@ def forward(state, config, cat_idx, cont, n_fields, training, task='binary', ret
                 outs[net] = run_dnn(c, 'cross_dnn')
             else:
                 outs[net] = torch.cat([c, run_dnn(ced, 'dcn')], dim=-1)
+        elif net == 'afm_nets':
+            if len(embeddings) < 2:
+                continue
+            act = _get(config, 'afm_params').get('activation', 'relu')
+            outs[net] = L.afm(embeddings, state['afm_layer/dense_attention/kernel'], state['afm_layer/dense_attention/bias'],
+                              state['afm_layer/projection_h'], state['afm_layer/dense_out/kernel'], act)
+        elif net in ('fibi_nets', 'fibi_dnn_nets'):
+            if len(embeddings) < 1 or (net == 'fibi_dnn_nets' and len(embeddings) < 2):
+                continue
+            p = _get(config, 'fibinet_params')
+            bt = p.get('bilinear_type', 'field_interaction')
+            cat = L.concat_embeddings(embeddings)
+            sl = f'senet_layer_{n_fibi}'
+            sen = L.senet(cat, state[f'{sl}/dense_att1/kernel'], state[f'{sl}/dense_att1/bias'],
+                          state[f'{sl}/dense_att2/kernel'], state[f'{sl}/dense_att2/bias'], p.get('senet_pooling_op', 'mean'))
+            f_ = cat.shape[1]
+            w_s = [state[n] for n in bilinear_weight_names(f'senet_bilinear_layer_{n_fibi}', f_, bt)]
+            w_e = [state[n] for n in bilinear_weight_names(f'embedding_bilinear_layer_{n_fibi}', f_, bt)]
+            n_fibi += 1
+            fibi = torch.cat([L.bilinear_interaction(sen, w_s, bt), L.bilinear_interaction(cat, w_e, bt)], dim=1)
+            if net == 'fibi_nets':
+                outs[net] = fibi
+            else:
+                outs[net] = run_dnn(torch.cat([fibi.reshape(fibi.shape[0], -1), dense_layer], dim=-1), 'fibi_dnn')
         elif net == 'autoint_nets':
             cat = L.concat_embeddings(embeddings)
             if cat is None:

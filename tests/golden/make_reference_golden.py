@@ -237,6 +237,96 @@ def make_model_cases(deepmodel, config_mod, metainfo, rec):
                 **{f'w/{k}': v for k, v in state.items()})
 
 
+# ------------------------------------------------------------------------------------------------------------
+# C. the SURVEY 8f-3 layers (AFM, SENET + BilinearInteraction = FiBiNet) and their nets, in a file of their own so that the
+#    vectors above stay bit-identical to the ones committed in round 1
+# ------------------------------------------------------------------------------------------------------------
+F3_CHILD_ATTRS = ('dense_attention', 'dense_out', 'dense_att1', 'dense_att2')
+
+F3_MODEL_CASES = [
+    ('afm', dict(nets=['afm_nets'], afm_params={'hidden_factor': 5, 'dropout_rate': 0}), [7, 5, 9, 4], 4, 3, 'binary', 2),
+    ('afm_linear_dnn', dict(nets=['linear', 'afm_nets', 'dnn_nets']), [7, 5, 9], 4, 2, 'binary', 2),
+    ('fibi_dnn', dict(nets=['fibi_dnn_nets']), [7, 5, 9, 4], 4, 3, 'binary', 2),
+    ('fibi_all_max', dict(nets=['fibi_dnn_nets'], fibinet_params={'senet_pooling_op': 'max', 'senet_reduction_ratio': 2,
+                                                                  'bilinear_type': 'field_all'}), [7, 5, 9], 4, 2, 'regression', None),
+    ('fibi_each_plus_fm', dict(nets=['fm_nets', 'fibi_nets'], fibinet_params={'senet_pooling_op': 'mean', 'senet_reduction_ratio': 3,
+                                                                              'bilinear_type': 'field_each'}), [7, 5, 9, 4], 4, 1, 'binary', 2),
+]
+
+
+def collect_state_f3(created):
+    children, state = set(), {}
+    for lyr in created:
+        for attr in F3_CHILD_ATTRS:
+            child = getattr(lyr, attr, None)
+            if isinstance(child, tf_shim.Layer):
+                children.add(id(child))
+                for k, v in child.weights_by_name.items():
+                    state[f'{lyr.name}/{attr}/{k}'] = np64(v)
+    for lyr in created:
+        if id(lyr) not in children:
+            for k, v in lyr.weights_by_name.items():
+                state[f'{lyr.name}/{k}'] = np64(v)
+    return state
+
+
+def make_f3_cases(layers, deepmodel, config_mod, metainfo, counter, rec):
+    # AFM (layers.py:742-812): list of F tensors (B,1,D) -> (B,1)
+    for case, params, n_f in (('afm_relu', {'hidden_factor': 6}, 4), ('afm_linear', {'hidden_factor': 3, 'activation': 'linear'}, 3)):
+        embs = [rand(5, 1, 3, seed=70 + i) for i in range(n_f)]
+        lyr = layers.AFM(params=params, name='afm_layer')
+        out = lyr(embs)
+        rec.add(case, 'afm', {**params, 'n_fields': n_f}, out=np64(out), att_kernel=np64(lyr.dense_attention.weights_by_name['kernel']),
+                att_bias=np64(lyr.dense_attention.weights_by_name['bias']), projection_h=np64(lyr.weights_by_name['projection_h']),
+                out_kernel=np64(lyr.dense_out.weights_by_name['kernel']), **{f'e{i}': np64(e) for i, e in enumerate(embs)})
+    # SENET (layers.py:245-311)
+    for case, op, ratio in (('senet_mean', 'mean', 3), ('senet_max', 'max', 2)):
+        x = rand(6, 7, 4, seed=80)
+        lyr = layers.SENET(pooling_op=op, reduction_ratio=ratio)
+        out = lyr(x)
+        rec.add(case, 'senet', {'pooling_op': op, 'reduction_ratio': ratio}, x=np64(x), out=np64(out),
+                **{f'w/{sub}/{k}': np64(v) for sub in ('dense_att1', 'dense_att2')
+                   for k, v in getattr(lyr, sub).weights_by_name.items()})
+    # BilinearInteraction (layers.py:314-382): the three weight-sharing types
+    for bt in ('field_all', 'field_each', 'field_interaction'):
+        x = rand(6, 5, 3, seed=90)
+        lyr = layers.BilinearInteraction(bilinear_type=bt)
+        out = lyr(x)
+        ws = [lyr.W] if bt == 'field_all' else list(lyr.W_list)
+        rec.add(f'bilinear_{bt}', 'bilinear', {'bilinear_type': bt}, x=np64(x), out=np64(out),
+                **{f'w{i}': np64(w) for i, w in enumerate(ws)})
+    # whole models with afm_nets / fibi_nets / fibi_dnn_nets through DeepModel.__build_model
+    for ci, (case, cfg_kwargs, vocab, dim, n_cont, task, num_classes) in enumerate(F3_MODEL_CASES):
+        conf = config_mod.ModelConfig(embedding_dropout=0, dense_dropout=0, embeddings_output_dim=dim, **cfg_kwargs)
+        cats = [metainfo.CategoricalColumn(f'c{i}', v, dim) for i, v in enumerate(vocab)]
+        conts = [metainfo.ContinuousColumn('input_continuous_all', [f'n{i}' for i in range(n_cont)])] if n_cont else []
+        b = 9
+        g = np.random.default_rng(300 + ci)
+        ids = np.stack([g.integers(0, v, size=b) for v in vocab], axis=1)
+        cont = g.normal(size=(b, n_cont))
+        outs = {}
+        for training in (False, True):
+            tf_shim.reset_layers()
+            tf_shim.seed(3000 + ci)
+            tf_shim.set_training(training)
+            counter._data_.clear()                       # senet_layer_<n>: n counts fibi_nets calls of the PROCESS (counter.py)
+            tf_shim.feed('input_categorical_vars_all', torch.tensor(ids.astype(np.float32)))
+            if n_cont:
+                tf_shim.feed('input_continuous_all', torch.tensor(cont, dtype=torch.float64))
+            dm = deepmodel.DeepModel(task, num_classes, conf, cats, conts)
+            model = dm._DeepModel__build_model(task=task, num_classes=num_classes, nets=conf.nets, categorical_columns=cats,
+                                               continuous_columns=conts, var_len_categorical_columns=None, config=conf)
+            outs[training] = np64(model.output)
+            state = collect_state_f3(tf_shim.created_layers())
+            tf_shim.set_training(False)
+        params = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg_kwargs.items()}
+        params['nets'] = list(conf.nets)
+        rec.add(case, 'model', {'config': json.loads(json.dumps(params)), 'vocab': vocab, 'dim': dim, 'n_cont': n_cont,
+                                'task': task, 'num_classes': num_classes},
+                ids=ids.astype(np.int64), cont=cont.astype(np.float64), out_infer=outs[False], out_train=outs[True],
+                **{f'w/{k}': v for k, v in state.items()})
+
+
 def dump_modelconfig(config_mod, deepnets, path):
     conf = config_mod.ModelConfig()
     d = conf._asdict()
@@ -266,6 +356,12 @@ def main():
     make_model_cases(deepmodel, config_mod, metainfo, rec)
     rec.save(os.path.join(HERE, 'reference_models.npz'))
     print(f'reference_models.npz: {len(rec.manifest)} cases')
+
+    rec = Recorder()
+    counter = importlib.import_module('deeptables.utils.counter')
+    make_f3_cases(layers, deepmodel, config_mod, metainfo, counter, rec)
+    rec.save(os.path.join(HERE, 'reference_f3.npz'))
+    print(f'reference_f3.npz: {len(rec.manifest)} cases')
 
     dump_modelconfig(config_mod, deepnets, os.path.join(HERE, 'reference_modelconfig.json'))
     print('reference_modelconfig.json written')

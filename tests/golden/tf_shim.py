@@ -105,6 +105,10 @@ def _make_tf():
     tf.float32, tf.float64, tf.int32, tf.int64 = 'float32', 'float64', 'int32', 'int64'
     tf.square = lambda x, name=None: _as_tensor(x) ** 2
     tf.reduce_sum = tf_reduce_sum
+    tf.reduce_mean = lambda x, axis=None, keepdims=False, name=None: \
+        _as_tensor(x).mean() if axis is None else _as_tensor(x).mean(dim=_axes(axis), keepdim=keepdims)
+    tf.reduce_max = lambda x, axis=None, keepdims=False, name=None: \
+        _as_tensor(x).max() if axis is None else _as_tensor(x).amax(dim=_axes(axis), keepdim=keepdims)
     tf.concat = lambda values, axis, name=None: torch.cat([_as_tensor(v) for v in values], dim=axis)
     tf.split = tf_split
     tf.transpose = lambda a, perm=None, name=None: _as_tensor(a).permute(*perm) if perm is not None else _as_tensor(a).t()
@@ -352,6 +356,7 @@ def install(reference_root='/root/reference'):
     keras = _module('keras')
     _module('keras.api')
     keras.layers = _module('keras.api.layers', **layer_names)
+    tf.keras.layers = keras.layers                # layers.AFM builds tf.keras.layers.Dropout (layers.py:788)
     _module('keras.api.metrics', RootMeanSquaredError=_Anything)
     _module('keras.api.models', Model=Model, load_model=_Anything(), save_model=_Anything())
     _module('keras.src')

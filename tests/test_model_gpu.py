@@ -41,13 +41,29 @@ def batch(vocab, n_cont, b, seed=0):
 
 NET_SETS = [['linear'], ['fm_nets'], ['dnn_nets'], ['cin_nets'], ['cross_nets'], ['dcn_nets'], ['cross_dnn_nets'],
             ['linear', 'fm_nets', 'dnn_nets'], ['linear', 'cin_nets', 'dnn_nets'], ['autoint_nets'], ['pnn_nets'],
-            ['ipnn_nets'], ['opnn_nets'], ['fm_nets', 'cin_nets', 'cross_nets', 'autoint_nets', 'pnn_nets']]
+            ['ipnn_nets'], ['opnn_nets'], ['fm_nets', 'cin_nets', 'cross_nets', 'autoint_nets', 'pnn_nets'],
+            ['afm_nets'], ['linear', 'afm_nets', 'dnn_nets'], ['fibi_dnn_nets'], ['fm_nets', 'fibi_nets']]
 
 
 @pytest.mark.parametrize('nets', NET_SETS)
 def test_forward_and_training_match_oracle(nets):
+    _forward_and_training_match_oracle(nets)
+
+
+@pytest.mark.parametrize('fibinet_params', [
+    {'senet_pooling_op': 'max', 'senet_reduction_ratio': 2, 'bilinear_type': 'field_all'},
+    {'senet_pooling_op': 'mean', 'senet_reduction_ratio': 3, 'bilinear_type': 'field_each'}])
+def test_fibinet_pooling_and_weight_sharing_variants(fibinet_params):
+    _forward_and_training_match_oracle(['fibi_dnn_nets'], fibinet_params=fibinet_params)
+
+
+def test_afm_hidden_factor_and_linear_attention():
+    _forward_and_training_match_oracle(['afm_nets', 'dnn_nets'], afm_params={'hidden_factor': 5, 'activation': 'linear', 'dropout_rate': 0})
+
+
+def _forward_and_training_match_oracle(nets, **cfg_kw):
     vocab, dim, n_cont, b = [11, 7, 13, 5, 9], 4, 3, 48
-    model, conf = build(nets, vocab, dim, n_cont)
+    model, conf = build(nets, vocab, dim, n_cont, **cfg_kw)
     idx, cont, y = batch(vocab, n_cont, b)
     state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     ref = M.RefTrainer(state, conf, len(vocab))

@@ -724,6 +724,100 @@ def test_pnn_fwd_bwd(nat, f, d, b, ktype):
     np.testing.assert_allclose(dk.cpu().numpy(), grads[-1].numpy(), rtol=1e-3, atol=1e-4 * np.abs(grads[-1].numpy()).max())
 
 
+@pytest.mark.parametrize('f,d,h,b,act', [(26, 16, 16, 70, 'relu'), (5, 4, 5, 33, 'linear'), (3, 8, 32, 200, 'relu'),
+                                         (7, 32, 8, 20, 'relu'), (2, 16, 4, 9, 'relu'), (12, 8, 16, 300, 'relu')])
+def test_afm_fwd_bwd(nat, f, d, h, b, act):
+    """AFM attention pooling (layers.py:790-804) and its gradients against the fp64 oracle's autograd."""
+    vocab = [11 + i for i in range(f)]
+    tabs, flat, offs = make_table(vocab, d, seed=61)
+    idx = make_idx(vocab, b, seed=62)
+    idx[1] = idx[0]
+    g = np.random.default_rng(63)
+    wa = (g.normal(size=(d, h)) / np.sqrt(d)).astype(np.float32) * 3
+    ba = (g.normal(size=(h,)) * 0.1).astype(np.float32)
+    ph = g.normal(size=(h, 1)).astype(np.float32)
+    act_code = {'linear': 0, 'relu': 1}[act]
+    d_idx, d_tab, d_offs, d_wa, d_ba, d_ph = dev(idx), dev(flat), dev(offs), dev(wa), dev(ba), dev(ph)
+    pooled = torch.empty(b, d, device='cuda')
+    nat.check(nat.lib.dtb_afm_fwd(P(d_idx), P(d_tab), P(d_offs), P(d_wa), P(d_ba), P(d_ph), P(pooled), b, f, d, h, act_code, None,
+                                  None))
+    t64 = [torch.tensor(t, dtype=torch.float64, requires_grad=True) for t in tabs]
+    w64 = [torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (wa, ba, ph)]
+    emb = L.embedding_lookup(t64, torch.tensor(idx))
+    want = L.afm_pooled(emb, w64[0], w64[1], w64[2], act)
+    np.testing.assert_allclose(pooled.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    gp = g.normal(size=(b, d)).astype(np.float32)
+    gt = torch.zeros(flat.shape, device='cuda')
+    dwa, dba, dph = torch.zeros(d, h, device='cuda'), torch.zeros(h, device='cuda'), torch.zeros(h, 1, device='cuda')
+    nb = nat.lib.dtb_afm_workspace_bytes(b, f, h)
+    ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
+    nat.check(nat.lib.dtb_afm_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_wa), P(d_ba), P(d_ph), P(dev(gp)), P(gt), P(dwa), P(dba), P(dph),
+                                  P(ws), nb, b, f, d, h, act_code, None))
+    grads = torch.autograd.grad((want * torch.tensor(gp, dtype=torch.float64)).sum(), t64 + w64)
+    want_t = torch.cat(grads[:f], dim=0).numpy()
+    scale = 1e-2 * float(np.abs(grads[f].numpy()).max())
+    for name, got, ref in (('table', gt, want_t), ('att_kernel', dwa, grads[f].numpy()), ('att_bias', dba, grads[f + 1].numpy()),
+                           ('projection_h', dph, grads[f + 2].numpy())):
+        # (with a linear attention the bias gradient is exactly zero -- the softmax ignores a common shift -- so the floor
+        # of the tolerance is the scale of the kernel gradient, not of the reference value)
+        np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=2e-3, atol=2e-4 * max(np.abs(ref).max(), scale), err_msg=name)
+
+
+@pytest.mark.parametrize('f,d,b', [(26, 16, 150), (5, 4, 33), (2, 8, 9), (7, 32, 130), (12, 8, 300)])
+@pytest.mark.parametrize('bt', ['field_all', 'field_each', 'field_interaction'])
+def test_bilinear_fwd_bwd(nat, f, d, b, bt):
+    """BilinearInteraction (layers.py:358-372) on a dense block and its gradients against the fp64 oracle's autograd."""
+    g = np.random.default_rng(71)
+    pairs = f * (f - 1) // 2
+    n_w = {'field_all': 1, 'field_each': f - 1, 'field_interaction': pairs}[bt]
+    code = {'field_all': 0, 'field_each': 1, 'field_interaction': 2}[bt]
+    x = g.normal(size=(b, f, d)).astype(np.float32)
+    w = (g.normal(size=(n_w, d, d)) / np.sqrt(d)).astype(np.float32)
+    d_x, d_w = dev(x), dev(w)
+    out = torch.empty(b, pairs, d, device='cuda')
+    nat.check(nat.lib.dtb_bilinear_fwd(P(d_x), P(d_w), P(out), b, f, d, code, None))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    w64 = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    want = L.bilinear_interaction(x64, list(w64), bt)
+    np.testing.assert_allclose(out.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5 * float(want.abs().max()))
+    go = g.normal(size=(b, pairs, d)).astype(np.float32)
+    dx, dw = torch.empty(b, f, d, device='cuda'), torch.zeros(n_w, d, d, device='cuda')
+    nat.check(nat.lib.dtb_bilinear_bwd(P(d_x), P(d_w), P(dev(go)), P(dx), P(dw), b, f, d, code, None))
+    gx, gw = torch.autograd.grad((want * torch.tensor(go, dtype=torch.float64)).sum(), [x64, w64])
+    np.testing.assert_allclose(dx.cpu().numpy(), gx.numpy(), rtol=1e-3, atol=1e-4 * float(gx.abs().max()))
+    np.testing.assert_allclose(dw.cpu().numpy(), gw.numpy(), rtol=1e-3, atol=1e-4 * float(gw.abs().max()))
+
+
+@pytest.mark.parametrize('op', ['mean', 'max'])
+def test_senet_pool_and_scale(nat, op):
+    """SENET squeeze / re-weighting kernels (layers.py:291-303) against torch autograd on the same arithmetic."""
+    g = np.random.default_rng(72)
+    b, f, d = 37, 7, 8
+    x = g.normal(size=(b, f, d)).astype(np.float32)
+    x[3, 2, 1] = x[3, 2, 5] = 9.0                                  # a tie of the maximum: the gradient is shared
+    a = np.abs(g.normal(size=(b, f))).astype(np.float32)
+    d_x, d_a = dev(x), dev(a)
+    z, v = torch.empty(b, f, device='cuda'), torch.empty(b, f, d, device='cuda')
+    code = 1 if op == 'max' else 0
+    nat.check(nat.lib.dtb_senet_pool_fwd(P(d_x), P(z), b, f, d, code, None))
+    nat.check(nat.lib.dtb_senet_scale_fwd(P(d_x), P(d_a), P(v), b, f, d, None))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    a64 = torch.tensor(a, dtype=torch.float64, requires_grad=True)
+    want_z = x64.amax(dim=-1) if op == 'max' else x64.mean(dim=-1)
+    want_v = x64 * a64.unsqueeze(2)
+    np.testing.assert_allclose(z.cpu().numpy(), want_z.detach().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(v.cpu().numpy(), want_v.detach().numpy(), rtol=1e-6, atol=1e-7)
+    gz, gv = g.normal(size=(b, f)).astype(np.float32), g.normal(size=(b, f, d)).astype(np.float32)
+    dxz, dxv, da = torch.empty(b, f, d, device='cuda'), torch.empty(b, f, d, device='cuda'), torch.empty(b, f, device='cuda')
+    nat.check(nat.lib.dtb_senet_pool_bwd(P(d_x), P(z), P(dev(gz)), P(dxz), b, f, d, code, None))
+    nat.check(nat.lib.dtb_senet_scale_bwd(P(d_x), P(d_a), P(dev(gv)), P(dxv), P(da), b, f, d, None))
+    (wz,) = torch.autograd.grad((want_z * torch.tensor(gz, dtype=torch.float64)).sum(), [x64])
+    wv, wa = torch.autograd.grad((want_v * torch.tensor(gv, dtype=torch.float64)).sum(), [x64, a64])
+    np.testing.assert_allclose(dxz.cpu().numpy(), wz.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dxv.cpu().numpy(), wv.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(da.cpu().numpy(), wa.numpy(), rtol=1e-4, atol=1e-5)
+
+
 @pytest.mark.parametrize('b,f,d,heads,res', [(40, 26, 32, 4, True), (17, 5, 4, 1, True), (9, 7, 16, 2, False), (3, 1, 8, 8, True),
                                                (1001, 26, 16, 1, True), (131, 26, 32, 4, False), (70, 3, 64, 1, True)])
 def test_attention_core_fwd_bwd(nat, b, f, d, heads, res):

@@ -87,6 +87,36 @@ def test_oracle_layer_reproduces_reference_layer(meta):
     np.testing.assert_allclose(got.numpy(), want, **TOL)
 
 
+F3_Z, F3_CASES = _load('reference_f3.npz')
+F3_LAYER_CASES = [m for m in F3_CASES if m['kind'] != 'model']
+F3_MODEL_CASES = [m for m in F3_CASES if m['kind'] == 'model']
+
+
+@pytest.mark.parametrize('meta', F3_LAYER_CASES, ids=[m['case'] for m in F3_LAYER_CASES])
+def test_oracle_f3_layer_reproduces_reference_layer(meta):
+    """AFM, SENET, BilinearInteraction against the reference's own classes (layers.py:742-812, 245-382)."""
+    z, case, p, kind = F3_Z, meta['case'], meta['params'], meta['kind']
+    want = z[f'{case}/out']
+    if kind == 'afm':
+        embs = [_t(z[f'{case}/e{i}']) for i in range(p['n_fields'])]
+        got = L.afm(embs, _t(z[f'{case}/att_kernel']), _t(z[f'{case}/att_bias']), _t(z[f'{case}/projection_h']),
+                    _t(z[f'{case}/out_kernel']), p.get('activation', 'relu'))
+        pooled = L.afm_pooled(embs, _t(z[f'{case}/att_kernel']), _t(z[f'{case}/att_bias']), _t(z[f'{case}/projection_h']),
+                              p.get('activation', 'relu'))
+        np.testing.assert_allclose((pooled @ _t(z[f'{case}/out_kernel'])).numpy(), want, **TOL)
+    elif kind == 'senet':
+        w = _weights(z, case)
+        got = L.senet(_t(z[f'{case}/x']), w['dense_att1/kernel'], w['dense_att1/bias'], w['dense_att2/kernel'],
+                      w['dense_att2/bias'], p['pooling_op'])
+    elif kind == 'bilinear':
+        n = len([k for k in z.files if k.startswith(f'{case}/w')])
+        got = L.bilinear_interaction(_t(z[f'{case}/x']), [_t(z[f'{case}/w{i}']) for i in range(n)], p['bilinear_type'])
+    else:
+        raise AssertionError(kind)
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(got.numpy(), want, **TOL)
+
+
 def _model_config(p):
     from deeptables_b200 import deeptable
     kw = dict(p['config'])
@@ -100,12 +130,16 @@ def _model_config(p):
     return deeptable.ModelConfig(embedding_dropout=0, dense_dropout=0, embeddings_output_dim=p['dim'], **kw)
 
 
-@pytest.mark.parametrize('meta', MODEL_CASES, ids=[m['case'] for m in MODEL_CASES])
-def test_oracle_model_reproduces_reference_build_model(meta):
+ALL_MODEL_CASES = [(MODELS_Z, m) for m in MODEL_CASES] + [(F3_Z, m) for m in F3_MODEL_CASES]
+
+
+@pytest.mark.parametrize('zm', ALL_MODEL_CASES, ids=[m['case'] for _, m in ALL_MODEL_CASES])
+def test_oracle_model_reproduces_reference_build_model(zm):
     """Same weights (by the reference's layer/weight names), same batch -> same task_output as the graph that
     DeepModel.__build_model (deepmodel.py:259-317) assembled, in inference and in training mode (batch-statistics
     BatchNormalization)."""
-    z, case, p = MODELS_Z, meta['case'], meta['params']
+    z, meta = zm
+    case, p = meta['case'], meta['params']
     conf = _model_config(p)
     state = _weights(z, case)
     spec, _ = M.param_spec(conf, p['vocab'], [p['dim']] * len(p['vocab']), p['n_cont'], p['task'], p['num_classes'] or 2)
@@ -144,14 +178,15 @@ def test_modelconfig_mirror_matches_reference_defaults():
 # GPU: the CUDA engine against the same reference-code vectors (through DeepModel -> C ABI)
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize('meta', MODEL_CASES, ids=[m['case'] for m in MODEL_CASES])
-def test_cuda_model_reproduces_reference_build_model(meta):
+@pytest.mark.parametrize('zm', ALL_MODEL_CASES, ids=[m['case'] for _, m in ALL_MODEL_CASES])
+def test_cuda_model_reproduces_reference_build_model(zm):
     """Load the reference model's weights by name into the CUDA DeepModel and compare task_output with the
     reference's own graph: inference (moving statistics) and, for binary/regression tasks, the training-mode
     forward (batch statistics) that train_step returns.  fp32 kernels, bf16x3 CIN: north_star tolerance 1e-3."""
     from deeptables_b200.deepmodel import DeepModel
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
-    z, case, p = MODELS_Z, meta['case'], meta['params']
+    z, meta = zm
+    case, p = meta['case'], meta['params']
     conf = _model_config(p)
     cats = [CategoricalColumn(f'c{i}', v, p['dim']) for i, v in enumerate(p['vocab'])]
     conts = [ContinuousColumn('input_continuous_all', [f'n{i}' for i in range(p['n_cont'])])] if p['n_cont'] else []
