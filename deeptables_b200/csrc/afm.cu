@@ -14,6 +14,7 @@
 // Widths are template parameters: DT = D in {4, 8, 16, 32}; HT = H rounded up to {8, 16, 32} with zero-padded columns
 // (a padded unit has a = act(0) = 0 for relu / linear and h = 0, so it contributes nothing).
 #include "dtb_common.cuh"
+#include <cstdlib>
 
 namespace dtb {
 
@@ -99,16 +100,20 @@ __host__ __device__ inline size_t afm_row_smem_floats(int F, int P, int DT, int 
   return (size_t)DT * HT + 2 * HT + afm_p4(P) + (size_t)kAfmWarps * ((size_t)F * (DT + 4) + 2 * (size_t)afm_p4(P));
 }
 
-// BWD = false: pooled[row, :] = sum_p softmax_p v_p.
-// BWD = true : given g = dLoss/d pooled[row, :], writes w_p and ds_p = w_p (g.v_p - sum_q w_q g.v_q) to w_out / ds_out [B, P].
-template <int DT, int HT, bool BWD>
+// MODE 0: pooled[row, :] = sum_p softmax_p v_p.
+// MODE 1: given g = dLoss/d pooled[row, :], writes w_p and ds_p = w_p (g.v_p - sum_q w_q g.v_q) to w_out / ds_out [B, P]
+//         (first backward: afm_bwd_de_kernel then recomputes the attention vector of every pair from both of its fields).
+// MODE 2: the whole per-pair backward, each pair once: da_p[h] = ds_p h[h] act'(a_p[h]) -> w_out [B, P, HT],
+//         dv_p[d] = g[d] w_p + sum_h da_p[h] Wa[d][h] -> ds_out [B, P, DT], d h += ds_p a_p (afm_bwd_gather_kernel finishes).
+template <int DT, int HT, int MODE>
 __global__ void __launch_bounds__(kAfmWarps * 32) afm_rows_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
                                                                   const int64_t* __restrict__ row_offsets,
                                                                   const float* __restrict__ wa, const float* __restrict__ ba,
                                                                   const float* __restrict__ hv, const float* __restrict__ g,
                                                                   float* __restrict__ pooled, float* __restrict__ w_out,
-                                                                  float* __restrict__ ds_out, int B, int F, int P, int H,
-                                                                  int act, int* status) {
+                                                                  float* __restrict__ ds_out, float* __restrict__ d_hv, int B,
+                                                                  int F, int P, int H, int act, int* status) {
+  constexpr bool BWD = MODE != 0;
   extern __shared__ __align__(16) float sm[];
   float* s_wa = sm;
   float* s_ba = s_wa + DT * HT;
@@ -127,6 +132,9 @@ __global__ void __launch_bounds__(kAfmWarps * 32) afm_rows_kernel(const int32_t*
     s_pair[p] = (uint32_t)i | ((uint32_t)j << 16);
   }
   __syncthreads();
+  float dh_acc[HT];
+#pragma unroll
+  for (int h = 0; h < HT; ++h) dh_acc[h] = 0.f;
   for (int row = blockIdx.x * kAfmWarps + warp; row < B; row += gridDim.x * kAfmWarps) {
     __syncwarp();
     for (int e = lane; e < F * (DT / 4); e += 32) {
@@ -185,12 +193,50 @@ __global__ void __launch_bounds__(kAfmWarps * 32) afm_rows_kernel(const int32_t*
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    if (BWD) {
+    if (MODE == 1) {
       const float delta = warp_sum(dsum) * inv;
       for (int p = lane; p < P; p += 32) {
         const float w = sc[p] * inv;
         w_out[(size_t)row * P + p] = w;
         ds_out[(size_t)row * P + p] = w * (dw[p] - delta);
+      }
+    } else if (MODE == 2) {
+      const float delta = warp_sum(dsum) * inv;
+      for (int p = lane; p < P; p += 32) {
+        const float w = sc[p] * inv;
+        const float ds = w * (dw[p] - delta);
+        const uint32_t ij = s_pair[p];
+        float a[HT];
+        {
+          float ei[DT], ej[DT];
+          afm_lds<DT>(es + (size_t)(ij & 0xffff) * RS, ei);
+          afm_lds<DT>(es + (size_t)(ij >> 16) * RS, ej);
+          afm_score<DT, HT>(ei, ej, s_wa, s_ba, s_hv, act, a);
+        }
+        float hvr[HT];
+        afm_lds<HT>(s_hv, hvr);
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          dh_acc[h] = fmaf(ds, a[h], dh_acc[h]);
+          const float slope = (act == DTB_ACT_RELU && !(a[h] > 0.f)) ? 0.f : 1.f;
+          a[h] = ds * hvr[h] * slope;            // a[] now holds da
+        }
+        float4* da_dst = reinterpret_cast<float4*>(w_out + ((size_t)row * P + p) * HT);
+#pragma unroll
+        for (int c = 0; c < HT / 4; ++c) da_dst[c] = make_float4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+        float dv[DT];
+#pragma unroll
+        for (int d = 0; d < DT; ++d) {
+          float wr[HT];
+          afm_lds<HT>(s_wa + d * HT, wr);
+          float t = gr[d] * w;
+#pragma unroll
+          for (int h = 0; h < HT; ++h) t = fmaf(a[h], wr[h], t);
+          dv[d] = t;
+        }
+        float4* dv_dst = reinterpret_cast<float4*>(ds_out + ((size_t)row * P + p) * DT);
+#pragma unroll
+        for (int c = 0; c < DT / 4; ++c) dv_dst[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
       }
     } else {
 #pragma unroll
@@ -201,6 +247,55 @@ __global__ void __launch_bounds__(kAfmWarps * 32) afm_rows_kernel(const int32_t*
           reinterpret_cast<float4*>(pooled + (size_t)row * DT)[c] =
               make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
       }
+    }
+  }
+  if (MODE == 2) {
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      const float t = warp_sum(dh_acc[h]);
+      if (lane == 0 && h < H && t != 0.f) atomicAdd(d_hv + h, t);
+    }
+  }
+}
+
+// d e_f = sum over the F-1 pairs that contain f of dv_p * e_other (dv_p from afm_rows_kernel<MODE 2>): thread = (row, field),
+// grid (F, row-chunk groups); one vector RED per 4 floats.
+template <int DT>
+__global__ void __launch_bounds__(kAfmRows) afm_bwd_gather_kernel(const int32_t* __restrict__ idx, const float* __restrict__ table,
+                                                                  const int64_t* __restrict__ row_offsets,
+                                                                  const float* __restrict__ dv_in, float* __restrict__ grad_table,
+                                                                  int B, int F, int P) {
+  const int f = blockIdx.x;
+  const int n_chunks = (B + kAfmRows - 1) / kAfmRows;
+  for (int chunk = blockIdx.y; chunk < n_chunks; chunk += gridDim.y) {
+    const int row = chunk * kAfmRows + threadIdx.x;
+    if (row >= B) continue;
+    const int64_t rb = table_row(row_offsets, f, __ldg(idx + (int64_t)row * F + f), DT, nullptr);
+    if (rb < 0) continue;
+    float acc[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) acc[d] = 0.f;
+    for (int q = 0; q < F - 1; ++q) {
+      const int o = q < f ? q : q + 1;
+      const int p = o < f ? afm_pair_index(o, f, F) : afm_pair_index(f, o, F);
+      const int64_t ro = table_row(row_offsets, o, __ldg(idx + (int64_t)row * F + o), DT, nullptr);
+      if (ro < 0) continue;
+      const float4* ev = reinterpret_cast<const float4*>(table + ro);
+      const float4* dv = reinterpret_cast<const float4*>(dv_in + ((size_t)row * P + p) * DT);
+#pragma unroll
+      for (int c = 0; c < DT / 4; ++c) {
+        const float4 e = __ldg(ev + c), t = __ldg(dv + c);
+        acc[4 * c] = fmaf(t.x, e.x, acc[4 * c]);
+        acc[4 * c + 1] = fmaf(t.y, e.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(t.z, e.z, acc[4 * c + 2]);
+        acc[4 * c + 3] = fmaf(t.w, e.w, acc[4 * c + 3]);
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(grad_table + rb);
+#pragma unroll
+    for (int c = 0; c < DT / 4; ++c) {
+      const float4 v = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+      if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(dst + c, v);
     }
   }
 }
@@ -397,10 +492,11 @@ int afm_ht(int H) { return H <= 8 ? 8 : (H <= 16 ? 16 : 32); }
 
 extern "C" {
 
-size_t dtb_afm_workspace_bytes(int B, int F, int H) {
-  if (B <= 0 || F < 2 || H < 1 || H > 32) return 0;
+size_t dtb_afm_workspace_bytes(int B, int F, int D, int H) {
+  if (B <= 0 || F < 2 || H < 1 || H > 32 || D < 1) return 0;
   const size_t P = (size_t)F * (F - 1) / 2;
-  return (size_t)B * P * (2 + afm_ht(H)) * sizeof(float) + 256;
+  const size_t per_pair = afm_ht(H) + (size_t)(D > 2 ? D : 2);      // da + dv per pair (or da + w + ds on the first path)
+  return (size_t)B * P * per_pair * sizeof(float) + 256;
 }
 
 int dtb_afm_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets, const float* att_kernel,
@@ -423,10 +519,10 @@ int dtb_afm_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
   int grid = sm_count() * 4;
   if (grid > ceil_div(B, kAfmWarps)) grid = ceil_div(B, kAfmWarps);
   DTB_AFM_DISPATCH(D, HT, {
-    auto kern = afm_rows_kernel<DT_, HT_, false>;
+    auto kern = afm_rows_kernel<DT_, HT_, 0>;
     DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kAfmWarps * 32, smem, (cudaStream_t)stream>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h,
-                                                               nullptr, pooled, nullptr, nullptr, B, F, P, H, act, status);
+                                                               nullptr, pooled, nullptr, nullptr, nullptr, B, F, P, H, act, status);
   })
   DTB_LAUNCH_OK();
   return DTB_OK;
@@ -446,7 +542,7 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
     return DTB_ERR_UNSUPPORTED;
   }
   if (B == 0) return DTB_OK;
-  DTB_CHECK_ARG(workspace && workspace_bytes >= dtb_afm_workspace_bytes(B, F, H) &&
+  DTB_CHECK_ARG(workspace && workspace_bytes >= dtb_afm_workspace_bytes(B, F, D, H) &&
                     (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
                 "workspace missing, misaligned or smaller than dtb_afm_workspace_bytes");
   const int P = F * (F - 1) / 2, HT = afm_ht(H);
@@ -466,19 +562,34 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
   if (grid > ceil_div(B, kAfmWarps)) grid = ceil_div(B, kAfmWarps);
   int groups = ceil_div(sm_count() * 6, F);
   if (groups > ceil_div(B, kAfmRows)) groups = ceil_div(B, kAfmRows);
+  // DTB_AFM_BWD=1 selects the first backward (every pair recomputed from both of its fields in afm_bwd_de_kernel)
+  static const int mode = [] { const char* e = getenv("DTB_AFM_BWD"); return e ? atoi(e) : 2; }();
+  float* da2 = reinterpret_cast<float*>(workspace);             // MODE 2 layout: da [B, P, HT] | dv [B, P, D]
+  float* dv2 = da2 + (size_t)B * P * HT;
   DTB_AFM_DISPATCH(D, HT, {
-    auto k1 = afm_rows_kernel<DT_, HT_, true>;
-    DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1<<<grid, kAfmWarps * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, w_s,
-                                           ds_s, B, F, P, H, act, nullptr);
-    afm_bwd_de_kernel<DT_, HT_><<<dim3(F, groups), kAfmRows, 0, st>>>(idx, table, row_offsets, att_kernel, att_bias,
-                                                                      projection_h, d_pooled, w_s, ds_s, da_s, grad_table,
-                                                                      d_projection_h, B, F, P, H, act);
+    if (mode == 1) {
+      auto k1 = afm_rows_kernel<DT_, HT_, 1>;
+      DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k1<<<grid, kAfmWarps * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, w_s,
+                                             ds_s, nullptr, B, F, P, H, act, nullptr);
+      afm_bwd_de_kernel<DT_, HT_><<<dim3(F, groups), kAfmRows, 0, st>>>(idx, table, row_offsets, att_kernel, att_bias,
+                                                                        projection_h, d_pooled, w_s, ds_s, da_s, grad_table,
+                                                                        d_projection_h, B, F, P, H, act);
+    } else {
+      auto k1 = afm_rows_kernel<DT_, HT_, 2>;
+      DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k1<<<grid, kAfmWarps * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, da2,
+                                             dv2, d_projection_h, B, F, P, H, act, nullptr);
+      int g2 = ceil_div(sm_count() * 8, F);
+      if (g2 > ceil_div(B, kAfmRows)) g2 = ceil_div(B, kAfmRows);
+      afm_bwd_gather_kernel<DT_><<<dim3(F, g2), kAfmRows, 0, st>>>(idx, table, row_offsets, dv2, grad_table, B, F, P);
+    }
     auto k3 = afm_bwd_dw_kernel<DT_, HT_>;
     DTB_CUDA_OK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     int grid_w = sm_count() * 2;
     if (grid_w > ceil_div(B, kAfmWarps)) grid_w = ceil_div(B, kAfmWarps);
-    k3<<<grid_w, kAfmWarps * 32, smem_w, st>>>(idx, table, row_offsets, da_s, d_att_kernel, d_att_bias, B, F, P, H);
+    k3<<<grid_w, kAfmWarps * 32, smem_w, st>>>(idx, table, row_offsets, mode == 1 ? da_s : da2, d_att_kernel, d_att_bias, B, F,
+                                               P, H);
   })
   DTB_LAUNCH_OK();
   return DTB_OK;

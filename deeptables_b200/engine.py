@@ -542,7 +542,7 @@ class AFMFn(torch.autograd.Function):
         g = _f32(g)
         gt = _grad_target(t)
         dk, db, dh = torch.zeros_like(att_kernel), torch.zeros_like(att_bias), torch.zeros_like(projection_h)
-        ws_bytes = N.lib.dtb_afm_workspace_bytes(b, f, h)
+        ws_bytes = N.lib.dtb_afm_workspace_bytes(b, f, d, h)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
         check(N.lib.dtb_afm_bwd(ptr(idx), ptr(w), ptr(offs), ptr(att_kernel), ptr(att_bias), ptr(projection_h), ptr(g), ptr(gt),
                                 ptr(dk), ptr(db), ptr(dh), ptr(ws), ws_bytes, b, f, d, h, act, stream_ptr()), 'afm_bwd')

@@ -256,8 +256,8 @@ int dtb_pnn_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
  * Dense(1, use_bias=False)).  att_kernel [D,H] row-major, att_bias [H], projection_h [H];
  * act = DTB_ACT_NONE | DTB_ACT_RELU.  D in {4,8,16,32}, H <= 32, else DTB_ERR_UNSUPPORTED.
  * Backward: adds into grad_table (same layout as the table) and into d_att_kernel / d_att_bias /
- * d_projection_h (caller zero-fills); workspace of dtb_afm_workspace_bytes(B,F,H) bytes. */
-size_t dtb_afm_workspace_bytes(int B, int F, int H);
+ * d_projection_h (caller zero-fills); workspace of dtb_afm_workspace_bytes(B,F,D,H) bytes. */
+size_t dtb_afm_workspace_bytes(int B, int F, int D, int H);
 int dtb_afm_fwd(const int32_t* idx, const float* table, const int64_t* row_offsets,
                 const float* att_kernel, const float* att_bias, const float* projection_h,
                 float* pooled, int B, int F, int D, int H, int act, int* status, void* stream);

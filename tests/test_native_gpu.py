@@ -749,7 +749,7 @@ def test_afm_fwd_bwd(nat, f, d, h, b, act):
     gp = g.normal(size=(b, d)).astype(np.float32)
     gt = torch.zeros(flat.shape, device='cuda')
     dwa, dba, dph = torch.zeros(d, h, device='cuda'), torch.zeros(h, device='cuda'), torch.zeros(h, 1, device='cuda')
-    nb = nat.lib.dtb_afm_workspace_bytes(b, f, h)
+    nb = nat.lib.dtb_afm_workspace_bytes(b, f, d, h)
     ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
     nat.check(nat.lib.dtb_afm_bwd(P(d_idx), P(d_tab), P(d_offs), P(d_wa), P(d_ba), P(d_ph), P(dev(gp)), P(gt), P(dwa), P(dba), P(dph),
                                   P(ws), nb, b, f, d, h, act_code, None))

@@ -34,7 +34,7 @@ def main():
         wa, ba, ph = torch.randn(d, h, device='cuda') * 0.3, torch.zeros(h, device='cuda'), torch.randn(h, device='cuda')
         pooled, gp = torch.empty(b, d, device='cuda'), torch.randn(b, d, device='cuda')
         gt, dwa, dba, dph = torch.zeros_like(table), torch.zeros_like(wa), torch.zeros_like(ba), torch.zeros_like(ph)
-        nb = N.lib.dtb_afm_workspace_bytes(b, f, h)
+        nb = N.lib.dtb_afm_workspace_bytes(b, f, d, h)
         ws = torch.empty(nb, dtype=torch.uint8, device='cuda')
         fw = lambda: N.check(N.lib.dtb_afm_fwd(P(idx), P(table), P(offs), P(wa), P(ba), P(ph), P(pooled), b, f, d, h, 1, None, None), 'f')
         bw = lambda: N.check(N.lib.dtb_afm_bwd(P(idx), P(table), P(offs), P(wa), P(ba), P(ph), P(gp), P(gt), P(dwa), P(dba), P(dph), P(ws),
