@@ -83,6 +83,10 @@ _SIGNATURES = {
     'dtb_senet_pool_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_senet_scale_fwd': (c_int, [P, P, P, c_int, c_int, c_int, P]),
     'dtb_senet_scale_bwd': (c_int, [P, P, P, P, P, c_int, c_int, c_int, P]),
+    'dtb_conv_fields_fwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dtb_conv_fields_bwd': (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P]),
+    'dtb_maxpool_fields_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
+    'dtb_maxpool_fields_bwd': (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     'dtb_attention_core_fwd': (c_int, [P, P, c_int, c_int, c_int, c_int, c_int, P]),
     'dtb_attention_core_bwd': (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P]),
 }

@@ -140,14 +140,21 @@ __global__ void bias_act_kernel(float* __restrict__ Y, const float* __restrict__
     float v = Y[i];
     if (bias) v += bias[i % out_dim];
     if (act == DTB_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == DTB_ACT_TANH) v = tanhf(v);
     Y[i] = v;
   }
 }
 
-__global__ void act_bwd_kernel(const float* __restrict__ Y, float* __restrict__ dY, int64_t total) {
+__global__ void act_bwd_kernel(const float* __restrict__ Y, float* __restrict__ dY, int64_t total, int act) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x)
-    if (!(Y[i] > 0.f)) dY[i] = 0.f;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    if (act == DTB_ACT_TANH) {
+      const float y = Y[i];
+      dY[i] *= 1.f - y * y;
+    } else if (!(Y[i] > 0.f)) {
+      dY[i] = 0.f;
+    }
+  }
 }
 
 constexpr int kNarrow = 8;
@@ -176,6 +183,7 @@ __global__ void dense_narrow_fwd(const float* __restrict__ X, const float* __res
       if (lane == 0) {
         if (bias) v += bias[o];
         if (act == DTB_ACT_RELU) v = fmaxf(v, 0.f);
+        else if (act == DTB_ACT_TANH) v = tanhf(v);
         Y[(int64_t)r * out_dim + o] = v;
       }
     }
@@ -429,7 +437,7 @@ int dtb_dense_fwd(const float* X, const float* W, const float* bias, float* Y, v
                   size_t workspace_bytes, int rows, int in_dim, int out_dim, int act, void* stream) {
   DTB_CHECK_ARG(X && W && Y, "NULL argument");
   DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
-  DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU, "unsupported activation");
+  DTB_CHECK_ARG(act == DTB_ACT_NONE || act == DTB_ACT_RELU || act == DTB_ACT_TANH, "unsupported activation");
   if (rows == 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dim <= kNarrow) {
@@ -449,13 +457,13 @@ int dtb_dense_bwd(const float* X, const float* W, const float* Y, float* dY, flo
                   float* dbias, void* workspace, size_t workspace_bytes, int rows, int in_dim, int out_dim, int act,
                   void* stream) {
   DTB_CHECK_ARG(X && W && dY && dW, "NULL argument");
-  DTB_CHECK_ARG(act == DTB_ACT_NONE || (act == DTB_ACT_RELU && Y), "relu backward needs Y");
+  DTB_CHECK_ARG(act == DTB_ACT_NONE || ((act == DTB_ACT_RELU || act == DTB_ACT_TANH) && Y), "relu / tanh backward needs Y");
   DTB_CHECK_ARG(rows >= 0 && in_dim > 0 && out_dim > 0, "bad shape");
   if (rows == 0) return DTB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total_out = (int64_t)rows * out_dim;
-  if (act == DTB_ACT_RELU) {
-    act_bwd_kernel<<<ew_grid(total_out), 256, 0, st>>>(Y, dY, total_out);
+  if (act != DTB_ACT_NONE) {
+    act_bwd_kernel<<<ew_grid(total_out), 256, 0, st>>>(Y, dY, total_out, act);
     DTB_LAUNCH_OK();
   }
   dim3 grid, block;

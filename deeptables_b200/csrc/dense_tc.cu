@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
               }
               if (p.act == DTB_ACT_RELU) {
                 o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+              } else if (p.act == DTB_ACT_TANH) {
+                o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
               }
               if (grow < p.M) *reinterpret_cast<float4*>(p.out + (int64_t)grow * p.ldo + col) = o;
             }
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(kDtThreads, 1) dense_tc_rows_kernel(const __gr
           float val = __uint_as_float(v[j]);
           if (p.bias && col0 + j < p.Nout) val += __ldg(p.bias + col0 + j);
           if (p.act == DTB_ACT_RELU) val = fmaxf(val, 0.f);
+          else if (p.act == DTB_ACT_TANH) val = tanhf(val);
           tb[lane * 17 + j] = val;
         }
         __syncwarp();

@@ -9,8 +9,8 @@ Differences a maintainer should know:
   builders fuse the gather into their interaction kernels;
 * ``get_nets`` keeps the user's order (the reference loses it through ``set()``,
   deepnets.py:486), which only matters for ``stacking_op='concat'``;
-* fgcnn builders are outside the hot path of this build and raise ``NotImplementedError``
-  (SURVEY.md 8f rank 3); afm_nets, fibi_nets and fibi_dnn_nets run on their own kernels (afm.cu, fibinet.cu).
+* the SURVEY.md 8f rank 3 nets (afm_nets, fibi_nets, fibi_dnn_nets, fg_nets and the fgcnn_* family) run on their own
+  kernels (afm.cu, fibinet.cu, fgcnn.cu); var-len columns are not implemented.
 """
 from inspect import signature
 
@@ -177,12 +177,88 @@ def afm_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, confi
     return afm_output
 
 
-fg_nets = _out_of_scope('fg_nets')
-fgcnn_cin_nets = _out_of_scope('fgcnn_cin_nets')
-fgcnn_fm_nets = _out_of_scope('fgcnn_fm_nets')
-fgcnn_afm_nets = _out_of_scope('fgcnn_afm_nets')
-fgcnn_ipnn_nets = _out_of_scope('fgcnn_ipnn_nets')
-fgcnn_dnn_nets = _out_of_scope('fgcnn_dnn_nets')
+def fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """Feature Generation: FGCNN layers over the embedding block, new features + the embeddings (reference deepnets.py:227-261)."""
+    scope = layers.current_scope()
+    index = scope.next_index('concat_fgcnn_embedding')
+    fgcnn_emb_concat = _concat_embeddings(embeddings, f'concat_fgcnn_embedding_{index}')
+    if fgcnn_emb_concat is None:
+        model_desc.add_net('fgcnn', (None), (None))
+        return None
+    fgcnn_emb_concat = layers._materialize(fgcnn_emb_concat)
+    fg_inputs = fgcnn_emb_concat.unsqueeze(-1)
+    p = config.fgcnn_params
+    new_features = []
+    for filters, width, pool, new_filters in zip(p.get('fg_filters', (14, 16)), p.get('fg_heights', (7, 7)),
+                                                 p.get('fg_pool_heights', (2, 2)), p.get('fg_new_feat_filters', (2, 2))):
+        fg_inputs, new_feats = layers.FGCNN(filters=filters, kernel_height=width, pool_height=pool,
+                                            new_filters=new_filters)(fg_inputs)
+        new_features.append(new_feats)
+    concat_all_features = Concatenate(axis=1)(new_features + [fgcnn_emb_concat])
+    model_desc.add_net('fg', _shape(fgcnn_emb_concat), _shape(concat_all_features))
+    return concat_all_features
+
+
+def fgcnn_cin_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FGCNN with CIN as deep classifier (reference deepnets.py:264-275)."""
+    fg_output = fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if fg_output is None:
+        return None
+    cin_output = layers.CIN(params=config.cin_params)(fg_output)
+    model_desc.add_net('fgcnn-cin', _shape(fg_output), _shape(cin_output))
+    return cin_output
+
+
+def fgcnn_fm_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FGCNN with FM as deep classifier (reference deepnets.py:278-290)."""
+    fg_output = fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if fg_output is None:
+        return None
+    fm_output = layers.FM(name='fm_fgcnn_layer')(fg_output)
+    model_desc.add_net('fgcnn-fm', _shape(fg_output), _shape(fm_output))
+    return fm_output
+
+
+def fgcnn_afm_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FGCNN with AFM as deep classifier (reference deepnets.py:293-304; the split into F (B, 1, D) tensors that AFM
+    concatenates again is skipped)."""
+    fg_output = fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if fg_output is None:
+        return None
+    afm_output = layers.AFM(params=config.afm_params)(fg_output)
+    model_desc.add_net('fgcnn-afm', _shape(fg_output), _shape(afm_output))
+    return afm_output
+
+
+def fgcnn_ipnn_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FGCNN with IPNN as deep classifier (reference deepnets.py:307-324)."""
+    fg_output = fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if fg_output is None:
+        return None
+    inner_product = layers.InnerProduct()(fg_output)
+    dnn_input_layers = [Flatten()(fg_output), inner_product]
+    if dense_layer is not None:
+        dnn_input_layers.append(dense_layer)
+    dnn_input = Concatenate()(dnn_input_layers)
+    dnn_out = dnn(dnn_input, config.dnn_params, cellname='fgcnn_ipnn')
+    model_desc.add_net('fgcnn-ipnn', _shape(fg_output), _shape(dnn_out))
+    return dnn_out
+
+
+def fgcnn_dnn_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
+    """FGCNN with DNN as deep classifier (reference deepnets.py:327-341)."""
+    fg_output = fg_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc)
+    if fg_output is None:
+        return None
+    if dense_layer is not None:
+        dnn_input = Concatenate()([Flatten()(fg_output), dense_layer])
+    else:
+        dnn_input = Flatten()(fg_output)
+    dnn_out = dnn(dnn_input, config.dnn_params, cellname='fgcnn_dnn')
+    model_desc.add_net('fgcnn-ipnn', _shape(fg_output), _shape(dnn_out))
+    return dnn_out
+
+
 def fibi_nets(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
     """SENET + BilinearInteraction on the original and on the SENET-like embeddings (reference deepnets.py:344-371).
     The reference numbers its layers with a process-wide counter (utils/counter.py); here the index counts the fibi nets of

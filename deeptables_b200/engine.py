@@ -361,7 +361,7 @@ class DropoutFn(torch.autograd.Function):
         return dx, None, None
 
 
-ACT_CODES = {None: 0, 'linear': 0, 'relu': 1}
+ACT_CODES = {None: 0, 'linear': 0, 'relu': 1, 'tanh': 2}
 
 
 class DenseFn(torch.autograd.Function):
@@ -618,6 +618,58 @@ class SenetScaleFn(torch.autograd.Function):
         dx, da = torch.empty_like(x), torch.empty_like(a)
         check(N.lib.dtb_senet_scale_bwd(ptr(x), ptr(a), ptr(_f32(dv)), ptr(dx), ptr(da), b, f, d, stream_ptr()), 'senet_scale_bwd')
         return dx, da
+
+
+class ConvFieldsFn(torch.autograd.Function):
+    """FGCNN's Conv2D(filters, (kh, 1), padding='same', activation) along the field axis of [B, H, W, Cin] (layers.py:204-212)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias, act):
+        x = _f32(x)
+        b, h, w, cin = x.shape
+        kh, _, _, cout = kernel.shape
+        y = torch.empty(b, h, w, cout, dtype=torch.float32, device=x.device)
+        check(N.lib.dtb_conv_fields_fwd(ptr(x), ptr(kernel), ptr(bias), ptr(y), b, h, w, cin, cout, kh, act, stream_ptr()),
+              'conv_fields_fwd')
+        ctx.save_for_backward(x, kernel, y)
+        ctx.cfg = (act, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, kernel, y = ctx.saved_tensors
+        act, has_bias = ctx.cfg
+        b, h, w, cin = x.shape
+        kh, _, _, cout = kernel.shape
+        g = _f32(g)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dk = torch.zeros_like(kernel)
+        db = torch.zeros(cout, dtype=torch.float32, device=x.device) if has_bias else None
+        check(N.lib.dtb_conv_fields_bwd(ptr(x), ptr(kernel), ptr(y), ptr(g), ptr(dx), ptr(dk), ptr(db), b, h, w, cin, cout, kh, act,
+                                        stream_ptr()), 'conv_fields_bwd')
+        return dx, dk, db, None
+
+
+class MaxPoolFieldsFn(torch.autograd.Function):
+    """FGCNN's MaxPooling2D((pool, 1), padding='same') along the field axis (layers.py:214)."""
+
+    @staticmethod
+    def forward(ctx, x, pool):
+        x = _f32(x)
+        b, h, w, c = x.shape
+        y = torch.empty(b, -(-h // pool), w, c, dtype=torch.float32, device=x.device)
+        check(N.lib.dtb_maxpool_fields_fwd(ptr(x), ptr(y), b, h, w * c, pool, stream_ptr()), 'maxpool_fields_fwd')
+        ctx.save_for_backward(x)
+        ctx.pool = pool
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        b, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        check(N.lib.dtb_maxpool_fields_bwd(ptr(x), ptr(_f32(g)), ptr(dx), b, h, w * c, ctx.pool, stream_ptr()), 'maxpool_fields_bwd')
+        return dx, None
 
 
 class AttentionCoreFn(torch.autograd.Function):

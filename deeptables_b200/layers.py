@@ -420,7 +420,10 @@ class AFM(Layer):
             raise NotImplementedError(f'AFM attention activation {self.activation_function!r}: relu or linear')
 
     def call(self, scope, x):
-        if not isinstance(x, (list, tuple, EmbeddingList)) or len(x) < 2:
+        if torch.is_tensor(x):
+            if x.dim() != 3 or x.shape[1] < 2:           # the (B, F, D) block a list of F (B, 1, D) tensors concatenates to
+                raise ValueError('A `AttentionalFM` layer should be called on a list of at least 2 inputs')
+        elif not isinstance(x, (list, tuple, EmbeddingList)) or len(x) < 2:
             raise ValueError('A `AttentionalFM` layer should be called on a list of at least 2 inputs')
         block = _as_block(x)
         _, f, d = block.shape
@@ -436,7 +439,43 @@ class AFM(Layer):
         return E.DenseFn.apply(pooled, wo, None, E.ACT_CODES['linear'])
 
 
-FGCNN = _out_of_scope('FGCNN')
+class FGCNN(Layer):
+    """Feature generation by a convolution along the fields, max pooling and a recombination Dense layer (reference
+    layers.py:161-242).  x: (B, F, D, C).  Returns (pooling_output (B, ceil(F/pool), D, filters), new_features
+    (B, F*new_filters, D)).  Weight names: <name>/conv2d/{kernel,bias}, <name>/dense_output/{kernel,bias}."""
+
+    def __init__(self, filters, kernel_height, new_filters, pool_height, activation='tanh', name=None):
+        super().__init__(name)
+        self.filters, self.kernel_height = int(filters), int(kernel_height)
+        self.new_filters, self.pool_height = int(new_filters), int(pool_height)
+        self.activation = activation
+        if activation not in E.ACT_CODES:
+            raise NotImplementedError(f'FGCNN activation {activation!r}: tanh, relu or linear')
+
+    def call(self, scope, x):
+        x = _materialize(x)
+        if x.dim() != 4:
+            raise ValueError(f'Wrong dimensions of inputs, expected 4 but input {x.dim()}.')
+        b, h, w, cin = x.shape
+        act = E.ACT_CODES[self.activation]
+        ck = scope.param(f'{self.name}/conv2d/kernel', (self.kernel_height, 1, cin, self.filters), 'glorot_uniform')
+        cb = scope.param(f'{self.name}/conv2d/bias', (self.filters,), 'zeros')
+        h_out = -(-h // self.pool_height)
+        dk = scope.param(f'{self.name}/dense_output/kernel', (h_out * w * self.filters, h * w * self.new_filters), 'glorot_uniform')
+        db = scope.param(f'{self.name}/dense_output/bias', (h * w * self.new_filters,), 'zeros')
+        out = E.ConvFieldsFn.apply(x, ck, cb, act)
+        pooled = E.MaxPoolFieldsFn.apply(out, self.pool_height)
+        new_features = E.DenseFn.apply(pooled.reshape(b, -1), dk, db, act)
+        return pooled, new_features.reshape(b, h * self.new_filters, w)
+
+    def __call__(self, *args, **kwargs):
+        scope = current_scope()
+        self.name = scope.full_name(self._given_name, 'fgcnn')
+        out = self.call(scope, *args, **kwargs)
+        scope.record_output(self.name, out[1])
+        return out
+
+
 
 
 class SENET(Layer):
@@ -494,7 +533,7 @@ VarLenColumnEmbedding = _out_of_scope('VarLenColumnEmbedding')
 dt_custom_objects = {
     'FM': FM, 'CIN': CIN, 'Cross': Cross, 'MultiheadAttention': MultiheadAttention,
     'InnerProduct': InnerProduct, 'OuterProduct': OuterProduct, 'AFM': AFM, 'SENET': SENET,
-    'BilinearInteraction': BilinearInteraction,
+    'BilinearInteraction': BilinearInteraction, 'FGCNN': FGCNN,
 }
 
 

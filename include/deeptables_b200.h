@@ -39,6 +39,7 @@ extern "C" {
 /* activation codes (keras Activation names the hot path uses) */
 #define DTB_ACT_NONE 0
 #define DTB_ACT_RELU 1
+#define DTB_ACT_TANH 2 /* Dense layers and the FGCNN convolution (layers.py:211,219) */
 
 /* ---- library ---------------------------------------------------------------------------- */
 int dtb_version(void);
@@ -285,6 +286,24 @@ int dtb_senet_pool_bwd(const float* X, const float* Z, const float* dZ, float* d
 int dtb_senet_scale_fwd(const float* X, const float* A, float* V, int B, int F, int D, void* stream);
 int dtb_senet_scale_bwd(const float* X, const float* A, const float* dV, float* dX, float* dA, int B,
                         int F, int D, void* stream);
+
+/* ---- FGCNN (layers.py:161-242; fg_nets deepnets.py:227-261) -------------------------------- */
+/* Channels-last block X [B,H,W,Cin] (H = fields, W = embedding width).  Convolution along H only:
+ * Y[b,h,w,co] = act(bias[co] + sum_{t,ci} X[b,h+t-pad,w,ci] kernel[t,ci,co]), kernel [kh,1,Cin,Cout]
+ * as Keras stores it, TensorFlow 'same' padding (pad = (kh-1)/2 in front), act = NONE | RELU | TANH.
+ * Cin, Cout <= 32, kh <= 8, else DTB_ERR_UNSUPPORTED.  Backward: dX overwritten (may be NULL),
+ * d_kernel / d_bias accumulated (caller zero-fills; d_bias may be NULL).
+ * Max pooling along H: windows of `pool` rows, stride `pool`, 'same' padding; Y [B,ceil(H/pool),WC];
+ * the gradient goes to the first maximum of a window; dX [B,H,WC] overwritten.
+ * The recombination layer is dtb_dense_fwd/bwd with DTB_ACT_TANH. */
+int dtb_conv_fields_fwd(const float* X, const float* kernel, const float* bias, float* Y, int B,
+                        int H, int W, int Cin, int Cout, int kh, int act, void* stream);
+int dtb_conv_fields_bwd(const float* X, const float* kernel, const float* Y, const float* dY,
+                        float* dX, float* d_kernel, float* d_bias, int B, int H, int W, int Cin,
+                        int Cout, int kh, int act, void* stream);
+int dtb_maxpool_fields_fwd(const float* X, float* Y, int B, int H, int WC, int pool, void* stream);
+int dtb_maxpool_fields_bwd(const float* X, const float* dY, float* dX, int B, int H, int WC, int pool,
+                           void* stream);
 
 /* ---- MultiheadAttention core (layers.py:129-150), between the projections and the BN ------- */
 /* qkvr [B, F, 4*D]: the four relu(Dense) projections of each field row, concatenated [Q|K|V|R]

@@ -357,6 +357,43 @@ def bilinear_interaction(x, weights, bilinear_type='field_interaction'):
     return torch.cat(outs, dim=1)
 
 
+def same_padding(size, k, stride):
+    """TensorFlow 'SAME' padding along one axis: (before, after, output size)."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return total // 2, total - total // 2, out
+
+
+def conv_fields(x, kernel, bias, act='tanh'):
+    """Conv2D(filters, kernel_size=(kh, 1), strides 1, padding='same', channels_last) of FGCNN.build (layers.py:204-212):
+    x (B, H, W, Cin), kernel (kh, 1, Cin, Cout); the convolution runs along the FIELD axis H only."""
+    kh = kernel.shape[0]
+    before, after, _ = same_padding(x.shape[1], kh, 1)
+    xp = torch.nn.functional.pad(x, (0, 0, 0, 0, before, after))          # pad H
+    h = x.shape[1]
+    y = sum(torch.einsum('bhwc,co->bhwo', xp[:, t:t + h], kernel[t, 0]) for t in range(kh))
+    return activation(y + bias, act)
+
+
+def maxpool_fields(x, pool):
+    """MaxPooling2D(pool_size=(pool, 1), padding='same') (layers.py:214): windows of `pool` fields, stride `pool`,
+    TensorFlow 'SAME' padding (padded cells never win)."""
+    before, _, out = same_padding(x.shape[1], pool, pool)
+    rows = []
+    for o in range(out):
+        lo, hi = max(o * pool - before, 0), min(o * pool - before + pool, x.shape[1])
+        rows.append(x[:, lo:hi].max(dim=1).values)        # the gradient goes to the first maximum (TensorFlow's MaxPoolGrad argmax)
+    return torch.stack(rows, dim=1)
+
+
+def fgcnn(x, conv_kernel, conv_bias, dense_kernel, dense_bias, pool_height, new_filters, act='tanh'):
+    """FGCNN.call (layers.py:223-232): x (B, F, D, C) -> (pooling_output (B, F', D, filters), new_features (B, F*new_filters, D))."""
+    out = conv_fields(x, conv_kernel, conv_bias, act)
+    pooled = maxpool_fields(out, pool_height)
+    new = activation(pooled.reshape(pooled.shape[0], -1) @ dense_kernel + dense_bias, act)
+    return pooled, new.reshape(-1, out.shape[1] * new_filters, out.shape[2])
+
+
 def dnn(x, params, weights, bn_state, training, cellname='dnn'):
     """deepnets.dnn (deepnets.py:401-427): [Dense(use_bias=not bn) -> BN? -> act -> Dropout?]*.
     Dropout layers are identity in this oracle (parity runs use rate 0 / inference)."""

@@ -21,7 +21,8 @@ import torch
 from . import layers_ref as L
 
 SUPPORTED_NETS = ('linear', 'cin_nets', 'fm_nets', 'opnn_nets', 'ipnn_nets', 'pnn_nets', 'dnn_nets',
-                  'cross_nets', 'cross_dnn_nets', 'dcn_nets', 'autoint_nets', 'afm_nets', 'fibi_nets', 'fibi_dnn_nets')
+                  'cross_nets', 'cross_dnn_nets', 'dcn_nets', 'autoint_nets', 'afm_nets', 'fibi_nets', 'fibi_dnn_nets', 'fg_nets',
+                  'fgcnn_cin_nets', 'fgcnn_fm_nets', 'fgcnn_afm_nets', 'fgcnn_ipnn_nets', 'fgcnn_dnn_nets')
 
 
 def bilinear_weight_names(layer, f, bilinear_type):
@@ -31,6 +32,71 @@ def bilinear_weight_names(layer, f, bilinear_type):
     if bilinear_type == 'field_each':
         return [f'{layer}/bilinear_weight{i}' for i in range(f - 1)]
     return [f'{layer}/bilinear_weight{i}_{j}' for i in range(f) for j in range(i + 1, f)]
+
+
+FG_NETS = ('fg_nets', 'fgcnn_cin_nets', 'fgcnn_fm_nets', 'fgcnn_afm_nets', 'fgcnn_ipnn_nets', 'fgcnn_dnn_nets')
+
+
+def _fg_levels(f, params):
+    """fg_nets (deepnets.py:245-258): per FGCNN layer (filters, kernel height, pool height, new filters, fields in, fields out)."""
+    levels, h = [], f
+    for filters, kh, pool, new in zip(params.get('fg_filters', (14, 16)), params.get('fg_heights', (7, 7)),
+                                      params.get('fg_pool_heights', (2, 2)), params.get('fg_new_feat_filters', (2, 2))):
+        h_out = -(-h // pool)
+        levels.append((filters, kh, pool, new, h, h_out))
+        h = h_out
+    return levels
+
+
+def _fg_entries(f, d0, params, first_layer_index):
+    """Weights of the FGCNN layers of one fg_nets call (auto-named fgcnn, fgcnn_1, ... in creation order), the number of
+    fields of its output (new features + the original embeddings) and the next free layer index."""
+    ents, cin, total, k = [], 1, f, first_layer_index
+    for filters, kh, pool, new, h, h_out in _fg_levels(f, params):
+        name = 'fgcnn' if k == 0 else f'fgcnn_{k}'
+        ents += [(f'{name}/conv2d/kernel', (kh, 1, cin, filters), 'glorot_uniform'), (f'{name}/conv2d/bias', (filters,), 'zeros'),
+                 (f'{name}/dense_output/kernel', (h_out * d0 * filters, h * d0 * new), 'glorot_uniform'),
+                 (f'{name}/dense_output/bias', (h * d0 * new,), 'zeros')]
+        total += h * new
+        cin = filters
+        k += 1
+    return ents, total, k
+
+
+def fg_forward(state, cat, params, first_layer_index):
+    """fg_nets (deepnets.py:227-261): (B, F, D) -> (B, F_fg, D) = [new features of every FGCNN layer ..., the embeddings]."""
+    x = cat.unsqueeze(-1)
+    feats, k = [], first_layer_index
+    for filters, kh, pool, new, h, h_out in _fg_levels(cat.shape[1], params):
+        name = 'fgcnn' if k == 0 else f'fgcnn_{k}'
+        x, nf = L.fgcnn(x, state[f'{name}/conv2d/kernel'], state[f'{name}/conv2d/bias'], state[f'{name}/dense_output/kernel'],
+                        state[f'{name}/dense_output/bias'], pool, new)
+        feats.append(nf)
+        k += 1
+    return torch.cat(feats + [cat], dim=1), k
+
+
+def _cin_entries(f, d0, p, name):
+    ents = []
+    sizes = tuple(p.get('cross_layer_size', (128, 128)))
+    fns = L.cin_field_nums(f, sizes, p.get('direct', False))
+    for k, size in enumerate(sizes):
+        if p.get('reduce_D', False):
+            ents.append((f'{name}/f0_{k}', (1, size, fns[0], d0), 'he_uniform'))
+            ents.append((f'{name}/f__{k}', (1, size, d0, fns[k]), 'he_uniform'))
+        else:
+            ents.append((f'{name}/f_{k}', (1, fns[k] * fns[0], size), 'he_uniform'))
+        if p.get('use_bias', False):
+            ents.append((f'{name}/bias{k}', (size,), 'zeros'))
+    pooled = L.cin_pooled_width(f, p)
+    if p.get('use_residual', False):
+        ents.append((f'{name}/exFM_out0/kernel', (pooled, sizes[-1]), 'he_uniform'))
+        ents.append((f'{name}/exFM_out0/bias', (sizes[-1],), 'zeros'))
+        ents.append((f'{name}/exFM_out/kernel', (pooled + sizes[-1], 1), 'glorot_uniform'))
+    else:
+        ents.append((f'{name}/exFM_out/kernel', (pooled, 1), 'glorot_uniform'))
+    ents.append((f'{name}/exFM_out/bias', (1,), 'zeros'))
+    return ents
 
 
 def _fibi_entries(f, d0, params, index):
@@ -127,6 +193,7 @@ def param_spec(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes
     widths = {}
     d0 = emb_dims[0] if f else 0
     n_fibi = 0
+    n_fg = 0
     for net in nets:
         if net == 'linear':
             ents.append(('linear_logit/kernel', (f + n_cont, 1), 'glorot_uniform'))
@@ -137,26 +204,31 @@ def param_spec(config, vocab_sizes, emb_dims, n_cont, task='binary', num_classes
         elif net == 'cin_nets':
             if not f:
                 continue
-            p = _get(config, 'cin_params')
-            sizes = tuple(p.get('cross_layer_size', (128, 128)))
-            fns = L.cin_field_nums(f, sizes, p.get('direct', False))
-            for k, size in enumerate(sizes):
-                if p.get('reduce_D', False):
-                    ents.append((f'cin/f0_{k}', (1, size, fns[0], d0), 'he_uniform'))
-                    ents.append((f'cin/f__{k}', (1, size, d0, fns[k]), 'he_uniform'))
-                else:
-                    ents.append((f'cin/f_{k}', (1, fns[k] * fns[0], size), 'he_uniform'))
-                if p.get('use_bias', False):
-                    ents.append((f'cin/bias{k}', (size,), 'zeros'))
-            pooled = L.cin_pooled_width(f, p)
-            if p.get('use_residual', False):
-                ents.append(('cin/exFM_out0/kernel', (pooled, sizes[-1]), 'he_uniform'))
-                ents.append(('cin/exFM_out0/bias', (sizes[-1],), 'zeros'))
-                ents.append(('cin/exFM_out/kernel', (pooled + sizes[-1], 1), 'glorot_uniform'))
-            else:
-                ents.append(('cin/exFM_out/kernel', (pooled, 1), 'glorot_uniform'))
-            ents.append(('cin/exFM_out/bias', (1,), 'zeros'))
+            ents += _cin_entries(f, d0, _get(config, 'cin_params'), 'cin')
             widths[net] = 1
+        elif net in FG_NETS:
+            if not f:
+                continue
+            fg_ents, f_fg, n_fg = _fg_entries(f, d0, _get(config, 'fgcnn_params'), n_fg)
+            ents += fg_ents
+            if net == 'fg_nets':
+                widths[net] = f_fg * d0
+            elif net == 'fgcnn_cin_nets':
+                ents += _cin_entries(f_fg, d0, _get(config, 'cin_params'), 'cin')
+                widths[net] = 1
+            elif net == 'fgcnn_fm_nets':
+                widths[net] = 1
+            elif net == 'fgcnn_afm_nets':
+                h = _get(config, 'afm_params').get('hidden_factor', 16)
+                ents += [('afm/dense_attention/kernel', (d0, h), 'glorot_normal'), ('afm/dense_attention/bias', (h,), 'zeros'),
+                         ('afm/dense_out/kernel', (d0, 1), 'glorot_uniform'), ('afm/projection_h', (h, 1), 'glorot_uniform')]
+                widths[net] = 1
+            else:
+                cell = 'fgcnn_ipnn' if net == 'fgcnn_ipnn_nets' else 'fgcnn_dnn'
+                width_in = f_fg * d0 + n_cont + (f_fg * (f_fg - 1) // 2 if net == 'fgcnn_ipnn_nets' else 0)
+                e, width = _dnn_entries(width_in, _get(config, 'dnn_params'), cell)
+                ents += e
+                widths[net] = width
         elif net in ('opnn_nets', 'ipnn_nets', 'pnn_nets'):
             if f < 2:
                 continue
@@ -299,6 +371,7 @@ def forward(state, config, cat_idx, cont, n_fields, training, task='binary', ret
 
     outs = {}
     n_fibi = 0
+    n_fg = 0
     for net in nets:
         if net == 'linear':
             outs[net] = L.linear(embeddings, dense_layer, state['linear_logit/kernel'])
@@ -336,6 +409,29 @@ def forward(state, config, cat_idx, cont, n_fields, training, task='binary', ret
                 outs[net] = run_dnn(c, 'cross_dnn')
             else:
                 outs[net] = torch.cat([c, run_dnn(ced, 'dcn')], dim=-1)
+        elif net in FG_NETS:
+            cat = L.concat_embeddings(embeddings)
+            if cat is None:
+                continue
+            fg, n_fg = fg_forward(state, cat, _get(config, 'fgcnn_params'), n_fg)
+            split = [fg[:, i:i + 1, :] for i in range(fg.shape[1])]
+            if net == 'fg_nets':
+                outs[net] = fg
+            elif net == 'fgcnn_cin_nets':
+                outs[net] = L.cin(fg, _get(config, 'cin_params'), _sub(state, 'cin'))
+            elif net == 'fgcnn_fm_nets':
+                outs[net] = L.fm(fg)
+            elif net == 'fgcnn_afm_nets':
+                outs[net] = L.afm(split, state['afm/dense_attention/kernel'], state['afm/dense_attention/bias'],
+                                  state['afm/projection_h'], state['afm/dense_out/kernel'],
+                                  _get(config, 'afm_params').get('activation', 'relu'))
+            else:
+                parts_in = [fg.reshape(fg.shape[0], -1)]
+                if net == 'fgcnn_ipnn_nets':
+                    parts_in.append(L.inner_product(split))
+                if dense_layer is not None:
+                    parts_in.append(dense_layer)
+                outs[net] = run_dnn(torch.cat(parts_in, dim=-1), 'fgcnn_ipnn' if net == 'fgcnn_ipnn_nets' else 'fgcnn_dnn')
         elif net == 'afm_nets':
             if len(embeddings) < 2:
                 continue

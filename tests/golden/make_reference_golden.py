@@ -241,7 +241,7 @@ def make_model_cases(deepmodel, config_mod, metainfo, rec):
 # C. the SURVEY 8f-3 layers (AFM, SENET + BilinearInteraction = FiBiNet) and their nets, in a file of their own so that the
 #    vectors above stay bit-identical to the ones committed in round 1
 # ------------------------------------------------------------------------------------------------------------
-F3_CHILD_ATTRS = ('dense_attention', 'dense_out', 'dense_att1', 'dense_att2')
+F3_CHILD_ATTRS = ('dense_attention', 'dense_out', 'dense_att1', 'dense_att2', 'conv2d', 'dense_output', 'exFM_out', 'exFM_out0')
 
 F3_MODEL_CASES = [
     ('afm', dict(nets=['afm_nets'], afm_params={'hidden_factor': 5, 'dropout_rate': 0}), [7, 5, 9, 4], 4, 3, 'binary', 2),
@@ -249,6 +249,13 @@ F3_MODEL_CASES = [
     ('fibi_dnn', dict(nets=['fibi_dnn_nets']), [7, 5, 9, 4], 4, 3, 'binary', 2),
     ('fibi_all_max', dict(nets=['fibi_dnn_nets'], fibinet_params={'senet_pooling_op': 'max', 'senet_reduction_ratio': 2,
                                                                   'bilinear_type': 'field_all'}), [7, 5, 9], 4, 2, 'regression', None),
+    ('fgcnn_dnn', dict(nets=['fgcnn_dnn_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}), [7, 5, 9, 4, 6], 4, 3, 'binary', 2),
+    ('fgcnn_dnn_no_cont', dict(nets=['fgcnn_dnn_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}), [7, 5, 9], 4, 0, 'regression', None),
+    ('fgcnn_fm_plus_linear', dict(nets=['linear', 'fgcnn_fm_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}), [7, 5, 9, 4], 4, 2, 'binary', 2),
+    ('fgcnn_cin', dict(nets=['fgcnn_cin_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}, cin_params=CIN_SMALL), [7, 5, 9, 4], 4, 0, 'binary', 2),
+    ('fgcnn_afm', dict(nets=['fgcnn_afm_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}, afm_params={'hidden_factor': 4}), [7, 5, 9], 4, 1, 'binary', 2),
+    ('fgcnn_ipnn', dict(nets=['fgcnn_ipnn_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}), [7, 5, 9, 4], 4, 2, 'binary', 2),
+    ('fg_only', dict(nets=['fg_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2), 'fg_pool_heights': (2, 2), 'fg_new_feat_filters': (2, 1)}), [7, 5, 9], 4, 1, 'binary', 2),
     ('fibi_each_plus_fm', dict(nets=['fm_nets', 'fibi_nets'], fibinet_params={'senet_pooling_op': 'mean', 'senet_reduction_ratio': 3,
                                                                               'bilinear_type': 'field_each'}), [7, 5, 9, 4], 4, 1, 'binary', 2),
 ]
@@ -295,7 +302,18 @@ def make_f3_cases(layers, deepmodel, config_mod, metainfo, counter, rec):
         ws = [lyr.W] if bt == 'field_all' else list(lyr.W_list)
         rec.add(f'bilinear_{bt}', 'bilinear', {'bilinear_type': bt}, x=np64(x), out=np64(out),
                 **{f'w{i}': np64(w) for i, w in enumerate(ws)})
-    # whole models with afm_nets / fibi_nets / fibi_dnn_nets through DeepModel.__build_model
+    # FGCNN (layers.py:161-242): two stacked layers, odd / even kernel heights, pool heights that do and do not divide F
+    x = rand(5, 7, 4, 1, seed=95)
+    lyr1 = layers.FGCNN(filters=3, kernel_height=3, new_filters=2, pool_height=2)
+    po1, nf1 = lyr1(x)
+    lyr2 = layers.FGCNN(filters=4, kernel_height=4, new_filters=1, pool_height=3)
+    po2, nf2 = lyr2(po1)
+    for case, lyr, xin, po, nf, p_ in (('fgcnn_first', lyr1, x, po1, nf1, dict(filters=3, kernel_height=3, new_filters=2, pool_height=2)),
+                                       ('fgcnn_second', lyr2, po1, po2, nf2, dict(filters=4, kernel_height=4, new_filters=1, pool_height=3))):
+        rec.add(case, 'fgcnn', p_, x=np64(xin), out=np64(nf), pooled=np64(po),
+                conv_kernel=np64(lyr.conv2d.weights_by_name['kernel']), conv_bias=np64(lyr.conv2d.weights_by_name['bias']),
+                dense_kernel=np64(lyr.dense_output.weights_by_name['kernel']), dense_bias=np64(lyr.dense_output.weights_by_name['bias']))
+    # whole models with afm_nets / fibi_nets / fibi_dnn_nets / fgcnn_* through DeepModel.__build_model
     for ci, (case, cfg_kwargs, vocab, dim, n_cont, task, num_classes) in enumerate(F3_MODEL_CASES):
         conf = config_mod.ModelConfig(embedding_dropout=0, dense_dropout=0, embeddings_output_dim=dim, **cfg_kwargs)
         cats = [metainfo.CategoricalColumn(f'c{i}', v, dim) for i, v in enumerate(vocab)]

@@ -280,6 +280,56 @@ class Add(Layer):
         return out
 
 
+def _same_pad(size, k, stride):
+    """TensorFlow 'SAME' padding along one axis: (before, after)."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return total // 2, total - total // 2
+
+
+class Conv2D(Layer):
+    """keras Conv2D, channels_last, stride 1: kernel [kh, kw, in, filters]; 'same' = TensorFlow's asymmetric padding."""
+
+    def __init__(self, filters, kernel_size, strides=(1, 1), padding='valid', activation=None, use_bias=True,
+                 kernel_initializer='glorot_uniform', **kwargs):
+        super().__init__(**kwargs)
+        assert tuple(strides) == (1, 1)
+        self.filters, self.kernel_size, self.padding = int(filters), tuple(kernel_size), padding
+        self.activation, self.use_bias = activation, use_bias
+
+    def build(self, input_shape):
+        kh, kw = self.kernel_size
+        self.kernel = self.add_weight('kernel', (kh, kw, input_shape[-1], self.filters))
+        self.bias = self.add_weight('bias', (self.filters,)) if self.use_bias else None
+
+    def call(self, x, **kwargs):
+        kh, kw = self.kernel_size
+        xc = x.permute(0, 3, 1, 2)                                    # NHWC -> NCHW
+        if self.padding == 'same':
+            (t, b), (l, r) = _same_pad(x.shape[1], kh, 1), _same_pad(x.shape[2], kw, 1)
+            xc = torch.nn.functional.pad(xc, (l, r, t, b))
+        w = self.weights_by_name['kernel'].permute(3, 2, 0, 1)        # [filters, in, kh, kw]
+        y = torch.nn.functional.conv2d(xc, w, self.weights_by_name['bias'] if self.use_bias else None)
+        return _ACTIVATIONS[self.activation](y.permute(0, 2, 3, 1))
+
+
+class MaxPooling2D(Layer):
+    """keras MaxPooling2D, channels_last, strides = pool_size; 'same' pads with -inf the TensorFlow way."""
+
+    def __init__(self, pool_size=(2, 2), strides=None, padding='valid', **kwargs):
+        super().__init__(**kwargs)
+        self.pool_size, self.padding = tuple(pool_size), padding
+        self.strides = tuple(strides) if strides is not None else self.pool_size
+
+    def call(self, x, **kwargs):
+        (ph, pw), (sh, sw) = self.pool_size, self.strides
+        xc = x.permute(0, 3, 1, 2)
+        if self.padding == 'same':
+            (t, b), (l, r) = _same_pad(x.shape[1], ph, sh), _same_pad(x.shape[2], pw, sw)
+            xc = torch.nn.functional.pad(xc, (l, r, t, b), value=float('-inf'))
+        return torch.nn.functional.max_pool2d(xc, (ph, pw), (sh, sw)).permute(0, 2, 3, 1)
+
+
 class _Unused(Layer):
     def __init__(self, *a, **k):
         raise NotImplementedError(f'{type(self).__name__} is not on the hot path; the shim does not restate it')
@@ -350,8 +400,8 @@ def install(reference_root='/root/reference'):
 
     layer_names = dict(Layer=Layer, Dense=Dense, Dropout=Dropout, BatchNormalization=BatchNormalization,
                        Activation=Activation, Concatenate=Concatenate, Flatten=Flatten, Input=Input, Add=Add,
-                       SpatialDropout1D=SpatialDropout1D)
-    for unused in ('Embedding', 'Lambda', 'Conv2D', 'MaxPooling2D'):
+                       SpatialDropout1D=SpatialDropout1D, Conv2D=Conv2D, MaxPooling2D=MaxPooling2D)
+    for unused in ('Embedding', 'Lambda'):
         layer_names[unused] = type(unused, (_Unused,), {})
     keras = _module('keras')
     _module('keras.api')
@@ -368,6 +418,8 @@ def install(reference_root='/root/reference'):
     ops.sum = lambda x, axis=None, keepdims=False: tf_reduce_sum(x, axis, keepdims)
     ops.cast = lambda x, dtype: _as_tensor(x).to(torch.int64 if 'int' in str(dtype) else DTYPE)
     ops.not_equal = lambda a, b: _as_tensor(a) != b
+    ops.expand_dims = lambda x, axis: _as_tensor(x).unsqueeze(axis)
+    ops.split = lambda x, indices_or_sections, axis=0: tf_split(x, indices_or_sections, axis)
     keras.ops = ops
     getter = types.SimpleNamespace(get=lambda ident: ident, serialize=lambda obj: obj)
     for sub in ('initializers', 'regularizers', 'constraints'):

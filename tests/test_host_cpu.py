@@ -67,8 +67,6 @@ def test_nets_registry_names_presets_and_signature():
     with pytest.raises(ValueError):
         deepnets.get(None)
     assert deepnets.get('afm_nets')(None, None, None, None, None, None) is None      # fewer than 2 embeddings (deepnets.py:103)
-    with pytest.raises(NotImplementedError):
-        deepnets.get('fg_nets')(None, None, None, None, None, None)
 
     def custom(embeddings, flatten_emb_layer, dense_layer, concat_emb_dense, config, model_desc):
         return None

@@ -2,6 +2,8 @@
 fp32 kernels: rtol 1e-4 (tolerance stated per test); index bookkeeping bit-exact."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -786,6 +788,70 @@ def test_bilinear_fwd_bwd(nat, f, d, b, bt):
     gx, gw = torch.autograd.grad((want * torch.tensor(go, dtype=torch.float64)).sum(), [x64, w64])
     np.testing.assert_allclose(dx.cpu().numpy(), gx.numpy(), rtol=1e-3, atol=1e-4 * float(gx.abs().max()))
     np.testing.assert_allclose(dw.cpu().numpy(), gw.numpy(), rtol=1e-3, atol=1e-4 * float(gw.abs().max()))
+
+
+FGCNN_GATE = pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='FGCNN kernels: set DTB_TEST_FGCNN=1 (not yet run on a B200)')
+
+
+@FGCNN_GATE
+@pytest.mark.parametrize('b,h,w,cin,cout,kh,pool,act', [(9, 26, 16, 1, 14, 7, 2, 'tanh'), (5, 13, 16, 14, 16, 7, 2, 'tanh'),
+                                                        (7, 7, 4, 3, 4, 4, 3, 'relu'), (33, 5, 8, 32, 32, 8, 5, 'linear'),
+                                                        (300, 3, 4, 2, 5, 1, 1, 'tanh')])
+def test_fgcnn_conv_and_pool_fwd_bwd(nat, b, h, w, cin, cout, kh, pool, act):
+    """FGCNN's convolution and max pooling along the field axis (layers.py:204-214) against the fp64 oracle's autograd."""
+    g = np.random.default_rng(81)
+    x = g.normal(size=(b, h, w, cin)).astype(np.float32)
+    k = (g.normal(size=(kh, 1, cin, cout)) / np.sqrt(kh * cin)).astype(np.float32)
+    bias = (g.normal(size=(cout,)) * 0.1).astype(np.float32)
+    code = {'linear': 0, 'relu': 1, 'tanh': 2}[act]
+    d_x, d_k, d_b = dev(x), dev(k), dev(bias)
+    y = torch.empty(b, h, w, cout, device='cuda')
+    nat.check(nat.lib.dtb_conv_fields_fwd(P(d_x), P(d_k), P(d_b), P(y), b, h, w, cin, cout, kh, code, None))
+    x64 = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    k64 = torch.tensor(k, dtype=torch.float64, requires_grad=True)
+    b64 = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+    want = L.conv_fields(x64, k64, b64, act)
+    np.testing.assert_allclose(y.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=1e-5)
+    ho = -(-h // pool)
+    pooled = torch.empty(b, ho, w, cout, device='cuda')
+    nat.check(nat.lib.dtb_maxpool_fields_fwd(P(y), P(pooled), b, h, w * cout, pool, None))
+    want_p = L.maxpool_fields(want, pool)
+    np.testing.assert_allclose(pooled.cpu().numpy(), want_p.detach().numpy(), rtol=1e-4, atol=1e-5)
+    gp = g.normal(size=(b, ho, w, cout)).astype(np.float32)
+    dy = torch.empty_like(y)
+    nat.check(nat.lib.dtb_maxpool_fields_bwd(P(y), P(dev(gp)), P(dy), b, h, w * cout, pool, None))
+    dx, dk, db = torch.empty_like(d_x), torch.zeros_like(d_k), torch.zeros_like(d_b)
+    nat.check(nat.lib.dtb_conv_fields_bwd(P(d_x), P(d_k), P(y), P(dy), P(dx), P(dk), P(db), b, h, w, cin, cout, kh, code, None))
+    gy, = torch.autograd.grad((want_p * torch.tensor(gp, dtype=torch.float64)).sum(), [want], retain_graph=True)
+    gx, gk, gb = torch.autograd.grad((want_p * torch.tensor(gp, dtype=torch.float64)).sum(), [x64, k64, b64])
+    np.testing.assert_allclose(dy.cpu().numpy(), gy.numpy(), rtol=1e-4, atol=1e-6)
+    for name, got, ref in (('dx', dx, gx), ('dk', dk, gk), ('db', db, gb)):
+        np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4 * float(ref.abs().max()), err_msg=name)
+
+
+@FGCNN_GATE
+def test_dense_tanh_activation(nat):
+    """DTB_ACT_TANH in the Dense epilogues (wide: tcgen05 path, narrow: row-dot path) and its backward."""
+    g = np.random.default_rng(82)
+    for rows, i, o in ((300, 36, 40), (200, 48, 5)):
+        x = g.normal(size=(rows, i)).astype(np.float32)
+        w = (g.normal(size=(i, o)) / np.sqrt(i)).astype(np.float32)
+        bias = (g.normal(size=(o,)) * 0.1).astype(np.float32)
+        d_x, d_w, d_b = dev(x), dev(w), dev(bias)
+        y = torch.empty(rows, o, device='cuda')
+        nb = nat.lib.dtb_dense_workspace_bytes(i, o)
+        ws = torch.empty(max(nb, 16), dtype=torch.uint8, device='cuda')
+        nat.check(nat.lib.dtb_dense_fwd(P(d_x), P(d_w), P(d_b), P(y), P(ws), nb, rows, i, o, 2, None))
+        x64, w64, b64 = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, w, bias))
+        want = torch.tanh(x64 @ w64 + b64)
+        np.testing.assert_allclose(y.cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=2e-5)
+        gy = g.normal(size=(rows, o)).astype(np.float32)
+        dyv, dx, dw, db = dev(gy), torch.empty_like(d_x), torch.zeros_like(d_w), torch.zeros_like(d_b)
+        y_ref = torch.tensor(want.detach().numpy().astype(np.float32)).cuda()        # the oracle's outputs: same tanh' on both sides
+        nat.check(nat.lib.dtb_dense_bwd(P(d_x), P(d_w), P(y_ref), P(dyv), P(dx), P(dw), P(db), P(ws), nb, rows, i, o, 2, None))
+        gx, gw, gb = torch.autograd.grad((want * torch.tensor(gy, dtype=torch.float64)).sum(), [x64, w64, b64])
+        for name, got, ref in (('dx', dx, gx), ('dw', dw, gw), ('db', db, gb)):
+            np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4 * float(ref.abs().max()), err_msg=name)
 
 
 @pytest.mark.parametrize('op', ['mean', 'max'])

@@ -108,6 +108,10 @@ def test_oracle_f3_layer_reproduces_reference_layer(meta):
         w = _weights(z, case)
         got = L.senet(_t(z[f'{case}/x']), w['dense_att1/kernel'], w['dense_att1/bias'], w['dense_att2/kernel'],
                       w['dense_att2/bias'], p['pooling_op'])
+    elif kind == 'fgcnn':
+        pooled, got = L.fgcnn(_t(z[f'{case}/x']), _t(z[f'{case}/conv_kernel']), _t(z[f'{case}/conv_bias']),
+                              _t(z[f'{case}/dense_kernel']), _t(z[f'{case}/dense_bias']), p['pool_height'], p['new_filters'])
+        np.testing.assert_allclose(pooled.numpy(), z[f'{case}/pooled'], **TOL)
     elif kind == 'bilinear':
         n = len([k for k in z.files if k.startswith(f'{case}/w')])
         got = L.bilinear_interaction(_t(z[f'{case}/x']), [_t(z[f'{case}/w{i}']) for i in range(n)], p['bilinear_type'])
@@ -127,10 +131,13 @@ def _model_config(p):
         kw['dnn_params']['hidden_units'] = tuple(tuple(h) for h in kw['dnn_params']['hidden_units'])
     if 'cin_params' in kw:
         kw['cin_params']['cross_layer_size'] = tuple(kw['cin_params']['cross_layer_size'])
+    if 'fgcnn_params' in kw:
+        kw['fgcnn_params'] = {k: tuple(v) for k, v in kw['fgcnn_params'].items()}
     return deeptable.ModelConfig(embedding_dropout=0, dense_dropout=0, embeddings_output_dim=p['dim'], **kw)
 
 
 ALL_MODEL_CASES = [(MODELS_Z, m) for m in MODEL_CASES] + [(F3_Z, m) for m in F3_MODEL_CASES]
+FGCNN_ON_GPU = os.environ.get('DTB_TEST_FGCNN') == '1'          # the FGCNN kernels have not yet run on a B200
 
 
 @pytest.mark.parametrize('zm', ALL_MODEL_CASES, ids=[m['case'] for _, m in ALL_MODEL_CASES])
@@ -187,6 +194,8 @@ def test_cuda_model_reproduces_reference_build_model(zm):
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
     z, meta = zm
     case, p = meta['case'], meta['params']
+    if any(n.startswith('fg') for n in p['config']['nets']) and not FGCNN_ON_GPU:
+        pytest.skip('FGCNN: set DTB_TEST_FGCNN=1')
     conf = _model_config(p)
     cats = [CategoricalColumn(f'c{i}', v, p['dim']) for i, v in enumerate(p['vocab'])]
     conts = [ContinuousColumn('input_continuous_all', [f'n{i}' for i in range(p['n_cont'])])] if p['n_cont'] else []
