@@ -304,6 +304,70 @@ __global__ void loss_kernel(const float* __restrict__ z, const float* __restrict
   if (loss_sum && (threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(loss_sum, local);
 }
 
+// Focal losses (reference layers.py:983-1083) on the task_output pre-activation.
+// task 0: BinaryFocalLoss on p = sigmoid(z): pt_1 = (y == 1 ? p : 1), pt_0 = (y == 0 ? p : 0), both clipped to [eps, 1-eps];
+//         loss = mean over ALL elements of  -alpha (1-pt_1)^gamma log pt_1 - (1-alpha) pt_0^gamma log(1-pt_0)  (a scalar).
+// task 2: CategoricalFocalLoss on p = softmax(z): renormalise (identity, but its Jacobian is kept), clip,
+//         per-sample sum_c alpha (1-p_c)^gamma (-y_c log p_c); Keras averages the samples.
+//         dL/dz_k = p_k (g_k - sum_c g_c p_c) / rows,  g_c = dL/dq_c on the clipped renormalised probability.
+__global__ void focal_loss_kernel(const float* __restrict__ z, const float* __restrict__ y, float* __restrict__ prob,
+                                  float* __restrict__ dz, double* __restrict__ loss_sum, int rows, int cols, int task,
+                                  float gamma, float alpha) {
+  const float eps = 1e-7f;
+  double local = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float* zr = z + (int64_t)r * cols;
+    const float* yr = y + (int64_t)r * cols;
+    float* pr = prob + (int64_t)r * cols;
+    float* dr = dz ? dz + (int64_t)r * cols : nullptr;
+    float row_loss = 0.f;
+    if (task == 0) {
+      const float scale = 1.f / ((float)rows * (float)cols);
+      for (int c = 0; c < cols; ++c) {
+        const float p = 1.f / (1.f + expf(-zr[c]));
+        pr[c] = p;
+        const bool is1 = yr[c] == 1.f, is0 = yr[c] == 0.f;
+        const float pt1 = fminf(fmaxf(is1 ? p : 1.f, eps), 1.f - eps);
+        const float pt0 = fminf(fmaxf(is0 ? p : 0.f, eps), 1.f - eps);
+        row_loss += -alpha * powf(1.f - pt1, gamma) * logf(pt1) - (1.f - alpha) * powf(pt0, gamma) * logf(1.f - pt0);
+        if (dr) {
+          float g = 0.f;                                   // dLoss/dp: only the branch that depends on p, inside the clip range
+          if (p >= eps && p <= 1.f - eps) {
+            if (is1) g = alpha * (gamma * powf(1.f - p, gamma - 1.f) * logf(p) - powf(1.f - p, gamma) / p);
+            else if (is0) g = (1.f - alpha) * (-gamma * powf(p, gamma - 1.f) * logf(1.f - p) + powf(p, gamma) / (1.f - p));
+          }
+          dr[c] = g * p * (1.f - p) * scale;
+        }
+      }
+      row_loss /= (float)cols;
+    } else {
+      float mx = -INFINITY;
+      for (int c = 0; c < cols; ++c) mx = fmaxf(mx, zr[c]);
+      float den = 0.f;
+      for (int c = 0; c < cols; ++c) den += expf(zr[c] - mx);
+      float gp = 0.f;                                      // sum_c g_c p_c
+      for (int c = 0; c < cols; ++c) {
+        const float p = expf(zr[c] - mx) / den;
+        pr[c] = p;
+        const float q = fminf(fmaxf(p, eps), 1.f - eps);
+        row_loss += alpha * powf(1.f - q, gamma) * (-yr[c] * logf(q));
+        if (p >= eps && p <= 1.f - eps)
+          gp += alpha * yr[c] * (gamma * powf(1.f - p, gamma - 1.f) * logf(p) - powf(1.f - p, gamma) / p) * p;
+      }
+      if (dr)
+        for (int c = 0; c < cols; ++c) {
+          const float p = pr[c];
+          float g = 0.f;
+          if (p >= eps && p <= 1.f - eps) g = alpha * yr[c] * (gamma * powf(1.f - p, gamma - 1.f) * logf(p) - powf(1.f - p, gamma) / p);
+          dr[c] = p * (g - gp) / (float)rows;
+        }
+    }
+    local += (double)row_loss;
+  }
+  local = warp_sum(local);
+  if (loss_sum && (threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(loss_sum, local);
+}
+
 // ------------------------------------------------------------------------------------------
 // Dropout (keras Dropout / SpatialDropout1D on (B,1,D) field embeddings == element-wise): counter-based
 // mask, so forward and backward regenerate the same bits from (seed, element index); nothing is stored.
@@ -504,6 +568,21 @@ int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_we
   if (blocks > cap) blocks = cap;
   loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, y_true, sample_weight, prob, dz, loss_sum, rows,
                                                         cols, task);
+  DTB_LAUNCH_OK();
+  return DTB_OK;
+}
+
+int dtb_focal_loss_fwd_bwd(const float* z, const float* y_true, float* prob, float* dz, double* loss_sum, int rows, int cols,
+                           int task, float gamma, float alpha, void* stream) {
+  DTB_CHECK_ARG(z && y_true && prob, "NULL argument");
+  DTB_CHECK_ARG(rows >= 0 && cols >= 1, "bad shape");
+  DTB_CHECK_ARG(task == 0 || task == 2, "focal loss: task 0 (binary / multilabel) or 2 (multiclass)");
+  DTB_CHECK_ARG(gamma >= 0.f && alpha >= 0.f && alpha <= 1.f, "focal loss: gamma >= 0, 0 <= alpha <= 1");
+  if (rows == 0) return DTB_OK;
+  int blocks = ceil_div(rows, 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  focal_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(z, y_true, prob, dz, loss_sum, rows, cols, task, gamma, alpha);
   DTB_LAUNCH_OK();
   return DTB_OK;
 }

@@ -254,6 +254,7 @@ class DeepModel:
         self._scope = None
         self.table = None
         self._loss_acc = None
+        self._focal = None                  # (gamma, alpha) when ModelConfig.loss is one of the focal losses
         self._alpha = None
         self._step_dev = None              # optimiser step counter in device memory (CUDA-graph replay of the train step)
         self._graphs = {}
@@ -266,8 +267,19 @@ class DeepModel:
     # ------------------------------------------------------------------------------------------
     def _build_model(self):
         cfg = self.config
-        if cfg.optimizer != 'auto' or cfg.loss != 'auto':
-            raise NotImplementedError("only optimizer='auto' (Adam 1e-3) and loss='auto' are built natively")
+        if cfg.optimizer != 'auto':
+            raise NotImplementedError("only optimizer='auto' (Adam 1e-3) is built natively")
+        self._focal = None
+        if isinstance(cfg.loss, L.CategoricalFocalLoss):
+            if self.task != consts.TASK_MULTICLASS:
+                raise ValueError('CategoricalFocalLoss needs a multiclass task')
+            self._focal = (cfg.loss.gamma, cfg.loss.alpha)
+        elif isinstance(cfg.loss, L.BinaryFocalLoss):
+            if self.task not in (consts.TASK_BINARY, consts.TASK_MULTILABEL):
+                raise ValueError('BinaryFocalLoss needs a binary or multilabel task')
+            self._focal = (cfg.loss.gamma, cfg.loss.alpha)
+        elif cfg.loss != 'auto':
+            raise NotImplementedError("loss must be 'auto' or one of layers.BinaryFocalLoss / CategoricalFocalLoss")
         if cfg.embeddings_regularizer is not None or cfg.embeddings_activity_regularizer is not None:
             raise NotImplementedError('embedding regularizers are outside the hot path')
         if self.task not in consts.ALL_TASKS:
@@ -290,6 +302,8 @@ class DeepModel:
         self.model_desc.loss = {consts.TASK_BINARY: 'binary_crossentropy', consts.TASK_MULTILABEL:
                                 'binary_crossentropy', consts.TASK_REGRESSION: 'mse'}.get(
             self.task, 'binary_crossentropy' if self.num_classes == 2 else 'categorical_crossentropy')
+        if self._focal is not None:
+            self.model_desc.loss = 'focal_loss'
         # dry run on two rows materialises every weight (define-by-run build)
         cat = torch.zeros(2, self.n_fields, dtype=torch.int32, device=self.device) if self.n_fields else None
         cont = torch.zeros(2, self.n_cont, dtype=torch.float32, device=self.device) if self.n_cont else None
@@ -460,7 +474,7 @@ class DeepModel:
             t.on_grad_final = (lambda: self._begin_table_exchange(cat)) if (self._dist and t.lazy_adam) else None
         self._early_exchange = None
         z = self._forward(cat, cont, training=True)
-        prob, dz = E.loss_forward_backward(z, y, self.task, sample_weight, True, self._loss_acc)
+        prob, dz = E.loss_forward_backward(z, y, self.task, sample_weight, True, self._loss_acc, focal=self._focal)
         dp.scale_for_mean(dz)
         z.backward(dz)
         step = self._step + 1
@@ -825,7 +839,7 @@ class DeepModel:
                 self._catch_up(bc, self._step)
             with torch.no_grad():
                 z = self._forward(bc, bx, training=False)
-                p, _ = E.loss_forward_backward(z, by, self.task, None, False, loss_acc)
+                p, _ = E.loss_forward_backward(z, by, self.task, None, False, loss_acc, focal=self._focal)
             probs.append(p)
             targets.append(by)
             seen += by.shape[0]

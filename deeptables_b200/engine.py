@@ -704,14 +704,21 @@ class AttentionCoreFn(torch.autograd.Function):
 TASK_CODES = {'binary': 0, 'multilabel': 0, 'regression': 1, 'multiclass': 2}
 
 
-def loss_forward_backward(z, y_true, task, sample_weight=None, want_grad=True, loss_acc=None):
+def loss_forward_backward(z, y_true, task, sample_weight=None, want_grad=True, loss_acc=None, focal=None):
     """task_output activation + loss + dLoss/dz in one launch (deepmodel.py:319-346, 436-457).
-    Returns (prob, dz or None); adds the sum of per-row losses to ``loss_acc`` (float64[1])."""
+    Returns (prob, dz or None); adds the sum of per-row losses to ``loss_acc`` (float64[1]).
+    ``focal`` = (gamma, alpha): the reference's Binary / CategoricalFocalLoss (layers.py:983-1083) instead of BCE / CCE."""
     z = _f32(z)
     y_true = _f32(y_true).view(z.shape)
     prob = torch.empty_like(z)
     dz = torch.empty_like(z) if want_grad else None
     rows, cols = z.shape
+    if focal is not None:
+        if sample_weight is not None:
+            raise NotImplementedError('focal losses take no sample weights')
+        check(N.lib.dtb_focal_loss_fwd_bwd(ptr(z), ptr(y_true), ptr(prob), ptr(dz), ptr(loss_acc), rows, cols, TASK_CODES[task],
+                                           float(focal[0]), float(focal[1]), stream_ptr()), 'focal_loss_fwd_bwd')
+        return prob, dz
     check(N.lib.dtb_loss_fwd_bwd(ptr(z), ptr(y_true), ptr(sample_weight), ptr(prob), ptr(dz), ptr(loss_acc), rows,
                                  cols, TASK_CODES[task], stream_ptr()), 'loss_fwd_bwd')
     return prob, dz

@@ -530,10 +530,30 @@ class BilinearInteraction(Layer):
 
 VarLenColumnEmbedding = _out_of_scope('VarLenColumnEmbedding')
 
+
+class BinaryFocalLoss:
+    """``ModelConfig(loss=BinaryFocalLoss(gamma, alpha))`` for binary / multilabel tasks (reference layers.py:983-1022):
+    FL = -alpha (1 - p_t)^gamma log p_t on the sigmoid probabilities, averaged over every element."""
+
+    def __init__(self, gamma=2., alpha=.25, reduction=None, name='focal_loss'):
+        self.gamma, self.alpha, self.name = float(gamma), float(alpha), name
+
+    def get_config(self):
+        return {'gamma': self.gamma, 'alpha': self.alpha, 'name': self.name}
+
+
+class CategoricalFocalLoss(BinaryFocalLoss):
+    """Softmax form for multiclass tasks (reference layers.py:1025-1083): sum_c alpha (1 - p_c)^gamma (-y_c log p_c)."""
+
+
+def GHMCLoss(*a, **k):
+    raise NotImplementedError('GHMCLoss (a TF1-style stateful helper, layers.py:1086-1163) is not implemented')
+
 dt_custom_objects = {
     'FM': FM, 'CIN': CIN, 'Cross': Cross, 'MultiheadAttention': MultiheadAttention,
     'InnerProduct': InnerProduct, 'OuterProduct': OuterProduct, 'AFM': AFM, 'SENET': SENET,
-    'BilinearInteraction': BilinearInteraction, 'FGCNN': FGCNN,
+    'BilinearInteraction': BilinearInteraction, 'FGCNN': FGCNN, 'BinaryFocalLoss': BinaryFocalLoss,
+    'CategoricalFocalLoss': CategoricalFocalLoss,
 }
 
 

@@ -130,6 +130,13 @@ int dtb_dropout(const float* X, float* Y, int64_t n, float rate, unsigned long l
 int dtb_loss_fwd_bwd(const float* z, const float* y_true, const float* sample_weight, float* prob,
                      float* dz, double* loss_sum, int rows, int cols, int task, void* stream);
 
+/* Focal losses (layers.py:983-1083) passed as ModelConfig.loss: task 0 BinaryFocalLoss (sigmoid; the
+ * loss is the mean over all rows x cols elements), task 2 CategoricalFocalLoss (softmax; mean over
+ * rows of the per-sample sums).  Same outputs as dtb_loss_fwd_bwd; no sample weights. */
+int dtb_focal_loss_fwd_bwd(const float* z, const float* y_true, float* prob, float* dz,
+                           double* loss_sum, int rows, int cols, int task, float gamma, float alpha,
+                           void* stream);
+
 /* ---- keras Adam (deepmodel.py:321-322), dense semantics ---------------------------------- */
 /* m += (g-m)(1-b1); v += (g^2-v)(1-b2); p -= m*alpha/(sqrt(v)+eps), alpha computed by caller
  * as lr*sqrt(1-b2^t)/(1-b1^t).  If zero_grad != 0, g is zeroed after use. */

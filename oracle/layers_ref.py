@@ -436,6 +436,23 @@ def categorical_crossentropy(y_true, y_pred, eps=BCE_EPS):
     return (-(y_true * torch.log(p)).sum(dim=-1)).mean()
 
 
+def binary_focal_loss(y_true, y_pred, gamma=2.0, alpha=0.25, eps=BCE_EPS):
+    """BinaryFocalLoss.call (layers.py:1006-1017) on probabilities: a SCALAR, both terms averaged over every element.
+    pt_1 = p where y == 1 else 1; pt_0 = p where y == 0 else 0; both clipped to [eps, 1 - eps]."""
+    pt_1 = torch.where(y_true == 1, y_pred, torch.ones_like(y_pred)).clamp(eps, 1.0 - eps)
+    pt_0 = torch.where(y_true == 0, y_pred, torch.zeros_like(y_pred)).clamp(eps, 1.0 - eps)
+    return -(alpha * torch.pow(1.0 - pt_1, gamma) * torch.log(pt_1)).mean() \
+        - ((1.0 - alpha) * torch.pow(pt_0, gamma) * torch.log(1.0 - pt_0)).mean()
+
+
+def categorical_focal_loss(y_true, y_pred, gamma=2.0, alpha=0.25, eps=BCE_EPS):
+    """CategoricalFocalLoss.call (layers.py:1061-1077) on probabilities: per-sample losses (B,) -- renormalise, clip,
+    alpha (1 - p)^gamma (-y log p) summed over the classes.  Keras then averages over the batch."""
+    p = y_pred / y_pred.sum(dim=-1, keepdim=True)
+    p = torch.clamp(p, eps, 1.0 - eps)
+    return (alpha * torch.pow(1.0 - p, gamma) * (-y_true * torch.log(p))).sum(dim=1)
+
+
 def adam_step(p, g, m, v, step, lr=ADAM_LR, b1=ADAM_B1, b2=ADAM_B2, eps=ADAM_EPS):
     """keras.optimizers.Adam.update_step (dense semantics; deepmodel.py:321-322).
     step is 1-based.  Updates p, m, v in place (all same shape)."""

@@ -511,7 +511,14 @@ def forward(state, config, cat_idx, cont, n_fields, training, task='binary', ret
     return y, new_bn
 
 
-def loss_fn(task, y_true, y_pred):
+def loss_fn(task, y_true, y_pred, loss='auto'):
+    """ModelConfig.loss: 'auto' (deepmodel.py:327-336) or one of the reference's focal-loss objects (recognised by class
+    name and their gamma / alpha attributes, so that this file imports nothing of the product)."""
+    kind = type(loss).__name__
+    if kind == 'BinaryFocalLoss':
+        return L.binary_focal_loss(y_true, y_pred, loss.gamma, loss.alpha)
+    if kind == 'CategoricalFocalLoss':
+        return L.categorical_focal_loss(y_true, y_pred, loss.gamma, loss.alpha).mean()
     if task in ('binary', 'multilabel'):
         return L.binary_crossentropy(y_true, y_pred)
     if task == 'regression':
@@ -537,7 +544,7 @@ class RefTrainer:
     def loss_and_grads(self, cat_idx, cont, y):
         params = {k: v.detach().clone().requires_grad_(is_trainable(k)) for k, v in self.state.items()}
         out, new_bn = forward(params, self.config, cat_idx, cont, self.n_fields, True, self.task)
-        loss = loss_fn(self.task, y.to(out.dtype).reshape(out.shape[0], -1), out)
+        loss = loss_fn(self.task, y.to(out.dtype).reshape(out.shape[0], -1), out, _get(self.config, 'loss', 'auto'))
         names = [k for k in params if is_trainable(k)]
         grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
         gd = {k: (g if g is not None else torch.zeros_like(params[k])) for k, g in zip(names, grads)}

@@ -313,6 +313,18 @@ def make_f3_cases(layers, deepmodel, config_mod, metainfo, counter, rec):
         rec.add(case, 'fgcnn', p_, x=np64(xin), out=np64(nf), pooled=np64(po),
                 conv_kernel=np64(lyr.conv2d.weights_by_name['kernel']), conv_bias=np64(lyr.conv2d.weights_by_name['bias']),
                 dense_kernel=np64(lyr.dense_output.weights_by_name['kernel']), dense_bias=np64(lyr.dense_output.weights_by_name['bias']))
+    # focal losses (layers.py:983-1083) on probabilities: binary (scalar) and categorical (per sample)
+    g = np.random.default_rng(97)
+    for case, cols, gamma, alpha in (('focal_binary', 1, 2.0, 0.25), ('focal_multilabel', 3, 1.5, 0.6)):
+        p_ = torch.tensor(g.random((8, cols)))
+        p_[0, 0], p_[1, 0] = 1e-9, 1.0 - 1e-9                    # inside the clipped range's edges
+        y_ = torch.tensor((g.random((8, cols)) < 0.4).astype(np.float64))
+        rec.add(case, 'focal_binary', {'gamma': gamma, 'alpha': alpha}, y_true=np64(y_), y_pred=np64(p_),
+                out=np64(layers.BinaryFocalLoss(gamma=gamma, alpha=alpha).call(y_, p_.clone())))
+    p_ = torch.softmax(torch.tensor(g.normal(size=(6, 4)) * 2), dim=-1)
+    y_ = torch.nn.functional.one_hot(torch.tensor(g.integers(0, 4, size=6)), 4).double()
+    rec.add('focal_categorical', 'focal_categorical', {'gamma': 2.0, 'alpha': 0.25}, y_true=np64(y_), y_pred=np64(p_),
+            out=np64(layers.CategoricalFocalLoss(gamma=2.0, alpha=0.25).call(y_, p_.clone())))
     # whole models with afm_nets / fibi_nets / fibi_dnn_nets / fgcnn_* through DeepModel.__build_model
     for ci, (case, cfg_kwargs, vocab, dim, n_cont, task, num_classes) in enumerate(F3_MODEL_CASES):
         conf = config_mod.ModelConfig(embedding_dropout=0, dense_dropout=0, embeddings_output_dim=dim, **cfg_kwargs)

@@ -117,6 +117,10 @@ def _make_tf():
     tf.expand_dims = lambda input, axis, name=None: _as_tensor(input).unsqueeze(axis)
     tf.multiply = lambda x, y, name=None: _as_tensor(x) * _as_tensor(y)
     tf.tensordot = tf_tensordot
+    tf.where = lambda cond, x, y, name=None: torch.where(cond, _as_tensor(x), _as_tensor(y))
+    tf.equal = lambda x, y, name=None: _as_tensor(x) == y
+    tf.ones_like = lambda x, name=None: torch.ones_like(_as_tensor(x))
+    tf.zeros_like = lambda x, name=None: torch.zeros_like(_as_tensor(x))
     nn = types.ModuleType('tensorflow.nn')
     nn.softmax = lambda logits, axis=-1, name=None: torch.softmax(_as_tensor(logits), dim=axis)
     nn.relu = lambda features, name=None: torch.relu(_as_tensor(features))
@@ -330,6 +334,16 @@ class MaxPooling2D(Layer):
         return torch.nn.functional.max_pool2d(xc, (ph, pw), (sh, sw)).permute(0, 2, 3, 1)
 
 
+class _LossBase:
+    """keras.losses.Loss: the reference's focal losses only use the constructor and call()."""
+
+    def __init__(self, reduction=None, name=None, **kwargs):
+        self.reduction, self.name = reduction, name
+
+    def get_config(self):
+        return {'name': self.name}
+
+
 class _Unused(Layer):
     def __init__(self, *a, **k):
         raise NotImplementedError(f'{type(self).__name__} is not on the hot path; the shim does not restate it')
@@ -412,19 +426,23 @@ def install(reference_root='/root/reference'):
     _module('keras.src')
     _module('keras.src.legacy')
     _module('keras.src.legacy.losses', Reduction=_Anything())
-    keras.backend = _module('keras.backend', floatx=lambda: 'float32')
+    keras.backend = _module('keras.backend', floatx=lambda: 'float32', epsilon=lambda: 1e-7)
     ops = _module('keras.ops')
     ops.ndim = lambda x: _as_tensor(x).dim()
     ops.sum = lambda x, axis=None, keepdims=False: tf_reduce_sum(x, axis, keepdims)
     ops.cast = lambda x, dtype: _as_tensor(x).to(torch.int64 if 'int' in str(dtype) else DTYPE)
     ops.not_equal = lambda a, b: _as_tensor(a) != b
     ops.expand_dims = lambda x, axis: _as_tensor(x).unsqueeze(axis)
+    ops.clip = lambda x, lo, hi: torch.clamp(_as_tensor(x), lo, hi)
+    ops.mean = lambda x, axis=None, keepdims=False: _as_tensor(x).mean() if axis is None else _as_tensor(x).mean(dim=_axes(axis), keepdim=keepdims)
+    ops.power = lambda x, y: torch.pow(_as_tensor(x), y)
+    ops.log = lambda x: torch.log(_as_tensor(x))
     ops.split = lambda x, indices_or_sections, axis=0: tf_split(x, indices_or_sections, axis)
     keras.ops = ops
     getter = types.SimpleNamespace(get=lambda ident: ident, serialize=lambda obj: obj)
     for sub in ('initializers', 'regularizers', 'constraints'):
         setattr(keras, sub, _module(f'keras.{sub}', get=getter.get, serialize=getter.serialize))
-    keras.losses = _module('keras.losses', Loss=object, BinaryCrossentropy=_Anything, MeanSquaredError=_Anything,
+    keras.losses = _module('keras.losses', Loss=_LossBase, BinaryCrossentropy=_Anything, MeanSquaredError=_Anything,
                            CategoricalCrossentropy=_Anything)
     keras.optimizers = _module('keras.optimizers', Adam=_Anything)
 

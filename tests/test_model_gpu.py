@@ -66,6 +66,12 @@ def test_fgcnn_small_kernels_and_uneven_pooling():
                                                                          'fg_pool_heights': (2, 3), 'fg_new_feat_filters': (2, 1)})
 
 
+@pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='focal loss: set DTB_TEST_FGCNN=1')
+def test_binary_focal_loss_training_matches_oracle():
+    from deeptables_b200 import layers
+    _forward_and_training_match_oracle(['linear', 'dnn_nets'], loss=layers.BinaryFocalLoss(gamma=2.0, alpha=0.25))
+
+
 def test_afm_hidden_factor_and_linear_attention():
     _forward_and_training_match_oracle(['afm_nets', 'dnn_nets'], afm_params={'hidden_factor': 5, 'activation': 'linear', 'dropout_rate': 0})
 

@@ -790,6 +790,39 @@ def test_bilinear_fwd_bwd(nat, f, d, b, bt):
     np.testing.assert_allclose(dw.cpu().numpy(), gw.numpy(), rtol=1e-3, atol=1e-4 * float(gw.abs().max()))
 
 
+@pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='focal-loss kernel: set DTB_TEST_FGCNN=1 (not yet run on a B200)')
+@pytest.mark.parametrize('task,cols,gamma,alpha', [(0, 1, 2.0, 0.25), (0, 3, 1.5, 0.6), (0, 1, 0.0, 0.5), (2, 4, 2.0, 0.25), (2, 3, 0.5, 1.0)])
+def test_focal_loss_fwd_bwd(nat, task, cols, gamma, alpha):
+    """Binary / categorical focal loss (layers.py:983-1083) on the task_output pre-activation against the oracle's autograd."""
+    g = np.random.default_rng(91)
+    rows = 257
+    z = (g.normal(size=(rows, cols)) * 3).astype(np.float32)
+    z[0, 0], z[1, 0] = 30.0, -30.0                                  # saturated probabilities: the clip turns the gradient off
+    if task == 0:
+        y = (g.random((rows, cols)) < 0.4).astype(np.float32)
+    else:
+        y = np.eye(cols, dtype=np.float32)[g.integers(0, cols, size=rows)]
+    prob, dz = torch.empty(rows, cols, device='cuda'), torch.empty(rows, cols, device='cuda')
+    acc = torch.zeros(1, dtype=torch.float64, device='cuda')
+    nat.check(nat.lib.dtb_focal_loss_fwd_bwd(P(dev(z)), P(dev(y)), P(prob), P(dz), P(acc), rows, cols, task, gamma, alpha, None))
+    z64 = torch.tensor(z, dtype=torch.float64, requires_grad=True)
+    y64 = torch.tensor(y, dtype=torch.float64)
+    if task == 0:
+        p64 = torch.sigmoid(z64)
+        loss = L.binary_focal_loss(y64, p64, gamma, alpha)
+    else:
+        p64 = torch.softmax(z64, dim=-1)
+        loss = L.categorical_focal_loss(y64, p64, gamma, alpha).mean()
+    (gz,) = torch.autograd.grad(loss, [z64])
+    np.testing.assert_allclose(prob.cpu().numpy(), p64.detach().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(float(acc.item()) / rows, float(loss), rtol=2e-5)
+    # fp32 probabilities saturate (1 - p = 0 or p clipped) where float64 does not: compare where the fp32 probability is interior
+    interior = (prob.cpu().numpy() > 1e-6) & (prob.cpu().numpy() < 1 - 1e-6)
+    if task == 2:
+        interior = np.repeat(interior.all(axis=1, keepdims=True), cols, axis=1)
+    np.testing.assert_allclose(dz.cpu().numpy()[interior], gz.numpy()[interior], rtol=2e-3, atol=1e-6 / rows)
+
+
 FGCNN_GATE = pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='FGCNN kernels: set DTB_TEST_FGCNN=1 (not yet run on a B200)')
 
 

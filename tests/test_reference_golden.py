@@ -108,6 +108,10 @@ def test_oracle_f3_layer_reproduces_reference_layer(meta):
         w = _weights(z, case)
         got = L.senet(_t(z[f'{case}/x']), w['dense_att1/kernel'], w['dense_att1/bias'], w['dense_att2/kernel'],
                       w['dense_att2/bias'], p['pooling_op'])
+    elif kind == 'focal_binary':
+        got = L.binary_focal_loss(_t(z[f'{case}/y_true']), _t(z[f'{case}/y_pred']), p['gamma'], p['alpha'])
+    elif kind == 'focal_categorical':
+        got = L.categorical_focal_loss(_t(z[f'{case}/y_true']), _t(z[f'{case}/y_pred']), p['gamma'], p['alpha'])
     elif kind == 'fgcnn':
         pooled, got = L.fgcnn(_t(z[f'{case}/x']), _t(z[f'{case}/conv_kernel']), _t(z[f'{case}/conv_bias']),
                               _t(z[f'{case}/dense_kernel']), _t(z[f'{case}/dense_bias']), p['pool_height'], p['new_filters'])
