@@ -54,5 +54,31 @@ def main():
             del out, go
 
 
+def fgcnn():
+    """The two FGCNN layers of the reference's defaults (14 / 16 filters, height 7, pool 2) at F = 26, D = 16."""
+    for b in [int(r) for r in os.environ.get('ROWS', '16384,65536').split(',')]:
+        h, w, cin = 26, 16, 1
+        x = torch.randn(b, h, w, cin, device='cuda')
+        for filters, kh, pool in ((14, 7, 2), (16, 7, 2)):
+            k = torch.randn(kh, 1, cin, filters, device='cuda') / (kh * cin) ** 0.5
+            bias = torch.zeros(filters, device='cuda')
+            y = torch.empty(b, h, w, filters, device='cuda')
+            ho = -(-h // pool)
+            pooled = torch.empty(b, ho, w, filters, device='cuda')
+            gy, gp = torch.randn_like(y), torch.randn_like(pooled)
+            dx, dk, db, dy = torch.empty_like(x), torch.zeros_like(k), torch.zeros_like(bias), torch.empty_like(y)
+            cf = lambda: N.check(N.lib.dtb_conv_fields_fwd(P(x), P(k), P(bias), P(y), b, h, w, cin, filters, kh, 2, None), 'cf')
+            cb = lambda: N.check(N.lib.dtb_conv_fields_bwd(P(x), P(k), P(y), P(gy), P(dx), P(dk), P(db), b, h, w, cin, filters, kh, 2,
+                                                           None), 'cb')
+            pf = lambda: N.check(N.lib.dtb_maxpool_fields_fwd(P(y), P(pooled), b, h, w * filters, pool, None), 'pf')
+            pb = lambda: N.check(N.lib.dtb_maxpool_fields_bwd(P(y), P(gp), P(dy), b, h, w * filters, pool, None), 'pb')
+            print(f'fgcnn conv rows {b} [{h} x {w} x {cin}] -> {filters} filters, height {kh}: fwd {timeit(cf):.3f} ms   '
+                  f'bwd {timeit(cb):.3f} ms   pool fwd {timeit(pf):.3f} ms   bwd {timeit(pb):.3f} ms', flush=True)
+            x, h, cin = pooled.clone(), ho, filters
+            del y, gy, dy
+
+
 if __name__ == '__main__':
-    main()
+    if os.environ.get('ONLY', '') != 'fgcnn':
+        main()
+    fgcnn()
