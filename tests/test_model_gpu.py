@@ -42,10 +42,8 @@ def batch(vocab, n_cont, b, seed=0):
 NET_SETS = [['linear'], ['fm_nets'], ['dnn_nets'], ['cin_nets'], ['cross_nets'], ['dcn_nets'], ['cross_dnn_nets'],
             ['linear', 'fm_nets', 'dnn_nets'], ['linear', 'cin_nets', 'dnn_nets'], ['autoint_nets'], ['pnn_nets'],
             ['ipnn_nets'], ['opnn_nets'], ['fm_nets', 'cin_nets', 'cross_nets', 'autoint_nets', 'pnn_nets'],
-            ['afm_nets'], ['linear', 'afm_nets', 'dnn_nets'], ['fibi_dnn_nets'], ['fm_nets', 'fibi_nets']
-            ] + [pytest.param(n, marks=pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='FGCNN: set DTB_TEST_FGCNN=1'))
-                 for n in (['fgcnn_dnn_nets'], ['linear', 'fgcnn_fm_nets'], ['fgcnn_cin_nets'], ['fgcnn_afm_nets'], ['fgcnn_ipnn_nets'],
-                           ['fg_nets'])]
+            ['afm_nets'], ['linear', 'afm_nets', 'dnn_nets'], ['fibi_dnn_nets'], ['fm_nets', 'fibi_nets'],
+            ['fgcnn_dnn_nets'], ['linear', 'fgcnn_fm_nets'], ['fgcnn_cin_nets'], ['fgcnn_afm_nets'], ['fgcnn_ipnn_nets'], ['fg_nets']]
 
 
 @pytest.mark.parametrize('nets', NET_SETS)
@@ -60,13 +58,11 @@ def test_fibinet_pooling_and_weight_sharing_variants(fibinet_params):
     _forward_and_training_match_oracle(['fibi_dnn_nets'], fibinet_params=fibinet_params)
 
 
-@pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='FGCNN: set DTB_TEST_FGCNN=1')
 def test_fgcnn_small_kernels_and_uneven_pooling():
     _forward_and_training_match_oracle(['fgcnn_dnn_nets'], fgcnn_params={'fg_filters': (3, 4), 'fg_heights': (3, 2),
                                                                          'fg_pool_heights': (2, 3), 'fg_new_feat_filters': (2, 1)})
 
 
-@pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='focal loss: set DTB_TEST_FGCNN=1')
 def test_binary_focal_loss_training_matches_oracle():
     from deeptables_b200 import layers
     _forward_and_training_match_oracle(['linear', 'dnn_nets'], loss=layers.BinaryFocalLoss(gamma=2.0, alpha=0.25))

@@ -790,7 +790,6 @@ def test_bilinear_fwd_bwd(nat, f, d, b, bt):
     np.testing.assert_allclose(dw.cpu().numpy(), gw.numpy(), rtol=1e-3, atol=1e-4 * float(gw.abs().max()))
 
 
-@pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='focal-loss kernel: set DTB_TEST_FGCNN=1 (not yet run on a B200)')
 @pytest.mark.parametrize('task,cols,gamma,alpha', [(0, 1, 2.0, 0.25), (0, 3, 1.5, 0.6), (0, 1, 0.0, 0.5), (2, 4, 2.0, 0.25), (2, 3, 0.5, 1.0)])
 def test_focal_loss_fwd_bwd(nat, task, cols, gamma, alpha):
     """Binary / categorical focal loss (layers.py:983-1083) on the task_output pre-activation against the oracle's autograd."""
@@ -823,10 +822,6 @@ def test_focal_loss_fwd_bwd(nat, task, cols, gamma, alpha):
     np.testing.assert_allclose(dz.cpu().numpy()[interior], gz.numpy()[interior], rtol=2e-3, atol=1e-6 / rows)
 
 
-FGCNN_GATE = pytest.mark.skipif(os.environ.get('DTB_TEST_FGCNN') != '1', reason='FGCNN kernels: set DTB_TEST_FGCNN=1 (not yet run on a B200)')
-
-
-@FGCNN_GATE
 @pytest.mark.parametrize('b,h,w,cin,cout,kh,pool,act', [(9, 26, 16, 1, 14, 7, 2, 'tanh'), (5, 13, 16, 14, 16, 7, 2, 'tanh'),
                                                         (7, 7, 4, 3, 4, 4, 3, 'relu'), (33, 5, 8, 32, 32, 8, 5, 'linear'),
                                                         (300, 3, 4, 2, 5, 1, 1, 'tanh')])
@@ -862,7 +857,6 @@ def test_fgcnn_conv_and_pool_fwd_bwd(nat, b, h, w, cin, cout, kh, pool, act):
         np.testing.assert_allclose(got.cpu().numpy(), ref.numpy(), rtol=2e-3, atol=2e-4 * float(ref.abs().max()), err_msg=name)
 
 
-@FGCNN_GATE
 def test_dense_tanh_activation(nat):
     """DTB_ACT_TANH in the Dense epilogues (wide: tcgen05 path, narrow: row-dot path) and its backward."""
     g = np.random.default_rng(82)

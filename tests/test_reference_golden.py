@@ -141,7 +141,6 @@ def _model_config(p):
 
 
 ALL_MODEL_CASES = [(MODELS_Z, m) for m in MODEL_CASES] + [(F3_Z, m) for m in F3_MODEL_CASES]
-FGCNN_ON_GPU = os.environ.get('DTB_TEST_FGCNN') == '1'          # the FGCNN kernels have not yet run on a B200
 
 
 @pytest.mark.parametrize('zm', ALL_MODEL_CASES, ids=[m['case'] for _, m in ALL_MODEL_CASES])
@@ -198,8 +197,6 @@ def test_cuda_model_reproduces_reference_build_model(zm):
     from deeptables_b200.metainfo import CategoricalColumn, ContinuousColumn
     z, meta = zm
     case, p = meta['case'], meta['params']
-    if any(n.startswith('fg') for n in p['config']['nets']) and not FGCNN_ON_GPU:
-        pytest.skip('FGCNN: set DTB_TEST_FGCNN=1')
     conf = _model_config(p)
     cats = [CategoricalColumn(f'c{i}', v, p['dim']) for i, v in enumerate(p['vocab'])]
     conts = [ContinuousColumn('input_continuous_all', [f'n{i}' for i in range(p['n_cont'])])] if p['n_cont'] else []
