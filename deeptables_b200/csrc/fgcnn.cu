@@ -7,6 +7,7 @@
 // with the filter in shared memory (read as 128-bit warp broadcasts) -- 43 GFLOP per 65 536-row step at the reference's
 // defaults (14 / 16 filters, height 7) against 1.5 GB of activations, i.e. bandwidth and issue bound, not a tensor-core shape.
 #include "dtb_common.cuh"
+#include <cstdlib>
 
 namespace dtb {
 
@@ -172,6 +173,79 @@ __global__ void __launch_bounds__(kFgThreads) conv_fields_bwd_dw_kernel(const fl
   }
 }
 
+// The same gradient with the positions in parallel: a CTA takes tiles of kFgTile consecutive positions, stages their taps
+// xs[p][a] (a = t Cin + ci, zero outside the block) and dzs[p][co] in shared memory, and every thread accumulates its
+// (a, co) entries -- dK is exactly the [A x Cout] matrix xs^T dzs in memory order -- over the tile; accumulators live in
+// registers across the CTA's tiles, one atomic per entry per CTA at the end.  (The first version above walks the positions
+// serially with one (ci, co) entry per thread: 106 ms per launch at 65 536 rows, 14 live threads per CTA in layer 1.)
+constexpr int kFgTile = 128;
+constexpr int kFgMaxEntries = 32;        // (kh Cin Cout) / 256 threads, kh <= 8, Cin, Cout <= 32
+
+__global__ void __launch_bounds__(kFgThreads) conv_fields_bwd_dw_tiled_kernel(const float* __restrict__ X, const float* __restrict__ Y,
+                                                                              const float* __restrict__ dY, float* __restrict__ dK,
+                                                                              float* __restrict__ dbias, int64_t n_pos, int H, int W,
+                                                                              int Cin, int Cout, int kh, int act, int64_t n_tiles) {
+  extern __shared__ __align__(16) float sm[];
+  const int A = kh * Cin;
+  float* xs = sm;                        // [kFgTile][A]
+  float* dzs = sm + (size_t)kFgTile * A; // [kFgTile][Cout]
+  const int n_out = A * Cout;
+  const int pad = fg_pad_before(H, kh, 1);
+  float acc[kFgMaxEntries];
+#pragma unroll
+  for (int k = 0; k < kFgMaxEntries; ++k) acc[k] = 0.f;
+  float accb = 0.f;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * kFgTile;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFgTile * A; i += kFgThreads) {
+      const int p = i / A, a = i - p * A;
+      const int64_t pos = p0 + p;
+      float v = 0.f;
+      if (pos < n_pos) {
+        const int w = (int)(pos % W);
+        const int64_t bh = pos / W;
+        const int h = (int)(bh % H);
+        const int t = a / Cin, ci = a - t * Cin;
+        const int hh = h + t - pad;
+        if (hh >= 0 && hh < H) v = __ldg(X + ((bh - h + hh) * W + w) * Cin + ci);
+      }
+      xs[i] = v;
+    }
+    for (int i = threadIdx.x; i < kFgTile * Cout; i += kFgThreads) {
+      const int64_t pos = p0 + i / Cout;
+      float v = 0.f;
+      if (pos < n_pos) {
+        const int64_t o = p0 * Cout + i;
+        v = __ldg(dY + o) * fg_act_grad(__ldg(Y + o), act);
+      }
+      dzs[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kFgMaxEntries; ++k) {
+      const int e = threadIdx.x + k * kFgThreads;
+      if (e < n_out) {
+        const int a = e / Cout, co = e - a * Cout;
+        float s = 0.f;
+        for (int p = 0; p < kFgTile; ++p) s = fmaf(xs[p * A + a], dzs[p * Cout + co], s);
+        acc[k] += s;
+      }
+    }
+    if (threadIdx.x < Cout) {
+      float s = 0.f;
+      for (int p = 0; p < kFgTile; ++p) s += dzs[p * Cout + threadIdx.x];
+      accb += s;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kFgMaxEntries; ++k) {
+    const int e = threadIdx.x + k * kFgThreads;
+    if (e < n_out && acc[k] != 0.f) atomicAdd(dK + e, acc[k]);
+  }
+  if (threadIdx.x < Cout && dbias && accb != 0.f) atomicAdd(dbias + threadIdx.x, accb);
+}
+
 // MaxPooling2D((pool, 1), strides = pool, 'same'): Y[b,ho,w,c] = max over the window's in-range rows; thread = output element
 __global__ void maxpool_fields_fwd_kernel(const float* __restrict__ X, float* __restrict__ Y, int64_t n_out, int H, int Ho,
                                           int WC, int pool) {
@@ -287,11 +361,24 @@ int dtb_conv_fields_bwd(const float* X, const float* kernel, const float* Y, con
     })
     DTB_LAUNCH_OK();
   }
-  int64_t ctas = (int64_t)sm_count() * 4;
-  if (ctas > n_pos) ctas = n_pos;
-  const int64_t per = (n_pos + ctas - 1) / ctas;
-  ctas = (n_pos + per - 1) / per;
-  conv_fields_bwd_dw_kernel<<<(int)ctas, kFgThreads, 0, st>>>(X, Y, dY, d_kernel, d_bias, n_pos, H, W, Cin, Cout, kh, act, per);
+  // DTB_FGCNN_DW=1 selects the position-tiled filter-gradient kernel (default: the first, serial-per-CTA kernel, until the
+  // tiled one has run against the oracle on a B200)
+  static const int tiled = [] { const char* e = getenv("DTB_FGCNN_DW"); return e ? atoi(e) : 0; }();
+  if (tiled) {
+    const int64_t n_tiles = (n_pos + kFgTile - 1) / kFgTile;
+    const size_t smem = (size_t)kFgTile * (kh * Cin + Cout) * sizeof(float);
+    int64_t ctas = (int64_t)sm_count() * 2;
+    if (ctas > n_tiles) ctas = n_tiles;
+    DTB_CUDA_OK(cudaFuncSetAttribute(conv_fields_bwd_dw_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_fields_bwd_dw_tiled_kernel<<<(int)ctas, kFgThreads, smem, st>>>(X, Y, dY, d_kernel, d_bias, n_pos, H, W, Cin, Cout, kh, act,
+                                                                         n_tiles);
+  } else {
+    int64_t ctas = (int64_t)sm_count() * 4;
+    if (ctas > n_pos) ctas = n_pos;
+    const int64_t per = (n_pos + ctas - 1) / ctas;
+    ctas = (n_pos + per - 1) / per;
+    conv_fields_bwd_dw_kernel<<<(int)ctas, kFgThreads, 0, st>>>(X, Y, dY, d_kernel, d_bias, n_pos, H, W, Cin, Cout, kh, act, per);
+  }
   DTB_LAUNCH_OK();
   return DTB_OK;
 }
