@@ -361,9 +361,8 @@ int dtb_conv_fields_bwd(const float* X, const float* kernel, const float* Y, con
     })
     DTB_LAUNCH_OK();
   }
-  // DTB_FGCNN_DW=1 selects the position-tiled filter-gradient kernel (default: the first, serial-per-CTA kernel, until the
-  // tiled one has run against the oracle on a B200)
-  static const int tiled = [] { const char* e = getenv("DTB_FGCNN_DW"); return e ? atoi(e) : 0; }();
+  // DTB_FGCNN_DW=0 selects the first (serial-per-CTA) filter-gradient kernel
+  static const int tiled = [] { const char* e = getenv("DTB_FGCNN_DW"); return e ? atoi(e) : 1; }();
   if (tiled) {
     const int64_t n_tiles = (n_pos + kFgTile - 1) / kFgTile;
     const size_t smem = (size_t)kFgTile * (kh * Cin + Cout) * sizeof(float);
