@@ -185,3 +185,42 @@ def test_no_undefined_globals_in_gpu_only_code():
              glob.glob(os.path.join(root, 'tools', '*.py')) + [os.path.join(root, 'bench.py'), os.path.join(root, '__graft_entry__.py')])
     problems = [p for f in files for p in lint.check(f)]
     assert not problems, '\n'.join(problems)
+
+
+def test_scope_param_stack_indices_and_f3_host_objects():
+    """Host logic of the round-2 widening that needs no GPU: stacked parameter families (BilinearInteraction's per-pair
+    matrices), per-model layer indices (fibi_nets / fg_nets), the focal-loss objects and the activation codes."""
+    import torch
+    from deeptables_b200 import layers, engine
+    from deeptables_b200.deepmodel import _Scope
+    scope = _Scope(torch.device('cpu'), 3)
+    names = ['l/bilinear_weight0_1', 'l/bilinear_weight0_2', 'l/bilinear_weight1_2']
+    w = scope.param_stack(names, (4, 4), 'glorot_uniform')
+    assert tuple(w.shape) == (3, 4, 4) and scope.param_stack(names, (4, 4), 'glorot_uniform') is w
+    assert scope.stacked == {'l/bilinear_weight0_1[*]': names}
+    assert not torch.equal(w[0], w[1])                       # every slice is drawn on its own, with the fans of a (4, 4) matrix
+    lim = (6.0 / 8) ** 0.5
+    assert float(w.detach().abs().max()) <= lim
+    with pytest.raises(ValueError):
+        scope.param_stack(names, (4, 5), 'glorot_uniform')
+    scope.param('l/bias', (3,), 'zeros')
+    scope.freeze()
+    assert scope.flat_p.numel() == 3 * 16 + 3 and scope.params['l/bilinear_weight0_1[*]'].grad is not None
+    with pytest.raises(RuntimeError):
+        scope.param_stack(['m/w0', 'm/w1'], (2, 2), 'zeros')
+    assert (scope.next_index('senet_layer'), scope.next_index('senet_layer'), scope.next_index('concat_fgcnn_embedding')) == (0, 1, 0)
+    scope._begin_pass()
+    assert scope.next_index('senet_layer') == 0              # indices restart with every forward pass of the model
+    fl = layers.BinaryFocalLoss(gamma=1.5, alpha=0.6)
+    assert (fl.gamma, fl.alpha) == (1.5, 0.6) and fl.get_config()['gamma'] == 1.5
+    assert isinstance(layers.CategoricalFocalLoss(), layers.BinaryFocalLoss)
+    with pytest.raises(NotImplementedError):
+        layers.GHMCLoss()
+    with pytest.raises(NotImplementedError):
+        layers.VarLenColumnEmbedding(3, 4, 'uniform', None, None)
+    assert engine.ACT_CODES == {None: 0, 'linear': 0, 'relu': 1, 'tanh': 2}
+    assert engine.BILINEAR_TYPES == {'field_all': 0, 'field_each': 1, 'field_interaction': 2}
+    g = torch.Generator().manual_seed(0)
+    t = layers.init_tensor((64, 32), 'glorot_normal', 'cpu', g)
+    std = (2.0 / 96) ** 0.5 / 0.87962566103423978
+    assert float(t.abs().max()) <= 2 * std + 1e-6 and abs(float(t.std()) - (2.0 / 96) ** 0.5) < 0.01
