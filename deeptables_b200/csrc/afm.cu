@@ -18,7 +18,7 @@
 
 namespace dtb {
 
-constexpr int kAfmWarps = 4;          // warps (= rows in flight) per CTA of the warp-per-row kernels
+constexpr int kAfmWarps = 4;          // warps (= rows in flight) per CTA of the warp-per-row kernels; fewer when F is large (shared memory)
 constexpr int kAfmRows = 128;         // rows (= threads) per CTA of the (row, field) kernel
 
 // pairs (i < j) in row-major order = itertools.combinations (layers.py:794-796)
@@ -96,8 +96,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // shared memory of the warp-per-row kernels: [Wa DT*HT | ba HT | hv HT | pair table P (i | j << 16) |
 //                                            per warp: es F*(DT+4) | sc P | dw P]
 __host__ __device__ inline int afm_p4(int P) { return (P + 3) & ~3; }        // keeps every region 16-byte aligned
-__host__ __device__ inline size_t afm_row_smem_floats(int F, int P, int DT, int HT) {
-  return (size_t)DT * HT + 2 * HT + afm_p4(P) + (size_t)kAfmWarps * ((size_t)F * (DT + 4) + 2 * (size_t)afm_p4(P));
+__host__ __device__ inline size_t afm_row_smem_floats(int F, int P, int DT, int HT, int n_warps) {
+  return (size_t)DT * HT + 2 * HT + afm_p4(P) + (size_t)n_warps * ((size_t)F * (DT + 4) + 2 * (size_t)afm_p4(P));
 }
 
 // MODE 0: pooled[row, :] = sum_p softmax_p v_p.
@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(kAfmWarps * 32) afm_rows_kernel(const int32_t*
   float dh_acc[HT];
 #pragma unroll
   for (int h = 0; h < HT; ++h) dh_acc[h] = 0.f;
-  for (int row = blockIdx.x * kAfmWarps + warp; row < B; row += gridDim.x * kAfmWarps) {
+  const int n_warps = blockDim.x >> 5;         // kAfmWarps unless the host shrank the CTA to fit the shared memory
+  for (int row = blockIdx.x * n_warps + warp; row < B; row += gridDim.x * n_warps) {
     __syncwarp();
     for (int e = lane; e < F * (DT / 4); e += 32) {
       const int f = e / (DT / 4), c = e - f * (DT / 4);
@@ -419,7 +420,8 @@ __global__ void __launch_bounds__(kAfmWarps * 32) afm_bwd_dw_kernel(const int32_
   float acc[G], accb[G];
 #pragma unroll
   for (int k = 0; k < G; ++k) acc[k] = accb[k] = 0.f;
-  for (int row = blockIdx.x * kAfmWarps + warp; row < B; row += gridDim.x * kAfmWarps) {
+  const int n_warps = blockDim.x >> 5;         // kAfmWarps unless the host shrank the CTA to fit the shared memory
+  for (int row = blockIdx.x * n_warps + warp; row < B; row += gridDim.x * n_warps) {
     __syncwarp();
     for (int e = lane; e < F * (DT / 4); e += 32) {
       const int f = e / (DT / 4), c = e - f * (DT / 4);
@@ -471,6 +473,7 @@ bool afm_shape(int D, int H, const void* table) {
   return (D == 4 || D == 8 || D == 16 || D == 32) && H >= 1 && H <= 32 && (reinterpret_cast<uintptr_t>(table) & 15) == 0;
 }
 int afm_ht(int H) { return H <= 8 ? 8 : (H <= 16 ? 16 : 32); }
+constexpr size_t kAfmSmemMax = 200 * 1024;
 }  // namespace
 
 #define DTB_AFM_DISPATCH(D, HT, ...)                                                  \
@@ -511,17 +514,19 @@ int dtb_afm_fwd(const int32_t* idx, const float* table, const int64_t* row_offse
   }
   if (B == 0) return DTB_OK;
   const int P = F * (F - 1) / 2, HT = afm_ht(H);
-  const size_t smem = afm_row_smem_floats(F, P, D, HT) * sizeof(float);
-  if (smem > 200 * 1024) {
+  int nw = kAfmWarps;                            // many fields (an FGCNN block has ~100): fewer rows in flight per CTA
+  while (nw > 1 && afm_row_smem_floats(F, P, D, HT, nw) * sizeof(float) > kAfmSmemMax) nw /= 2;
+  const size_t smem = afm_row_smem_floats(F, P, D, HT, nw) * sizeof(float);
+  if (smem > kAfmSmemMax) {
     set_error("dtb_afm_fwd: %d fields need %zu bytes of shared memory per CTA", F, smem);
     return DTB_ERR_UNSUPPORTED;
   }
   int grid = sm_count() * 4;
-  if (grid > ceil_div(B, kAfmWarps)) grid = ceil_div(B, kAfmWarps);
+  if (grid > ceil_div(B, nw)) grid = ceil_div(B, nw);
   DTB_AFM_DISPATCH(D, HT, {
     auto kern = afm_rows_kernel<DT_, HT_, 0>;
     DTB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kAfmWarps * 32, smem, (cudaStream_t)stream>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h,
+    kern<<<grid, nw * 32, smem, (cudaStream_t)stream>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h,
                                                                nullptr, pooled, nullptr, nullptr, nullptr, B, F, P, H, act, status);
   })
   DTB_LAUNCH_OK();
@@ -552,14 +557,18 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
   float* da_s = ds_s + (size_t)B * P;
   // the da block must start 16-byte aligned: 2 * B * P floats is a multiple of 4 only when B * P is even
   if ((2 * (size_t)B * P) % 4) da_s += 4 - (2 * (size_t)B * P) % 4;
-  const size_t smem = afm_row_smem_floats(F, P, D, HT) * sizeof(float);
-  const size_t smem_w = ((size_t)afm_p4(P) + (size_t)kAfmWarps * ((size_t)F * (D + 4) + 32 * HT)) * sizeof(float);
-  if (smem > 200 * 1024 || smem_w > 200 * 1024) {
+  int nw = kAfmWarps, nw_w = kAfmWarps;
+  while (nw > 1 && afm_row_smem_floats(F, P, D, HT, nw) * sizeof(float) > kAfmSmemMax) nw /= 2;
+  auto dw_smem = [&](int n) { return ((size_t)afm_p4(P) + (size_t)n * ((size_t)F * (D + 4) + 32 * HT)) * sizeof(float); };
+  while (nw_w > 1 && dw_smem(nw_w) > kAfmSmemMax) nw_w /= 2;
+  const size_t smem = afm_row_smem_floats(F, P, D, HT, nw) * sizeof(float);
+  const size_t smem_w = dw_smem(nw_w);
+  if (smem > kAfmSmemMax || smem_w > kAfmSmemMax) {
     set_error("dtb_afm_bwd: %d fields need %zu bytes of shared memory per CTA", F, smem > smem_w ? smem : smem_w);
     return DTB_ERR_UNSUPPORTED;
   }
   int grid = sm_count() * 4;
-  if (grid > ceil_div(B, kAfmWarps)) grid = ceil_div(B, kAfmWarps);
+  if (grid > ceil_div(B, nw)) grid = ceil_div(B, nw);
   int groups = ceil_div(sm_count() * 6, F);
   if (groups > ceil_div(B, kAfmRows)) groups = ceil_div(B, kAfmRows);
   // DTB_AFM_BWD=1 selects the first backward (every pair recomputed from both of its fields in afm_bwd_de_kernel)
@@ -570,7 +579,7 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
     if (mode == 1) {
       auto k1 = afm_rows_kernel<DT_, HT_, 1>;
       DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k1<<<grid, kAfmWarps * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, w_s,
+      k1<<<grid, nw * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, w_s,
                                              ds_s, nullptr, B, F, P, H, act, nullptr);
       afm_bwd_de_kernel<DT_, HT_><<<dim3(F, groups), kAfmRows, 0, st>>>(idx, table, row_offsets, att_kernel, att_bias,
                                                                         projection_h, d_pooled, w_s, ds_s, da_s, grad_table,
@@ -578,7 +587,7 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
     } else {
       auto k1 = afm_rows_kernel<DT_, HT_, 2>;
       DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k1<<<grid, kAfmWarps * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, da2,
+      k1<<<grid, nw * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, da2,
                                              dv2, d_projection_h, B, F, P, H, act, nullptr);
       int g2 = ceil_div(sm_count() * 8, F);
       if (g2 > ceil_div(B, kAfmRows)) g2 = ceil_div(B, kAfmRows);
@@ -587,8 +596,8 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
     auto k3 = afm_bwd_dw_kernel<DT_, HT_>;
     DTB_CUDA_OK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
     int grid_w = sm_count() * 2;
-    if (grid_w > ceil_div(B, kAfmWarps)) grid_w = ceil_div(B, kAfmWarps);
-    k3<<<grid_w, kAfmWarps * 32, smem_w, st>>>(idx, table, row_offsets, mode == 1 ? da_s : da2, d_att_kernel, d_att_bias, B, F,
+    if (grid_w > ceil_div(B, nw_w)) grid_w = ceil_div(B, nw_w);
+    k3<<<grid_w, nw_w * 32, smem_w, st>>>(idx, table, row_offsets, mode == 1 ? da_s : da2, d_att_kernel, d_att_bias, B, F,
                                                P, H);
   })
   DTB_LAUNCH_OK();

@@ -542,10 +542,17 @@ class AFMFn(torch.autograd.Function):
         g = _f32(g)
         gt = _grad_target(t)
         dk, db, dh = torch.zeros_like(att_kernel), torch.zeros_like(att_bias), torch.zeros_like(projection_h)
-        ws_bytes = N.lib.dtb_afm_workspace_bytes(b, f, d, h)
+        # the per-pair scratch (da, dv: (HT + D) floats per row and pair) is 3 GB at 65 536 rows x 26 fields and grows with
+        # F^2 (an FGCNN block has ~100 fields): row chunks keep it under 4 GB; every output of the call accumulates
+        ws_total = N.lib.dtb_afm_workspace_bytes(b, f, d, h)
+        rows_per = max(1, b) if ws_total <= (4 << 30) else max(1, int(b * (4 << 30) // ws_total))
+        ws_bytes = N.lib.dtb_afm_workspace_bytes(min(rows_per, b), f, d, h)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=w.device)
-        check(N.lib.dtb_afm_bwd(ptr(idx), ptr(w), ptr(offs), ptr(att_kernel), ptr(att_bias), ptr(projection_h), ptr(g), ptr(gt),
-                                ptr(dk), ptr(db), ptr(dh), ptr(ws), ws_bytes, b, f, d, h, act, stream_ptr()), 'afm_bwd')
+        for r0 in range(0, b, rows_per):
+            nb = min(rows_per, b - r0)
+            check(N.lib.dtb_afm_bwd(ptr(idx[r0:r0 + nb]), ptr(w), ptr(offs), ptr(att_kernel), ptr(att_bias), ptr(projection_h),
+                                    ptr(g[r0:r0 + nb]), ptr(gt), ptr(dk), ptr(db), ptr(dh), ptr(ws), ws_bytes, nb, f, d, h, act,
+                                    stream_ptr()), 'afm_bwd')
         _table_grad_done(t)
         return _TableBackwardMixin.finish_tensor_table(t), dk, db, dh, None, None
 
