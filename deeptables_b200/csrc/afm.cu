@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(kAfmRows) afm_bwd_gather_kernel(const int32_t*
   }
 }
 
+#ifdef DTB_FIRST_VERSIONS
+// (first backward, compiled only with -DDTB_FIRST_VERSIONS: tools/build_experiments.sh)
 // thread = (row, field f); grid (F, row-chunk groups).  For each other field o: pair p, v = e_f * e_o, a = act(v Wa + ba),
 // da[h] = ds_p h[h] act'(a[h]), dv[d] = g[d] w_p + sum_h da[h] Wa[d][h], d e_f += dv * e_o.
 // The f < o visit also writes da to da_out [B, P, HT] (read by the attention-kernel gradient) and adds ds_p a to d h.
@@ -396,6 +398,8 @@ __global__ void __launch_bounds__(kAfmRows, 2) afm_bwd_de_kernel(const int32_t* 
   for (int h = threadIdx.x; h < H; h += blockDim.x)
     if (s_dh[h] != 0.f) atomicAdd(d_hv + h, s_dh[h]);
 }
+
+#endif  // DTB_FIRST_VERSIONS
 
 // d Wa[d][h] = sum_{row, p} v_p[d] da_p[h],  d ba[h] = sum da_p[h].  One warp streams rows; lane = (d, group of G = DT*HT/32 units).
 template <int DT, int HT>
@@ -571,12 +575,20 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
   if (grid > ceil_div(B, nw)) grid = ceil_div(B, nw);
   int groups = ceil_div(sm_count() * 6, F);
   if (groups > ceil_div(B, kAfmRows)) groups = ceil_div(B, kAfmRows);
-  // DTB_AFM_BWD=1 selects the first backward (every pair recomputed from both of its fields in afm_bwd_de_kernel)
+  // DTB_AFM_BWD=1 selects the first backward (every pair recomputed from both of its fields in afm_bwd_de_kernel; only in
+  // builds with -DDTB_FIRST_VERSIONS)
   static const int mode = [] { const char* e = getenv("DTB_AFM_BWD"); return e ? atoi(e) : 2; }();
+#ifndef DTB_FIRST_VERSIONS
+  if (mode == 1) {
+    set_error("dtb_afm_bwd: DTB_AFM_BWD=1 needs a library built with -DDTB_FIRST_VERSIONS");
+    return DTB_ERR_UNSUPPORTED;
+  }
+#endif
   float* da2 = reinterpret_cast<float*>(workspace);             // MODE 2 layout: da [B, P, HT] | dv [B, P, D]
   float* dv2 = da2 + (size_t)B * P * HT;
   DTB_AFM_DISPATCH(D, HT, {
     if (mode == 1) {
+#ifdef DTB_FIRST_VERSIONS
       auto k1 = afm_rows_kernel<DT_, HT_, 1>;
       DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k1<<<grid, nw * 32, smem, st>>>(idx, table, row_offsets, att_kernel, att_bias, projection_h, d_pooled, nullptr, w_s,
@@ -584,6 +596,7 @@ int dtb_afm_bwd(const int32_t* idx, const float* table, const int64_t* row_offse
       afm_bwd_de_kernel<DT_, HT_><<<dim3(F, groups), kAfmRows, 0, st>>>(idx, table, row_offsets, att_kernel, att_bias,
                                                                         projection_h, d_pooled, w_s, ds_s, da_s, grad_table,
                                                                         d_projection_h, B, F, P, H, act);
+#endif
     } else {
       auto k1 = afm_rows_kernel<DT_, HT_, 2>;
       DTB_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

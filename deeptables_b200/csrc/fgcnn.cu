@@ -124,6 +124,8 @@ __global__ void __launch_bounds__(kFgThreads) conv_fields_bwd_dx_kernel(const fl
   }
 }
 
+#ifdef DTB_FIRST_VERSIONS
+// (first filter-gradient kernel, compiled only with -DDTB_FIRST_VERSIONS)
 // dK[t,ci,co] += sum_pos X[b, h + t - pad, w, ci] dZ[b,h,w,co];  dbias[co] += sum_pos dZ.  A thread owns up to 4 (ci, co)
 // entries with their kh taps in registers and streams the CTA's positions; lanes run over co (dZ reads coalesced, X reads
 // are broadcasts).  One atomic per filter element per CTA.
@@ -172,6 +174,8 @@ __global__ void __launch_bounds__(kFgThreads) conv_fields_bwd_dw_kernel(const fl
     if (ci[s] == 0 && dbias && accb[s] != 0.f) atomicAdd(dbias + co[s], accb[s]);
   }
 }
+
+#endif  // DTB_FIRST_VERSIONS
 
 // The same gradient with the positions in parallel: a CTA takes tiles of kFgTile consecutive positions, stages their taps
 // xs[p][a] (a = t Cin + ci, zero outside the block) and dzs[p][co] in shared memory, and every thread accumulates its
@@ -361,7 +365,7 @@ int dtb_conv_fields_bwd(const float* X, const float* kernel, const float* Y, con
     })
     DTB_LAUNCH_OK();
   }
-  // DTB_FGCNN_DW=0 selects the first (serial-per-CTA) filter-gradient kernel
+  // DTB_FGCNN_DW=0 selects the first (serial-per-CTA) filter-gradient kernel (builds with -DDTB_FIRST_VERSIONS only)
   static const int tiled = [] { const char* e = getenv("DTB_FGCNN_DW"); return e ? atoi(e) : 1; }();
   if (tiled) {
     const int64_t n_tiles = (n_pos + kFgTile - 1) / kFgTile;
@@ -372,11 +376,16 @@ int dtb_conv_fields_bwd(const float* X, const float* kernel, const float* Y, con
     conv_fields_bwd_dw_tiled_kernel<<<(int)ctas, kFgThreads, smem, st>>>(X, Y, dY, d_kernel, d_bias, n_pos, H, W, Cin, Cout, kh, act,
                                                                          n_tiles);
   } else {
+#ifdef DTB_FIRST_VERSIONS
     int64_t ctas = (int64_t)sm_count() * 4;
     if (ctas > n_pos) ctas = n_pos;
     const int64_t per = (n_pos + ctas - 1) / ctas;
     ctas = (n_pos + per - 1) / per;
     conv_fields_bwd_dw_kernel<<<(int)ctas, kFgThreads, 0, st>>>(X, Y, dY, d_kernel, d_bias, n_pos, H, W, Cin, Cout, kh, act, per);
+#else
+    set_error("dtb_conv_fields_bwd: DTB_FGCNN_DW=0 needs a library built with -DDTB_FIRST_VERSIONS");
+    return DTB_ERR_UNSUPPORTED;
+#endif
   }
   DTB_LAUNCH_OK();
   return DTB_OK;
